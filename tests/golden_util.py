@@ -1,0 +1,44 @@
+"""Helpers shared by the oracle (CPU) and engine (GPU) parity tests."""
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def load_golden(name):
+    z = np.load(os.path.join(HERE, "golden", name + ".npz"), allow_pickle=False)
+    g = {k: z[k] for k in z.files}
+    g["error"] = str(g["error"])
+    g["warned"] = str(g["warned"])
+    for k in ("n_acc", "n_rej", "nfe"):
+        g[k] = int(g[k])
+    return g
+
+
+def tolerances(case):
+    """The parity bar of BASELINE.json.north_star: 1e-6 (fp64) / 1e-3 (fp32) on the solution.
+
+    The oracle-vs-reference check is much tighter (same arithmetic, same op order): 1e-9 / 2e-5 relative
+    to the solution's max-abs (fp32 reductions differ in summation order between torch and numpy)."""
+    if case["dtype"] == "float64":
+        # at rtol <= 1e-10 the step sizes are rounding-noise sensitive (see dt_trace_rtol) and the 4th-order
+        # dense output turns a 1e-4 shift of a step boundary into ~1e-8 at interior output points
+        return dict(oracle=1e-9 if case["rtol"] >= 1e-9 else 1e-7, engine=1e-6)
+    return dict(oracle=2e-4, engine=1e-3)
+
+
+def max_rel_err(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    scale = max(1.0, float(np.max(np.abs(b)))) if b.size else 1.0
+    return float(np.max(np.abs(a - b))) / scale if b.size else 0.0
+
+
+def dt_trace_rtol(case):
+    """Step sizes are an ill-conditioned function of the inputs (the embedded error estimate is a
+    cancelling sum: one ulp in dt moves the next dt by ~1e-8 relative; at rtol <= 1e-10 the estimate is
+    rounding noise), so the dt trace is a soft check; the hard checks are values and accept/reject counts."""
+    if case["dtype"] != "float64":
+        return 5e-2
+    return 1e-5 if case["rtol"] >= 1e-9 else 5e-2
