@@ -1,0 +1,198 @@
+/*
+ * b2ode.h -- C ABI of libb2ode.so: the sm_100a kernels behind tfdiffeq's odeint() Runge-Kutta hot path.
+ *
+ * The reference (titu1994/tfdiffeq) is pure Python on TensorFlow-Eager and has no FFI layer; its seam
+ * is the solver protocol `SOLVERS[method](func, y0, rtol=, atol=, **options).integrate(t)`
+ * (tfdiffeq/odeint.py:77-78).  This library sits directly below that seam: every entry point replaces
+ * the per-step tensor arithmetic of one group of reference functions (cited per function, paths
+ * relative to the reference root).  The user's func(t, y) stays a host-side callable (a PyTorch
+ * nn.Module); its outputs land in device tensors whose pointers are handed to these calls.
+ *
+ * Conventions
+ *  - plain C: pointers, sizes, ints.  No torch / C++ types cross this boundary.
+ *  - every function returns 0 on success, a negative B2ODE_E* code for an invalid argument, or a
+ *    positive cudaError_t; b2ode_last_error() returns a thread-local description.  Nothing throws.
+ *  - all device pointers are CALLER-OWNED (allocated by the host framework's allocator) and must stay
+ *    valid until the stream reaches the call.  The library never allocates device memory and never
+ *    synchronises the host, with the single exception of b2ode_poll_sync().
+ *  - "segments": a state that is a tuple of tensors (tfdiffeq/misc.py:292-305) is a list of up to
+ *    B2ODE_MAXSEG flat arrays; the error norm is computed per segment (tfdiffeq/misc.py:250-264).
+ *  - dtype: 0 = float32, 1 = float64.  Time (t0, t1, dt, output times) is always float64
+ *    (tfdiffeq/solvers.py:30); stage arithmetic is in the state dtype (tfdiffeq/rk_common.py:45-46).
+ *  - vector (16-byte) loads are used for a segment when every pointer of that segment is 16-byte
+ *    aligned; otherwise that segment takes the scalar path.  No alignment is *required*.
+ */
+#ifndef B2ODE_H_
+#define B2ODE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2ODE_ABI_VERSION 1
+#define B2ODE_MAXSEG 8      /* tuple components per state                      */
+#define B2ODE_MAXK 14       /* k-buffers per step (dopri8: 14)                 */
+#define B2ODE_MAXPEERS 8    /* ranks in a shared-step group (one NVSwitch box) */
+
+#define B2ODE_F32 0
+#define B2ODE_F64 1
+
+/* error codes (negative) */
+#define B2ODE_EINVAL (-1)   /* bad argument                               */
+#define B2ODE_ESTATE (-2)   /* call sequence violated (e.g. not bound)    */
+#define B2ODE_ENOMEM (-3)   /* caller-provided workspace too small        */
+
+/* status bits of b2ode_state.status; the host driver re-raises them with the reference's messages */
+#define B2ODE_ST_UNDERFLOW 1u   /* `assert t0 + dt > t0`          tfdiffeq/dopri5.py:98  */
+#define B2ODE_ST_NONFINITE 2u   /* `assert _is_finite(abs(y0))`   tfdiffeq/dopri5.py:100 */
+#define B2ODE_ST_MAXSTEPS 4u    /* `assert n_steps < max_num_steps` tfdiffeq/dopri5.py:85 */
+
+/* controller flavours */
+#define B2ODE_CTRL_REFERENCE 0  /* tfdiffeq/misc.py:267-287 (sqrt, float32-rounded exponent, per-segment msr, max) */
+#define B2ODE_CTRL_TSIT5 1      /* tfdiffeq/tsit5.py:53-62,134-138 (pooled msr, no sqrt, exact exponent)           */
+
+/* Mirror of the device-resident solver state (tfdiffeq/rk_common.py:8-19 `_RungeKuttaState`, minus the
+ * tensors).  b2ode_poll_async() copies it to pinned host memory. 256 bytes. */
+typedef struct b2ode_state {
+    double t0;              /* start of the last accepted step                           */
+    double t1;              /* current time = end of the last accepted step              */
+    double dt;              /* size of the NEXT attempt                                  */
+    double dt_last;         /* size of the attempt just finalized                        */
+    double msr_max;         /* max over segments of the last mean-square error ratio     */
+    double h0;              /* initial-step probe size (misc.py:232-236)                 */
+    double reserved_d[2];
+    uint64_t n_acc;         /* accepted steps                                            */
+    uint64_t n_rej;         /* rejected attempts                                         */
+    uint64_t attempt;       /* attempts finalized so far (sequence number)               */
+    int64_t n_steps_adv;    /* attempts since the last emitted output (max_num_steps)    */
+    int32_t accept;         /* 1 iff the attempt just finalized was accepted             */
+    int32_t done;           /* all output points emitted, or status != 0                 */
+    uint32_t status;        /* B2ODE_ST_* bits                                           */
+    int32_t cursor;         /* next output index to emit                                 */
+    int32_t emit_j0;        /* outputs [emit_j0, emit_j1) fall in the step just accepted */
+    int32_t emit_j1;
+    uint32_t ticket;        /* last-block-done counter of the reduction kernels          */
+    uint32_t reserved_u;
+    uint64_t xseq;          /* cross-GPU exchange sequence number                        */
+    double reserved_t[15];
+} b2ode_state;
+
+/* Description of an adaptive Runge-Kutta solve.  Restates `_ButcherTableau` (tfdiffeq/rk_common.py:5) plus
+ * the solver options of tfdiffeq/dopri5.py:50-68 (same in dopri8.py, bosh3.py, tsit5.py, adaptive_huen.py). */
+typedef struct b2ode_adaptive_desc {
+    int32_t dtype;                      /* B2ODE_F32 / B2ODE_F64                                   */
+    int32_t nseg;                       /* tuple components                                        */
+    int64_t seg_len[B2ODE_MAXSEG];      /* elements per component                                  */
+    int32_t n_k;                        /* number of k buffers s (dopri5: 7); func evals/attempt = s-1 */
+    int32_t fsal;                       /* rk_common.py:54 shortcut holds (y1 = last stage input)  */
+    double alpha[B2ODE_MAXK];           /* s-1 entries                                             */
+    double beta[B2ODE_MAXK][B2ODE_MAXK];/* row i (0-based, i < s-1) has i+1 entries                */
+    double c_sol[B2ODE_MAXK];           /* s entries (used only when !fsal)                        */
+    double c_error[B2ODE_MAXK];         /* s entries                                               */
+    double c_mid[B2ODE_MAXK];           /* s entries; ignored when dense_kind != 0                 */
+    int32_t dense_kind;                 /* 0: quartic fit through y_mid (interp.py:6-67); 1: tsit5.py:33-50 */
+    int32_t controller;                 /* B2ODE_CTRL_*                                            */
+    double rtol[B2ODE_MAXSEG];
+    double atol[B2ODE_MAXSEG];
+    double safety, ifactor, dfactor;    /* already rounded through float32 as the reference does   */
+    double exponent;                    /* 1/order as the reference rounds it (misc.py:281-282)    */
+    int64_t max_num_steps;              /* per advance(), tfdiffeq/dopri5.py:83-88                 */
+    int32_t init_order;                 /* order passed to _select_initial_step (dopri5.py:74)     */
+    int32_t sm_count;                   /* SMs of the device (grid sizing); 0 -> 148               */
+} b2ode_adaptive_desc;
+
+/* Caller-owned device buffers of one solve. */
+typedef struct b2ode_adaptive_buffers {
+    void *state;                        /* sizeof(b2ode_state) bytes, zeroed by b2ode_adaptive_init  */
+    void *workspace;                    /* b2ode_workspace_bytes() bytes (reduction partials)        */
+    size_t workspace_bytes;
+    void *y0[B2ODE_MAXSEG];             /* current accepted state per segment (y0 of the step)       */
+    void *f0[B2ODE_MAXSEG];             /* derivative at y0 (k_1)                                    */
+    void *ystage[B2ODE_MAXSEG];         /* stage input handed to func; holds y1 after the last stage */
+    void *tstage;                       /* n_k state-dtype scalars: time argument of each func call  */
+    const double *t_out;                /* n_out output times (float64, increasing)                  */
+    int32_t n_out;
+    void *out[B2ODE_MAXSEG];            /* per segment: (n_out, seg_len) row-major solution slab     */
+} b2ode_adaptive_buffers;
+
+typedef struct b2ode_solver b2ode_solver;   /* opaque host-side handle */
+
+int b2ode_version(void);
+const char *b2ode_last_error(void);
+size_t b2ode_state_bytes(void);
+size_t b2ode_workspace_bytes(const b2ode_adaptive_desc *desc);
+
+/* ---- adaptive Runge-Kutta (tfdiffeq/solvers.py:27-35, dopri5.py:70-121 and siblings) ---------------- */
+
+int b2ode_adaptive_create(b2ode_solver **out, const b2ode_adaptive_desc *desc);
+void b2ode_adaptive_destroy(b2ode_solver *s);
+int b2ode_adaptive_bind(b2ode_solver *s, const b2ode_adaptive_buffers *buf, void *cuda_stream);
+
+/* Replaces Dopri5Solver.before_integrate's state construction (dopri5.py:78): zero the state, set
+ * t0 = t1 = t_start (= t_out[0]), copy y0 into out[.][0], write the stage-time scalars.  If first_step is not NaN it
+ * becomes dt (dopri5.py:76); otherwise call the two initial-step functions below.  y0/f0 must be filled. */
+int b2ode_adaptive_init(b2ode_solver *s, double t_start, double first_step);
+
+/* `_select_initial_step` (tfdiffeq/misc.py:183-247), first half: d0, d1, h0 and the Euler probe
+ * ystage = y0 + h0*f0, tstage[0] = t0 + h0 (:216-237).  The host then evaluates f1 = func(tstage[0], ystage). */
+int b2ode_initial_step_probe(b2ode_solver *s);
+/* second half (:238-247): d2, h1, dt = min(100*h0, h1); then rewrites the stage times for the first attempt. */
+int b2ode_initial_step_finish(b2ode_solver *s, const void *const *f1);
+
+/* `_runge_kutta_step` stage combine (tfdiffeq/rk_common.py:49-51 via misc.py:118-121):
+ *   ystage = y0 + sum_{j<=i} (dt*beta[i][j]) * k_j     for stage i = 0 .. n_k-2,
+ * with dt read from the device state.  `k_new` = per-segment pointers of k_i, the output of the func call
+ * that followed stage i-1 (ignored for i == 0, where k_0 = f0).  Stage 0 also commits the previous attempt
+ * if it was accepted (y0 <- y1, f0 <- k_last: dopri5.py:113-114) -- the accept decision lives on the device.
+ * i == n_k-1 is the extra solution combine with c_sol for non-FSAL tableaus (rk_common.py:54-56). */
+int b2ode_rk_stage(b2ode_solver *s, int i, const void *const *k_new);
+
+/* Everything after the last func call of an attempt (k_last = k_{s-1} = f1), fused:
+ *   error combine (rk_common.py:60), `_compute_error_ratio` (misc.py:250-264), finite check
+ *   (misc.py:147-150 / dopri5.py:100), accept decision (dopri5.py:108), `_optimal_step_size`
+ *   (misc.py:267-287 or tsit5.py:53-62), state update (dopri5.py:113-120), max_num_steps / dt-underflow
+ *   asserts (dopri5.py:85,98) as status bits, stage times of the next attempt;
+ * then, iff accepted and output times fall inside the step, the dense output for ALL of them:
+ *   `_interp_fit` + `_interp_evaluate` (interp.py:6-67, y_mid from dopri5.py:42) written straight into
+ *   out[.][j] -- the interpolation coefficients never touch HBM. */
+int b2ode_rk_finalize(b2ode_solver *s, const void *const *k_last);
+
+/* Asynchronous copy of the device state to (pinned) host memory on the solver's stream. */
+int b2ode_poll_async(b2ode_solver *s, b2ode_state *host_dst);
+/* Blocking variant (the only call that synchronises): copy + cudaStreamSynchronize. */
+int b2ode_poll_sync(b2ode_solver *s, b2ode_state *host_dst);
+
+/* ---- shared-step groups across GPUs (new; the reference has no distributed code) --------- */
+
+/* Per-rank mailbox for the per-attempt exchange of {sum err^2, max|y0|, max|y1|, non-finite} per segment.
+ * `mailboxes[r]` is the address, in THIS process, of rank r's mailbox (peer-mapped via CUDA IPC for r != rank;
+ * each at least b2ode_mailbox_bytes() bytes, zero-initialised).  After this call b2ode_rk_finalize and the
+ * initial-step functions push their partials to every peer with st.global stores over NVLink and spin on the
+ * arrival flags inside the same kernel (last block), so every rank takes the same accept / dt decision. */
+size_t b2ode_mailbox_bytes(void);
+int b2ode_comm_attach(b2ode_solver *s, int rank, int nranks, void *const *mailboxes);
+
+/* ---- fixed-grid steppers (tfdiffeq/solvers.py:82-115, fixed_grid.py, rk_common.py:73-81) ------------ */
+
+#define B2ODE_OP_EULER 0        /* out = y + dt*a                                  fixed_grid.py:6-7 + solvers.py:95 */
+#define B2ODE_OP_HALF_STEP 1    /* out = y + (a*dt)/2                              fixed_grid.py:17                  */
+#define B2ODE_OP_HEUN_FINAL 2   /* out = y + (dt/2)*(a + b)                        fixed_grid.py:32                  */
+#define B2ODE_OP_RK4_S2 3       /* out = y + (dt*a)/3                              rk_common.py:77                   */
+#define B2ODE_OP_RK4_S3 4       /* out = y + dt*(a/(-3) + b)                       rk_common.py:78                   */
+#define B2ODE_OP_RK4_S4 5       /* out = y + dt*((a - b) + c)                      rk_common.py:79-80                */
+#define B2ODE_OP_RK4_FINAL 6    /* out = y + (((a + 3b) + 3c) + d)*(dt/8)          rk_common.py:81                   */
+#define B2ODE_OP_LERP 7         /* out = y + ((a - y)/s1)*s2   (s1 = t1-t0, s2 = t-t0)  solvers.py:106-115            */
+
+/* One elementwise op over all segments.  dt, s1, s2 are host scalars already rounded to the state dtype
+ * (the fixed-grid loop has no device-side decisions).  Unused operands may be NULL. */
+int b2ode_fixed_op(int dtype, int op, int nseg, const int64_t *seg_len, void *const *out, const void *const *y,
+                   const void *const *a, const void *const *b, const void *const *c, const void *const *d,
+                   double dt, double s1, double s2, int sm_count, void *cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2ODE_H_ */

@@ -1,0 +1,106 @@
+"""ctypes binding of ``libb2ode.so`` (C ABI declared in ``include/b2ode.h``).
+
+The product path has NO fallback: if the shared library is missing or does not export the ABI this
+module raises ``ImportError``/``OSError`` loudly.  Nothing here imports ``oracle/``.
+"""
+import ctypes as C
+import os
+
+MAXSEG = 8
+MAXK = 14
+MAXPEERS = 8
+F32, F64 = 0, 1
+ST_UNDERFLOW, ST_NONFINITE, ST_MAXSTEPS = 1, 2, 4
+CTRL_REFERENCE, CTRL_TSIT5 = 0, 1
+OP_EULER, OP_HALF_STEP, OP_HEUN_FINAL, OP_RK4_S2, OP_RK4_S3, OP_RK4_S4, OP_RK4_FINAL, OP_LERP = range(8)
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.environ.get("B2ODE_LIB", os.path.join(_HERE, "libb2ode.so"))
+
+
+class State(C.Structure):
+    """mirror of ``b2ode_state`` (256 bytes)"""
+    _fields_ = [("t0", C.c_double), ("t1", C.c_double), ("dt", C.c_double), ("dt_last", C.c_double),
+                ("msr_max", C.c_double), ("h0", C.c_double), ("reserved_d", C.c_double * 2),
+                ("n_acc", C.c_uint64), ("n_rej", C.c_uint64), ("attempt", C.c_uint64), ("n_steps_adv", C.c_int64),
+                ("accept", C.c_int32), ("done", C.c_int32), ("status", C.c_uint32), ("cursor", C.c_int32),
+                ("emit_j0", C.c_int32), ("emit_j1", C.c_int32), ("ticket", C.c_uint32), ("reserved_u", C.c_uint32),
+                ("xseq", C.c_uint64), ("reserved_t", C.c_double * 15)]
+
+
+class AdaptiveDesc(C.Structure):
+    """mirror of ``b2ode_adaptive_desc``"""
+    _fields_ = [("dtype", C.c_int32), ("nseg", C.c_int32), ("seg_len", C.c_int64 * MAXSEG),
+                ("n_k", C.c_int32), ("fsal", C.c_int32), ("alpha", C.c_double * MAXK),
+                ("beta", (C.c_double * MAXK) * MAXK), ("c_sol", C.c_double * MAXK), ("c_error", C.c_double * MAXK),
+                ("c_mid", C.c_double * MAXK), ("dense_kind", C.c_int32), ("controller", C.c_int32),
+                ("rtol", C.c_double * MAXSEG), ("atol", C.c_double * MAXSEG),
+                ("safety", C.c_double), ("ifactor", C.c_double), ("dfactor", C.c_double), ("exponent", C.c_double),
+                ("max_num_steps", C.c_int64), ("init_order", C.c_int32), ("sm_count", C.c_int32)]
+
+
+class AdaptiveBuffers(C.Structure):
+    """mirror of ``b2ode_adaptive_buffers``"""
+    _fields_ = [("state", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+                ("y0", C.c_void_p * MAXSEG), ("f0", C.c_void_p * MAXSEG), ("ystage", C.c_void_p * MAXSEG),
+                ("tstage", C.c_void_p), ("t_out", C.c_void_p), ("n_out", C.c_int32),
+                ("out", C.c_void_p * MAXSEG)]
+
+
+assert C.sizeof(State) == 256
+
+PtrArray = C.c_void_p * MAXSEG
+LenArray = C.c_int64 * MAXSEG
+
+_SIGNATURES = {
+    "b2ode_version": (C.c_int, []),
+    "b2ode_last_error": (C.c_char_p, []),
+    "b2ode_state_bytes": (C.c_size_t, []),
+    "b2ode_mailbox_bytes": (C.c_size_t, []),
+    "b2ode_workspace_bytes": (C.c_size_t, [C.POINTER(AdaptiveDesc)]),
+    "b2ode_adaptive_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(AdaptiveDesc)]),
+    "b2ode_adaptive_destroy": (None, [C.c_void_p]),
+    "b2ode_adaptive_bind": (C.c_int, [C.c_void_p, C.POINTER(AdaptiveBuffers), C.c_void_p]),
+    "b2ode_adaptive_init": (C.c_int, [C.c_void_p, C.c_double, C.c_double]),
+    "b2ode_initial_step_probe": (C.c_int, [C.c_void_p]),
+    "b2ode_initial_step_finish": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "b2ode_rk_stage": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
+    "b2ode_rk_finalize": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "b2ode_poll_async": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "b2ode_poll_sync": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "b2ode_comm_attach": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "b2ode_comm_set_global_len": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
+    "b2ode_fixed_op": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_void_p),
+                                 C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                 C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_double, C.c_double, C.c_double,
+                                 C.c_int, C.c_void_p]),
+}
+
+EXPORTS = tuple(sorted(_SIGNATURES))
+
+
+class B2odeError(RuntimeError):
+    pass
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "tfdiffeq_b200: %s not found. Build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or `make -C tfdiffeq_b200/csrc`). There is no CPU fallback." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)      # AttributeError if the ABI is incomplete -- loud on purpose
+        fn.restype = res
+        fn.argtypes = args
+    if lib.b2ode_version() != 1:
+        raise ImportError("libb2ode.so ABI version %d != 1" % lib.b2ode_version())
+    return lib
+
+
+lib = _load()
+
+
+def check(rc):
+    if rc != 0:
+        raise B2odeError("libb2ode call failed (%d): %s" % (rc, lib.b2ode_last_error().decode("utf-8", "replace")))

@@ -1,0 +1,1504 @@
+// b2ode.cu -- sm_100a kernels + C ABI for the Runge-Kutta hot path of tfdiffeq's odeint().
+//
+// Reference citations are relative to the reference repository root (titu1994/tfdiffeq).
+//
+// Design (B200-first):
+//  * every kernel is a streaming, HBM-bound elementwise pass with 16-byte vector loads/stores and a
+//    grid sized from the SM count; there is no GEMM-shaped work here, so no tensor cores.
+//  * the step size, the accept/reject decision, the output cursor and all counters live in a 256-byte
+//    device-resident state (b2ode_state); no kernel argument depends on them, so the host enqueues whole
+//    attempts without reading anything back.
+//  * stage arithmetic uses explicit round-to-nearest mul/add intrinsics (no FMA contraction) in the
+//    reference's operation order, so single-kernel results are bit-identical to the oracle.
+//  * the error-norm reduction is warp-shuffle tree -> per-block partial -> last block (ticket) in a fixed
+//    order: deterministic.  The last block also runs the controller, so "finalize" is one launch; with a
+//    shared-step group attached it additionally exchanges the partials with the peer GPUs over NVLink
+//    (st/ld on peer-mapped mailboxes) inside the same kernel.
+//  * the dense output is evaluated for every output time inside the accepted step from registers; the
+//    quartic's coefficients are never written to HBM.
+
+#include "b2ode.h"
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+#include <type_traits>
+
+static_assert(sizeof(b2ode_state) == 256, "b2ode_state must stay 256 bytes");
+
+// ------------------------------------------------------------------------------------------------
+// host-side error plumbing
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define B2_CUDA(x)                                                                         \
+    do {                                                                                   \
+        cudaError_t e_ = (x);                                                              \
+        if (e_ != cudaSuccess) return fail((int)e_, "%s -> %s", #x, cudaGetErrorString(e_)); \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------------------
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+
+template <typename T>
+struct Ar;
+template <>
+struct Ar<double> {
+    static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+    static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+    static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+    static __device__ __forceinline__ double div(double a, double b) { return __ddiv_rn(a, b); }
+    static __device__ __forceinline__ double abs(double a) { return fabs(a); }
+    static __device__ __forceinline__ double sqrt(double a) { return __dsqrt_rn(a); }
+    static __device__ __forceinline__ double pow(double a, double b) { return ::pow(a, b); }
+};
+template <>
+struct Ar<float> {
+    static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+    static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+    static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+    static __device__ __forceinline__ float div(float a, float b) { return __fdiv_rn(a, b); }
+    static __device__ __forceinline__ float abs(float a) { return fabsf(a); }
+    static __device__ __forceinline__ float sqrt(float a) { return __fsqrt_rn(a); }
+    static __device__ __forceinline__ float pow(float a, float b) { return ::powf(a, b); }
+};
+
+// V elements of T; V*sizeof(T) is 16 (vector path) or sizeof(T) (scalar path)
+template <typename T, int V>
+struct alignas(sizeof(T) * V) Pack {
+    T v[V];
+};
+
+template <typename T, int V>
+__device__ __forceinline__ Pack<T, V> ld_pack(const T *p, long long i) {
+    Pack<T, V> r;
+    if constexpr (V == 1) {
+        r.v[0] = p[i];
+    } else {
+        static_assert(sizeof(T) * V == 16, "vector path is 16 bytes");
+        *reinterpret_cast<int4 *>(&r) = *reinterpret_cast<const int4 *>(p + i * V);
+    }
+    return r;
+}
+
+template <typename T, int V>
+__device__ __forceinline__ void st_pack(T *p, long long i, const Pack<T, V> &r) {
+    if constexpr (V == 1) {
+        p[i] = r.v[0];
+    } else {
+        *reinterpret_cast<int4 *>(p + i * V) = *reinterpret_cast<const int4 *>(&r);
+    }
+}
+
+// geometry of a launch: blocks [blk_begin[s], blk_begin[s+1]) work on segment s
+struct SegGeom {
+    int nseg;
+    int blk_begin[B2ODE_MAXSEG + 1];
+    long long n[B2ODE_MAXSEG];
+    unsigned vec_mask;  // bit s: every pointer of segment s is 16-byte aligned
+};
+
+__device__ __forceinline__ int find_seg(const SegGeom &g, int b) {
+    int s = 0;
+    while (s + 1 < g.nseg && b >= g.blk_begin[s + 1]) ++s;
+    return s;
+}
+
+template <int V>
+using IC = std::integral_constant<int, V>;
+
+// Run body(IC<V>, pack_index) over one segment: 16-byte packs + scalar tail, or all-scalar.
+template <typename T, typename F>
+__device__ __forceinline__ void seg_for_each(long long n, bool vec_ok, int bl, int nb, F &&body) {
+    constexpr int VW = 16 / sizeof(T);
+    const long long stride = (long long)nb * kThreads;
+    const long long first = (long long)bl * kThreads + threadIdx.x;
+    if (vec_ok) {
+        const long long nv = n / VW;
+        for (long long i = first; i < nv; i += stride) body(IC<VW>{}, i);
+        const long long tail = nv * VW + threadIdx.x;
+        if (bl == 0 && tail < n) body(IC<1>{}, tail);
+    } else {
+        for (long long i = first; i < n; i += stride) body(IC<1>{}, i);
+    }
+}
+
+// One record per block, written once, reduced by the last block in block order.  Four columns; the
+// template mask MM says which columns combine with a NaN-propagating max (bit set) instead of a sum.
+struct Partial {
+    double v[4];
+};
+
+__device__ __forceinline__ double nan_max(double a, double b) { return (a != a || b != b) ? (double)NAN : fmax(a, b); }
+__device__ __forceinline__ double nan_min(double a, double b) { return (a != a || b != b) ? (double)NAN : fmin(a, b); }
+
+template <unsigned MM>
+__device__ __forceinline__ Partial combine(const Partial &a, const Partial &b) {
+    Partial r;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) r.v[c] = ((MM >> c) & 1u) ? nan_max(a.v[c], b.v[c]) : a.v[c] + b.v[c];
+    return r;
+}
+
+template <unsigned MM>
+__device__ __forceinline__ Partial identity() {
+    Partial r;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) r.v[c] = 0.0;   // sums start at 0; the maxima are of absolute values (>= 0)
+    return r;
+}
+
+// block-wide reduction, fixed order (xor butterfly inside a warp, then warps 0..7); result valid in thread 0
+template <unsigned MM>
+__device__ __forceinline__ Partial block_reduce(Partial x) {
+    __shared__ Partial sh[kWarps];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        Partial y;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) y.v[c] = __shfl_xor_sync(0xffffffffu, x.v[c], o);
+        x = combine<MM>(x, y);
+    }
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();   // protect sh[] against a previous use
+    if (l == 0) sh[w] = x;
+    __syncthreads();
+    Partial r = identity<MM>();
+    if (threadIdx.x == 0) {
+        r = sh[0];
+        for (int i = 1; i < kWarps; ++i) r = combine<MM>(r, sh[i]);
+    }
+    return r;
+}
+
+// NaN-aware abs-max accumulation: fmax() drops NaN, so NaN is tracked separately and re-injected.
+template <typename T>
+struct AbsMax {
+    T mx = T(0);
+    bool nan = false;
+    __device__ __forceinline__ void see(T v) {
+        T a = Ar<T>::abs(v);
+        nan |= (a != a);
+        mx = (a > mx) ? a : mx;
+    }
+    __device__ __forceinline__ double value() const { return nan ? (double)NAN : (double)mx; }
+};
+
+// returns true in every thread of exactly one block: the last one to arrive
+__device__ __forceinline__ bool last_block_arrives(unsigned *ticket) {
+    __shared__ bool is_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned t = atomicAdd(ticket, 1u);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last) __threadfence();
+    return is_last;
+}
+
+// ------------------------------------------------------------------------------------------------
+// cross-GPU exchange of the per-segment partials (shared-step groups; new)
+// ------------------------------------------------------------------------------------------------
+struct MailSlot {
+    double vals[B2ODE_MAXSEG][4];
+    unsigned long long seq;
+    unsigned long long pad[7];
+};
+struct Mailbox {
+    MailSlot slot[2][B2ODE_MAXPEERS];
+};
+
+struct CommParams {
+    int rank;
+    int nranks;  // 0 or 1: no exchange
+    Mailbox *box[B2ODE_MAXPEERS];
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ double ld_relaxed_sys(const double *p) {
+    double v;
+    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_sys(double *p, double v) {
+    asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+
+// Called by ALL threads of the last block.  tot[s] (shared memory, [nseg]) holds this rank's totals on
+// entry and the group totals (combined in rank order: deterministic and identical on every rank) on exit.
+template <unsigned MM>
+__device__ void group_combine(const CommParams &cp, b2ode_state *st, Partial *tot, int nseg) {
+    if (cp.nranks <= 1) return;
+    __shared__ unsigned long long seq_sh;
+    if (threadIdx.x == 0) seq_sh = st->xseq + 1;
+    __syncthreads();
+    const unsigned long long seq = seq_sh;
+    const int par = (int)(seq & 1ull);
+    if (threadIdx.x < cp.nranks) {
+        // push my totals into peer q's mailbox, slot [par][my rank], then release the sequence number
+        const int q = threadIdx.x;
+        MailSlot *dst = &cp.box[q]->slot[par][cp.rank];
+        for (int s = 0; s < nseg; ++s)
+            for (int c = 0; c < 4; ++c) st_relaxed_sys(&dst->vals[s][c], tot[s].v[c]);
+        __threadfence_system();
+        st_release_sys(&dst->seq, seq);
+        // wait for rank q's totals in MY mailbox
+        const MailSlot *src = &cp.box[cp.rank]->slot[par][q];
+        while (ld_acquire_sys(&src->seq) != seq) __nanosleep(20);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const Mailbox *mine = cp.box[cp.rank];
+        for (int s = 0; s < nseg; ++s) {
+            Partial p = identity<MM>();
+            for (int q = 0; q < cp.nranks; ++q) {
+                const MailSlot *src = &mine->slot[par][q];
+                Partial x;
+                for (int c = 0; c < 4; ++c) x.v[c] = ld_relaxed_sys(&src->vals[s][c]);
+                p = (q == 0) ? x : combine<MM>(p, x);
+            }
+            tot[s] = p;
+        }
+        st->xseq = seq;
+    }
+    __syncthreads();
+}
+
+// Last block: reduce the per-block partials of every segment in block order into tot[] (shared).
+template <unsigned MM>
+__device__ void reduce_partials(const SegGeom &g, const Partial *part, Partial *tot) {
+    for (int s = 0; s < g.nseg; ++s) {
+        Partial acc = identity<MM>();
+        for (int b = g.blk_begin[s] + threadIdx.x; b < g.blk_begin[s + 1]; b += kThreads) acc = combine<MM>(acc, part[b]);
+        Partial r = block_reduce<MM>(acc);
+        if (threadIdx.x == 0) tot[s] = r;
+    }
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------------
+// controller parameters shared by the kernels that end an attempt / the initial step
+// ------------------------------------------------------------------------------------------------
+struct CtrlParams {
+    int n_k;                      // s
+    int controller;               // B2ODE_CTRL_*
+    double alpha[B2ODE_MAXK];     // s-1 entries
+    double rtol[B2ODE_MAXSEG], atol[B2ODE_MAXSEG];
+    double safety, ifactor, dfactor, exponent;
+    long long max_num_steps;
+    int init_order;
+    int n_out;
+    const double *t_out;
+    void *tstage;                 // n_k scalars of the state dtype
+    long long n_global[B2ODE_MAXSEG];   // element count of the segment over the whole shared-step group
+};
+
+// rk_common.py:45-50: t0 and dt are cast to the state dtype, ti = t0 + alpha_i * dt in that dtype
+template <typename T>
+__device__ void write_stage_times(const CtrlParams &c, double t_cur, double dt) {
+    T *ts = reinterpret_cast<T *>(c.tstage);
+    const T t0 = (T)t_cur, d = (T)dt;
+    for (int i = 0; i + 1 < c.n_k; ++i) ts[i] = Ar<T>::add(t0, Ar<T>::mul((T)c.alpha[i], d));
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1: stage combine   ystage = y0 + sum_j (dt*beta_j) * k_j        (rk_common.py:51, misc.py:118-121)
+// ------------------------------------------------------------------------------------------------
+template <int NK>
+struct StageParams {
+    SegGeom g;
+    const b2ode_state *st;
+    const void *y0[B2ODE_MAXSEG];
+    void *out[B2ODE_MAXSEG];
+    const void *k[NK][B2ODE_MAXSEG];
+    double coef[NK];
+};
+
+template <typename T, int NK>
+__global__ void __launch_bounds__(kThreads) k_rk_stage(const __grid_constant__ StageParams<NK> p) {
+    const int s = find_seg(p.g, blockIdx.x);
+    const int bl = blockIdx.x - p.g.blk_begin[s], nb = p.g.blk_begin[s + 1] - p.g.blk_begin[s];
+    const T dt = (T)p.st->dt;
+    T c[NK];
+#pragma unroll
+    for (int j = 0; j < NK; ++j) c[j] = Ar<T>::mul(dt, (T)p.coef[j]);   // (scale * x), misc.py:121
+    const T *y0 = (const T *)p.y0[s];
+    T *out = (T *)p.out[s];
+    const T *k[NK];
+#pragma unroll
+    for (int j = 0; j < NK; ++j) k[j] = (const T *)p.k[j][s];
+    seg_for_each<T>(p.g.n[s], (p.g.vec_mask >> s) & 1u, bl, nb, [&](auto vt, long long i) {
+        constexpr int V = decltype(vt)::value;
+        Pack<T, V> yv = ld_pack<T, V>(y0, i);
+        Pack<T, V> kv[NK];
+#pragma unroll
+        for (int j = 0; j < NK; ++j) kv[j] = ld_pack<T, V>(k[j], i);
+        Pack<T, V> o;
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+            T acc = Ar<T>::mul(c[0], kv[0].v[e]);
+#pragma unroll
+            for (int j = 1; j < NK; ++j) acc = Ar<T>::add(acc, Ar<T>::mul(c[j], kv[j].v[e]));   // add_n, left to right
+            o.v[e] = Ar<T>::add(yv.v[e], acc);
+        }
+        st_pack<T, V>(out, i, o);
+    });
+}
+
+// Stage 0 with the deferred commit of the previous attempt (dopri5.py:113-114: y_next = y1 if accept ...).
+// If the previous attempt was accepted: y0 <- ystage (= y1), f0 <- k_last, all in this pass; ystage is then
+// overwritten in place with the first stage input.  One extra N write per array, only after an accept.
+struct Stage0Params {
+    SegGeom g;
+    const b2ode_state *st;
+    void *y0[B2ODE_MAXSEG];
+    void *f0[B2ODE_MAXSEG];
+    void *ystage[B2ODE_MAXSEG];
+    const void *klast[B2ODE_MAXSEG];   // k_{s-1} of the previous attempt (may be null before the first attempt)
+    double coef;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) k_rk_stage0(const __grid_constant__ Stage0Params p) {
+    const int s = find_seg(p.g, blockIdx.x);
+    const int bl = blockIdx.x - p.g.blk_begin[s], nb = p.g.blk_begin[s + 1] - p.g.blk_begin[s];
+    const T c = Ar<T>::mul((T)p.st->dt, (T)p.coef);
+    const bool commit = p.st->accept != 0 && p.klast[s] != nullptr;
+    T *y0 = (T *)p.y0[s], *f0 = (T *)p.f0[s], *ys = (T *)p.ystage[s];
+    const T *kl = (const T *)p.klast[s];
+    if (commit) {
+        seg_for_each<T>(p.g.n[s], (p.g.vec_mask >> s) & 1u, bl, nb, [&](auto vt, long long i) {
+            constexpr int V = decltype(vt)::value;
+            Pack<T, V> yv = ld_pack<T, V>(ys, i);
+            Pack<T, V> fv = ld_pack<T, V>(kl, i);
+            Pack<T, V> o;
+#pragma unroll
+            for (int e = 0; e < V; ++e) o.v[e] = Ar<T>::add(yv.v[e], Ar<T>::mul(c, fv.v[e]));
+            st_pack<T, V>(y0, i, yv);
+            st_pack<T, V>(f0, i, fv);
+            st_pack<T, V>(ys, i, o);
+        });
+    } else {
+        seg_for_each<T>(p.g.n[s], (p.g.vec_mask >> s) & 1u, bl, nb, [&](auto vt, long long i) {
+            constexpr int V = decltype(vt)::value;
+            Pack<T, V> yv = ld_pack<T, V>(y0, i);
+            Pack<T, V> fv = ld_pack<T, V>(f0, i);
+            Pack<T, V> o;
+#pragma unroll
+            for (int e = 0; e < V; ++e) o.v[e] = Ar<T>::add(yv.v[e], Ar<T>::mul(c, fv.v[e]));
+            st_pack<T, V>(ys, i, o);
+        });
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2+K3: error combine + error-ratio reduction + finite check + controller + state update
+// ------------------------------------------------------------------------------------------------
+template <int NK>
+struct FinalizeParams {
+    SegGeom g;
+    b2ode_state *st;
+    Partial *part;
+    const void *y0[B2ODE_MAXSEG];
+    const void *y1[B2ODE_MAXSEG];
+    const void *k[NK][B2ODE_MAXSEG];
+    double coef[NK];
+    CtrlParams c;
+    CommParams comm;
+};
+
+// misc.py:250-264 + dopri5.py:106-120 + misc.py:267-287 (or tsit5.py:53-62,134-138), one thread.
+template <typename T>
+__device__ void control_step(b2ode_state *st, const CtrlParams &c, const Partial *tot, int nseg) {
+    const double dt = st->dt;
+    const double t_cur = st->t1;
+    unsigned status = st->status;
+    bool accept = true;
+    double m = 0.0;
+    double pooled = 0.0;
+    long long pooled_n = 0;
+    bool bad0 = false;
+    for (int s = 0; s < nseg; ++s) {
+        bad0 |= (tot[s].v[3] > 0.0);
+        // tol = atol + rtol * reduce_max([|y0|, |y1|]): ONE scalar per segment (misc.py:257)
+        const double mm = nan_max(tot[s].v[1], tot[s].v[2]);
+        const T tol = Ar<T>::add((T)c.atol[s], Ar<T>::mul((T)c.rtol[s], (T)mm));
+        const double ssq = tot[s].v[0] / ((double)tol * (double)tol);
+        if (c.controller == B2ODE_CTRL_TSIT5) {
+            pooled += ssq;
+            pooled_n += c.n_global[s];
+        } else {
+            const T msr = (T)(ssq / (double)c.n_global[s]);
+            accept = accept && (msr <= T(1));
+            m = (s == 0) ? (double)msr : nan_max(m, (double)msr);
+        }
+    }
+    if (c.controller == B2ODE_CTRL_TSIT5) {
+        const T msr = (T)(pooled / (double)pooled_n);
+        accept = (msr <= T(1));
+        m = (double)msr;
+    }
+    // _optimal_step_size
+    double dt_next;
+    if (m == 0.0) {
+        dt_next = dt * c.ifactor;
+    } else {
+        const double df = (m < 1.0) ? 1.0 : c.dfactor;
+        const double er = (c.controller == B2ODE_CTRL_TSIT5) ? m : (double)Ar<T>::sqrt((T)m);
+        const double cand = pow(er, c.exponent) / c.safety;
+        const double factor = nan_max(1.0 / c.ifactor, nan_min(cand, 1.0 / df));
+        dt_next = dt / factor;
+    }
+    if (bad0) status |= B2ODE_ST_NONFINITE;   // the reference asserts this before taking the step
+    st->dt_last = dt;
+    st->msr_max = m;
+    if (accept) {
+        st->t0 = t_cur;
+        st->t1 = t_cur + dt;
+        st->n_acc += 1;
+    } else {
+        st->n_rej += 1;
+    }
+    st->accept = accept ? 1 : 0;
+    st->attempt += 1;
+    st->dt = dt_next;
+    // outputs inside the accepted step: every t_out[j] with t_out[j] <= t1 (advance(): `while next_t > t1`)
+    int cur = st->cursor;
+    const int j0 = cur;
+    if (accept && !bad0) {
+        const double t1 = st->t1;
+        while (cur < c.n_out && c.t_out[cur] <= t1) ++cur;
+    }
+    st->cursor = cur;
+    st->emit_j0 = j0;
+    st->emit_j1 = cur;
+    long long nadv = (cur > j0) ? 0 : st->n_steps_adv + 1;
+    st->n_steps_adv = nadv;
+    int done = (cur >= c.n_out) ? 1 : 0;
+    if (!done) {
+        if (nadv >= c.max_num_steps) status |= B2ODE_ST_MAXSTEPS;        // dopri5.py:85
+        if (!(st->t1 + dt_next > st->t1)) status |= B2ODE_ST_UNDERFLOW;  // dopri5.py:98 (NaN dt lands here too)
+    }
+    if (status) done = 1;
+    st->status = status;
+    st->done = done;
+    write_stage_times<T>(c, st->t1, dt_next);
+}
+
+template <typename T, int NK>
+__global__ void __launch_bounds__(kThreads) k_rk_finalize(const __grid_constant__ FinalizeParams<NK> p) {
+    const int s = find_seg(p.g, blockIdx.x);
+    const int bl = blockIdx.x - p.g.blk_begin[s], nb = p.g.blk_begin[s + 1] - p.g.blk_begin[s];
+    const T dt = (T)p.st->dt;
+    T c[NK];
+#pragma unroll
+    for (int j = 0; j < NK; ++j) c[j] = Ar<T>::mul(dt, (T)p.coef[j]);
+    const T *y0 = (const T *)p.y0[s], *y1 = (const T *)p.y1[s];
+    const T *k[NK];
+#pragma unroll
+    for (int j = 0; j < NK; ++j) k[j] = (const T *)p.k[j][s];
+    double sum = 0.0;
+    AbsMax<T> m0, m1;
+    bool bad = false;
+    seg_for_each<T>(p.g.n[s], (p.g.vec_mask >> s) & 1u, bl, nb, [&](auto vt, long long i) {
+        constexpr int V = decltype(vt)::value;
+        Pack<T, V> a = ld_pack<T, V>(y0, i);
+        Pack<T, V> b = ld_pack<T, V>(y1, i);
+        Pack<T, V> kv[NK];
+#pragma unroll
+        for (int j = 0; j < NK; ++j) kv[j] = ld_pack<T, V>(k[j], i);
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+            T err = Ar<T>::mul(c[0], kv[0].v[e]);
+#pragma unroll
+            for (int j = 1; j < NK; ++j) err = Ar<T>::add(err, Ar<T>::mul(c[j], kv[j].v[e]));
+            const double ed = (double)err;
+            sum += ed * ed;
+            m0.see(a.v[e]);
+            m1.see(b.v[e]);
+            bad |= !isfinite((double)a.v[e]);
+        }
+    });
+    // columns: 0 = sum err^2, 1 = max|y0|, 2 = max|y1| (NaN poisons the tolerance like reduce_max), 3 = non-finite y0
+    constexpr unsigned MM = 0xEu;
+    Partial mine;
+    mine.v[0] = sum;
+    mine.v[1] = m0.value();
+    mine.v[2] = m1.value();
+    mine.v[3] = bad ? 1.0 : 0.0;
+    Partial r = block_reduce<MM>(mine);
+    if (threadIdx.x == 0) p.part[blockIdx.x] = r;
+    if (!last_block_arrives(&p.st->ticket)) return;
+    __shared__ Partial tot[B2ODE_MAXSEG];
+    reduce_partials<MM>(p.g, p.part, tot);
+    group_combine<MM>(p.comm, p.st, tot, p.g.nseg);
+    if (threadIdx.x == 0) {
+        control_step<T>(p.st, p.c, tot, p.g.nseg);
+        p.st->ticket = 0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5: dense output for all output times inside the accepted step
+//   y_mid (dopri5.py:42) + _interp_fit (interp.py:22-36) + _interp_evaluate (interp.py:55-67), fused.
+// ------------------------------------------------------------------------------------------------
+template <int NK>
+struct EmitParams {
+    SegGeom g;
+    const b2ode_state *st;
+    const void *y0[B2ODE_MAXSEG];
+    const void *y1[B2ODE_MAXSEG];
+    const void *k[NK][B2ODE_MAXSEG];   // union of {k_j : c_mid_j != 0} and {f0 = k_0, f1 = k_{s-1}}
+    double coef[NK];                   // c_mid of each listed k (0 for f0/f1 if they carry no weight)
+    unsigned mid_mask;                 // which listed k's enter y_mid
+    void *out[B2ODE_MAXSEG];           // (n_out, n_s) row-major
+    const double *t_out;
+};
+
+template <typename T, int NK>
+__global__ void __launch_bounds__(kThreads) k_emit_quartic(const __grid_constant__ EmitParams<NK> p) {
+    const b2ode_state *st = p.st;
+    const int j0 = st->emit_j0, j1 = st->emit_j1;
+    if (!st->accept || j1 <= j0) return;
+    const int s = find_seg(p.g, blockIdx.x);
+    const int bl = blockIdx.x - p.g.blk_begin[s], nb = p.g.blk_begin[s + 1] - p.g.blk_begin[s];
+    const long long n = p.g.n[s];
+    const T dt = (T)st->dt_last;                       // dopri5.py:41 `dt = tf.cast(dt, y0[0].dtype)`
+    const T t0 = (T)st->t0, t1 = (T)st->t1;            // interp.py:55-57
+    const T den = Ar<T>::sub(t1, t0);
+    T c[NK];
+#pragma unroll
+    for (int j = 0; j < NK; ++j) c[j] = Ar<T>::mul(dt, (T)p.coef[j]);
+    const T m2dt = Ar<T>::mul(T(-2), dt), p2dt = Ar<T>::mul(T(2), dt), p5dt = Ar<T>::mul(T(5), dt);
+    const T m3dt = Ar<T>::mul(T(-3), dt), m4dt = Ar<T>::mul(T(-4), dt);
+    const T *y0 = (const T *)p.y0[s], *y1 = (const T *)p.y1[s];
+    T *out = (T *)p.out[s];
+    const T *k[NK];
+#pragma unroll
+    for (int j = 0; j < NK; ++j) k[j] = (const T *)p.k[j][s];
+    // rows of `out` keep the 16-byte alignment of the base only if the row length is a multiple of the pack
+    constexpr int VW = 16 / sizeof(T);
+    const bool vec_ok = ((p.g.vec_mask >> s) & 1u) && (n % VW == 0);
+    seg_for_each<T>(n, vec_ok, bl, nb, [&](auto vt, long long i) {
+        constexpr int V = decltype(vt)::value;
+        Pack<T, V> a0 = ld_pack<T, V>(y0, i);
+        Pack<T, V> a1 = ld_pack<T, V>(y1, i);
+        Pack<T, V> kv[NK];
+#pragma unroll
+        for (int j = 0; j < NK; ++j) kv[j] = ld_pack<T, V>(k[j], i);
+        T ca[V], cb[V], cc[V], cd[V];
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+            // y_mid = y0 + sum (dt*c_mid_j) k_j
+            T acc = T(0);
+            bool first = true;
+#pragma unroll
+            for (int j = 0; j < NK; ++j) {
+                if ((p.mid_mask >> j) & 1u) {
+                    const T term = Ar<T>::mul(c[j], kv[j].v[e]);
+                    acc = first ? term : Ar<T>::add(acc, term);
+                    first = false;
+                }
+            }
+            const T ymid = Ar<T>::add(a0.v[e], acc);
+            const T f0 = kv[0].v[e], f1 = kv[NK - 1].v[e], y0e = a0.v[e], y1e = a1.v[e];   // list is k-ordered: f0 first, f1 last
+            // interp.py:22-36, python sum() left to right
+            T a = Ar<T>::mul(m2dt, f0);
+            a = Ar<T>::add(a, Ar<T>::mul(p2dt, f1));
+            a = Ar<T>::add(a, Ar<T>::mul(T(-8), y0e));
+            a = Ar<T>::add(a, Ar<T>::mul(T(-8), y1e));
+            a = Ar<T>::add(a, Ar<T>::mul(T(16), ymid));
+            T b = Ar<T>::mul(p5dt, f0);
+            b = Ar<T>::add(b, Ar<T>::mul(m3dt, f1));
+            b = Ar<T>::add(b, Ar<T>::mul(T(18), y0e));
+            b = Ar<T>::add(b, Ar<T>::mul(T(14), y1e));
+            b = Ar<T>::add(b, Ar<T>::mul(T(-32), ymid));
+            T cq = Ar<T>::mul(m4dt, f0);
+            cq = Ar<T>::add(cq, Ar<T>::mul(dt, f1));
+            cq = Ar<T>::add(cq, Ar<T>::mul(T(-11), y0e));
+            cq = Ar<T>::add(cq, Ar<T>::mul(T(-5), y1e));
+            cq = Ar<T>::add(cq, Ar<T>::mul(T(16), ymid));
+            ca[e] = a;
+            cb[e] = b;
+            cc[e] = cq;
+            cd[e] = Ar<T>::mul(dt, f0);
+        }
+        for (int j = j0; j < j1; ++j) {
+            const T x = Ar<T>::div(Ar<T>::sub((T)p.t_out[j], t0), den);   // interp.py:60
+            const T x2 = Ar<T>::mul(x, x), x3 = Ar<T>::mul(x2, x), x4 = Ar<T>::mul(x3, x);
+            Pack<T, V> o;
+#pragma unroll
+            for (int e = 0; e < V; ++e) {
+                T r = Ar<T>::mul(ca[e], x4);
+                r = Ar<T>::add(r, Ar<T>::mul(cb[e], x3));
+                r = Ar<T>::add(r, Ar<T>::mul(cc[e], x2));
+                r = Ar<T>::add(r, Ar<T>::mul(cd[e], x));
+                r = Ar<T>::add(r, a0.v[e]);      // e * 1
+                o.v[e] = r;
+            }
+            st_pack<T, V>(out + (long long)j * n, i, o);
+        }
+    });
+}
+
+// tsit5.py:33-50 as written (the "y0" it adds is k[0] = f0, :47): out = f0 + sum_j (dt*b_j(x)) k_j, all 7 k's.
+struct EmitTsitParams {
+    SegGeom g;
+    const b2ode_state *st;
+    const void *k[7][B2ODE_MAXSEG];
+    void *out[B2ODE_MAXSEG];
+    const double *t_out;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) k_emit_tsit5(const __grid_constant__ EmitTsitParams p) {
+    const b2ode_state *st = p.st;
+    const int j0 = st->emit_j0, j1 = st->emit_j1;
+    if (!st->accept || j1 <= j0) return;
+    const int s = find_seg(p.g, blockIdx.x);
+    const int bl = blockIdx.x - p.g.blk_begin[s], nb = p.g.blk_begin[s + 1] - p.g.blk_begin[s];
+    const long long n = p.g.n[s];
+    const double dt = st->t1 - st->t0;
+    const T *k[7];
+#pragma unroll
+    for (int j = 0; j < 7; ++j) k[j] = (const T *)p.k[j][s];
+    T *out = (T *)p.out[s];
+    constexpr int VW = 16 / sizeof(T);
+    const bool vec_ok = ((p.g.vec_mask >> s) & 1u) && (n % VW == 0);
+    seg_for_each<T>(n, vec_ok, bl, nb, [&](auto vt, long long i) {
+        constexpr int V = decltype(vt)::value;
+        Pack<T, V> kv[7];
+#pragma unroll
+        for (int j = 0; j < 7; ++j) kv[j] = ld_pack<T, V>(k[j], i);
+        for (int jj = j0; jj < j1; ++jj) {
+            const double t = __ddiv_rn(__dsub_rn(p.t_out[jj], st->t0), dt);
+            const double t2 = __dmul_rn(t, t);
+            double b[7];
+            // tsit5.py:35-41, python operator order
+            b[0] = __dmul_rn(__dmul_rn(__dmul_rn(-1.0530884977290216, t), __dsub_rn(t, 1.3299890189751412)),
+                             __dadd_rn(__dsub_rn(t2, __dmul_rn(1.4364028541716351, t)), 0.7139816917074209));
+            b[1] = __dmul_rn(__dmul_rn(0.1017, t2), __dadd_rn(__dsub_rn(t2, __dmul_rn(2.1966568338249754, t)), 1.2949852507374631));
+            b[2] = __dmul_rn(__dmul_rn(2.490627285651252793, t2),
+                             __dadd_rn(__dsub_rn(t2, __dmul_rn(2.38535645472061657, t)), 1.57803468208092486));
+            b[3] = __dmul_rn(__dmul_rn(__dmul_rn(-16.54810288924490272, __dsub_rn(t, 1.21712927295533244)),
+                                       __dsub_rn(t, 0.61620406037800089)), t2);
+            b[4] = __dmul_rn(__dmul_rn(__dmul_rn(47.37952196281928122, __dsub_rn(t, 1.203071208372362603)),
+                                       __dsub_rn(t, 0.658047292653547382)), t2);
+            b[5] = __dmul_rn(__dmul_rn(__dmul_rn(-34.87065786149660974, __dsub_rn(t, 1.2)),
+                                       __dsub_rn(t, 0.666666666666666667)), t2);
+            b[6] = __dmul_rn(__dmul_rn(__dmul_rn(2.5, __dsub_rn(t, 1.0)), __dsub_rn(t, 0.6)), t2);
+            T c[7];
+#pragma unroll
+            for (int j = 0; j < 7; ++j) c[j] = (T)__dmul_rn(dt, b[j]);
+            Pack<T, V> o;
+#pragma unroll
+            for (int e = 0; e < V; ++e) {
+                T acc = Ar<T>::mul(c[0], kv[0].v[e]);
+#pragma unroll
+                for (int j = 1; j < 7; ++j) acc = Ar<T>::add(acc, Ar<T>::mul(c[j], kv[j].v[e]));
+                o.v[e] = Ar<T>::add(kv[0].v[e], acc);
+            }
+            st_pack<T, V>(out + (long long)jj * n, i, o);
+        }
+    });
+}
+
+// ------------------------------------------------------------------------------------------------
+// K6: _select_initial_step (misc.py:183-247)
+// ------------------------------------------------------------------------------------------------
+struct InitParams {
+    SegGeom g;
+    b2ode_state *st;
+    Partial *part;
+    const void *y0[B2ODE_MAXSEG];
+    const void *f0[B2ODE_MAXSEG];
+    const void *f1[B2ODE_MAXSEG];
+    void *ystage[B2ODE_MAXSEG];
+    double rtol0, atol0;       // the reference passes rtol[0], atol[0] for every component (dopri5.py:74)
+    CtrlParams c;
+    CommParams comm;
+};
+
+// pass 1: d0 = rms(y0/scale), d1 = rms(f0/scale) per segment; last block derives h0 (misc.py:226-234)
+template <typename T>
+__global__ void __launch_bounds__(kThreads) k_init_norms(const __grid_constant__ InitParams p) {
+    const int s = find_seg(p.g, blockIdx.x);
+    const int bl = blockIdx.x - p.g.blk_begin[s], nb = p.g.blk_begin[s + 1] - p.g.blk_begin[s];
+    const T *y0 = (const T *)p.y0[s], *f0 = (const T *)p.f0[s];
+    const T rtol = (T)p.rtol0, atol = (T)p.atol0;
+    double s0 = 0.0, s1 = 0.0;
+    seg_for_each<T>(p.g.n[s], (p.g.vec_mask >> s) & 1u, bl, nb, [&](auto vt, long long i) {
+        constexpr int V = decltype(vt)::value;
+        Pack<T, V> a = ld_pack<T, V>(y0, i);
+        Pack<T, V> f = ld_pack<T, V>(f0, i);
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+            const T scale = Ar<T>::add(atol, Ar<T>::mul(Ar<T>::abs(a.v[e]), rtol));
+            const double q0 = (double)Ar<T>::div(a.v[e], scale), q1 = (double)Ar<T>::div(f.v[e], scale);
+            s0 += q0 * q0;
+            s1 += q1 * q1;
+        }
+    });
+    Partial mine;
+    mine.v[0] = s0;
+    mine.v[1] = s1;
+    mine.v[2] = mine.v[3] = 0.0;
+    Partial r = block_reduce<0u>(mine);
+    if (threadIdx.x == 0) p.part[blockIdx.x] = r;
+    if (!last_block_arrives(&p.st->ticket)) return;
+    __shared__ Partial tot[B2ODE_MAXSEG];
+    reduce_partials<0u>(p.g, p.part, tot);
+    group_combine<0u>(p.comm, p.st, tot, p.g.nseg);
+    if (threadIdx.x == 0) {
+        b2ode_state *st = p.st;
+        T d0max = T(0), d1max = T(0), ratio = T(0);
+        bool first = true;
+        for (int sg = 0; sg < p.g.nseg; ++sg) {
+            const T rn = Ar<T>::sqrt((T)(double)p.c.n_global[sg]);               // numel ** 0.5, misc.py:173
+            const T d0 = Ar<T>::div((T)sqrt(tot[sg].v[0]), rn), d1 = Ar<T>::div((T)sqrt(tot[sg].v[1]), rn);
+            const T q = Ar<T>::div(d0, d1);
+            if (first) {
+                d0max = d0;
+                d1max = d1;
+                ratio = q;
+                first = false;
+            } else {
+                d0max = (d0 > d0max) ? d0 : d0max;     // python max(): keeps the first unless strictly greater
+                d1max = (d1 > d1max) ? d1 : d1max;
+                ratio = (q > ratio) ? q : ratio;
+            }
+        }
+        T h0;
+        if ((double)d0max < 1e-5 || (double)d1max < 1e-5) h0 = (T)1e-6;           // misc.py:231-232
+        else h0 = Ar<T>::mul((T)0.01, ratio);                                     // misc.py:234
+        st->h0 = (double)h0;
+        st->reserved_d[0] = (double)d1max;
+        T *ts = reinterpret_cast<T *>(p.c.tstage);
+        ts[0] = Ar<T>::add((T)st->t1, h0);                                        // fun(t0 + h0, y1), misc.py:237
+        st->ticket = 0;
+    }
+}
+
+// pass 2: the explicit Euler probe y1 = y0 + h0 * f0 (misc.py:236)
+template <typename T>
+__global__ void __launch_bounds__(kThreads) k_init_probe(const __grid_constant__ InitParams p) {
+    const int s = find_seg(p.g, blockIdx.x);
+    const int bl = blockIdx.x - p.g.blk_begin[s], nb = p.g.blk_begin[s + 1] - p.g.blk_begin[s];
+    const T h0 = (T)p.st->h0;
+    const T *y0 = (const T *)p.y0[s], *f0 = (const T *)p.f0[s];
+    T *ys = (T *)p.ystage[s];
+    seg_for_each<T>(p.g.n[s], (p.g.vec_mask >> s) & 1u, bl, nb, [&](auto vt, long long i) {
+        constexpr int V = decltype(vt)::value;
+        Pack<T, V> a = ld_pack<T, V>(y0, i);
+        Pack<T, V> f = ld_pack<T, V>(f0, i);
+        Pack<T, V> o;
+#pragma unroll
+        for (int e = 0; e < V; ++e) o.v[e] = Ar<T>::add(a.v[e], Ar<T>::mul(h0, f.v[e]));
+        st_pack<T, V>(ys, i, o);
+    });
+}
+
+// pass 3: d2 = rms((f1 - f0)/scale) / h0; h1; dt = min(100 h0, h1) (misc.py:238-247)
+template <typename T>
+__global__ void __launch_bounds__(kThreads) k_init_finish(const __grid_constant__ InitParams p) {
+    const int s = find_seg(p.g, blockIdx.x);
+    const int bl = blockIdx.x - p.g.blk_begin[s], nb = p.g.blk_begin[s + 1] - p.g.blk_begin[s];
+    const T *y0 = (const T *)p.y0[s], *f0 = (const T *)p.f0[s], *f1 = (const T *)p.f1[s];
+    const T rtol = (T)p.rtol0, atol = (T)p.atol0;
+    double s2 = 0.0;
+    seg_for_each<T>(p.g.n[s], (p.g.vec_mask >> s) & 1u, bl, nb, [&](auto vt, long long i) {
+        constexpr int V = decltype(vt)::value;
+        Pack<T, V> a = ld_pack<T, V>(y0, i);
+        Pack<T, V> f = ld_pack<T, V>(f0, i);
+        Pack<T, V> g = ld_pack<T, V>(f1, i);
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+            const T scale = Ar<T>::add(atol, Ar<T>::mul(Ar<T>::abs(a.v[e]), rtol));
+            const double q = (double)Ar<T>::div(Ar<T>::sub(g.v[e], f.v[e]), scale);
+            s2 += q * q;
+        }
+    });
+    Partial mine;
+    mine.v[0] = s2;
+    mine.v[1] = mine.v[2] = mine.v[3] = 0.0;
+    Partial r = block_reduce<0u>(mine);
+    if (threadIdx.x == 0) p.part[blockIdx.x] = r;
+    if (!last_block_arrives(&p.st->ticket)) return;
+    __shared__ Partial tot[B2ODE_MAXSEG];
+    reduce_partials<0u>(p.g, p.part, tot);
+    group_combine<0u>(p.comm, p.st, tot, p.g.nseg);
+    if (threadIdx.x == 0) {
+        b2ode_state *st = p.st;
+        const T h0 = (T)st->h0;
+        const T d1max = (T)st->reserved_d[0];
+        T d2max = T(0);
+        for (int sg = 0; sg < p.g.nseg; ++sg) {
+            const T rn = Ar<T>::sqrt((T)(double)p.c.n_global[sg]);
+            const T d2 = Ar<T>::div(Ar<T>::div((T)sqrt(tot[sg].v[0]), rn), h0);
+            d2max = (sg == 0 || d2 > d2max) ? d2 : d2max;
+        }
+        T h1;
+        if ((double)d1max <= 1e-15 && (double)d2max <= 1e-15) {
+            const T alt = Ar<T>::mul(h0, (T)1e-3);
+            h1 = ((T)1e-6 > alt) ? (T)1e-6 : alt;                                 // misc.py:242-243
+        } else {
+            const T mx = (d2max > d1max) ? d2max : d1max;                         // max(d1 + d2): tuple concat
+            h1 = Ar<T>::pow(Ar<T>::div((T)0.01, mx), (T)(1.0 / (double)(p.c.init_order + 1)));   // misc.py:245
+        }
+        const T h100 = Ar<T>::mul(T(100), h0);
+        const T dt0 = (h1 < h100) ? h1 : h100;                                    // misc.py:247
+        st->dt = (double)dt0;                                                     // cast to float64, dopri5.py:75
+        if (!(st->t1 + st->dt > st->t1) && st->cursor < p.c.n_out) {
+            st->status |= B2ODE_ST_UNDERFLOW;
+            st->done = 1;
+        }
+        write_stage_times<T>(p.c, st->t1, st->dt);
+        st->ticket = 0;
+    }
+}
+
+// state construction (dopri5.py:78); one thread
+struct StateInitParams {
+    b2ode_state *st;
+    double t_start, first_step;
+    int have_first_step;
+    CtrlParams c;
+};
+template <typename T>
+__global__ void k_state_init(const __grid_constant__ StateInitParams p) {
+    b2ode_state z;
+    memset(&z, 0, sizeof(z));
+    z.t0 = p.t_start;
+    z.t1 = p.t_start;
+    z.cursor = 1;                         // out[.][0] = y0 (solvers.py:29)
+    z.emit_j0 = z.emit_j1 = 1;
+    z.done = (p.c.n_out <= 1) ? 1 : 0;
+    if (p.have_first_step) {
+        z.dt = p.first_step;
+        if (!z.done && !(z.t1 + z.dt > z.t1)) {
+            z.status |= B2ODE_ST_UNDERFLOW;
+            z.done = 1;
+        }
+    }
+    *p.st = z;
+    if (p.have_first_step) write_stage_times<T>(p.c, p.t_start, p.first_step);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K7: fixed-grid ops (fixed_grid.py, rk_common.py:73-81, solvers.py:95,106-115)
+// ------------------------------------------------------------------------------------------------
+struct FixedParams {
+    SegGeom g;
+    int op;
+    void *out[B2ODE_MAXSEG];
+    const void *y[B2ODE_MAXSEG];
+    const void *a[B2ODE_MAXSEG];
+    const void *b[B2ODE_MAXSEG];
+    const void *c[B2ODE_MAXSEG];
+    const void *d[B2ODE_MAXSEG];
+    double dt, s1, s2;
+};
+
+template <typename T, int OP>
+__device__ __forceinline__ T fixed_eval(T y, T a, T b, T c, T d, T dt, T s1, T s2) {
+    using A = Ar<T>;
+    if constexpr (OP == B2ODE_OP_EULER) return A::add(y, A::mul(dt, a));
+    if constexpr (OP == B2ODE_OP_HALF_STEP) return A::add(y, A::div(A::mul(a, dt), T(2)));
+    if constexpr (OP == B2ODE_OP_HEUN_FINAL) return A::add(y, A::mul(A::div(dt, T(2)), A::add(a, b)));
+    if constexpr (OP == B2ODE_OP_RK4_S2) return A::add(y, A::div(A::mul(dt, a), T(3)));
+    if constexpr (OP == B2ODE_OP_RK4_S3) return A::add(y, A::mul(dt, A::add(A::div(a, T(-3)), b)));
+    if constexpr (OP == B2ODE_OP_RK4_S4) return A::add(y, A::mul(dt, A::add(A::sub(a, b), c)));
+    if constexpr (OP == B2ODE_OP_RK4_FINAL)
+        return A::add(y, A::mul(A::add(A::add(A::add(a, A::mul(T(3), b)), A::mul(T(3), c)), d), A::div(dt, T(8))));
+    if constexpr (OP == B2ODE_OP_LERP) return A::add(y, A::mul(A::div(A::sub(a, y), s1), s2));
+    return y;
+}
+
+template <int OP>
+struct FixedArity {
+    static constexpr int n = (OP == B2ODE_OP_HEUN_FINAL || OP == B2ODE_OP_RK4_S3)  ? 2
+                             : (OP == B2ODE_OP_RK4_S4)                             ? 3
+                             : (OP == B2ODE_OP_RK4_FINAL)                          ? 4
+                                                                                   : 1;
+};
+
+template <typename T, int OP>
+__global__ void __launch_bounds__(kThreads) k_fixed(const __grid_constant__ FixedParams p) {
+    const int s = find_seg(p.g, blockIdx.x);
+    const int bl = blockIdx.x - p.g.blk_begin[s], nb = p.g.blk_begin[s + 1] - p.g.blk_begin[s];
+    constexpr int NA = FixedArity<OP>::n;
+    const T dt = (T)p.dt, s1 = (T)p.s1, s2 = (T)p.s2;
+    const T *y = (const T *)p.y[s];
+    const T *in[4] = {(const T *)p.a[s], (const T *)p.b[s], (const T *)p.c[s], (const T *)p.d[s]};
+    T *out = (T *)p.out[s];
+    seg_for_each<T>(p.g.n[s], (p.g.vec_mask >> s) & 1u, bl, nb, [&](auto vt, long long i) {
+        constexpr int V = decltype(vt)::value;
+        Pack<T, V> yv = ld_pack<T, V>(y, i);
+        Pack<T, V> iv[4];
+#pragma unroll
+        for (int j = 0; j < NA; ++j) iv[j] = ld_pack<T, V>(in[j], i);
+        Pack<T, V> o;
+#pragma unroll
+        for (int e = 0; e < V; ++e)
+            o.v[e] = fixed_eval<T, OP>(yv.v[e], iv[0].v[e], NA > 1 ? iv[1].v[e] : T(0), NA > 2 ? iv[2].v[e] : T(0),
+                                       NA > 3 ? iv[3].v[e] : T(0), dt, s1, s2);
+        st_pack<T, V>(out, i, o);
+    });
+}
+
+// ================================================================================================
+// host side
+// ================================================================================================
+struct b2ode_solver {
+    b2ode_adaptive_desc d;
+    b2ode_adaptive_buffers b;
+    bool bound;
+    cudaStream_t stream;
+    SegGeom geom;          // blocks per segment; vec_mask filled per launch
+    int grid;
+    CtrlParams ctrl;
+    CommParams comm;
+    const void *k[B2ODE_MAXK][B2ODE_MAXSEG];   // k pointers of the current attempt (k[0] = f0)
+    const void *klast_prev[B2ODE_MAXSEG];      // k_{s-1} of the previous attempt
+    bool have_prev;
+    // compacted (zero-skipping) coefficient lists
+    int st_nk[B2ODE_MAXK];
+    int st_idx[B2ODE_MAXK][B2ODE_MAXK];
+    double st_coef[B2ODE_MAXK][B2ODE_MAXK];
+    int err_nk;
+    int err_idx[B2ODE_MAXK];
+    double err_coef[B2ODE_MAXK];
+    int mid_nk;
+    int mid_idx[B2ODE_MAXK];
+    double mid_coef[B2ODE_MAXK];
+    unsigned mid_mask;
+    int mid_if0, mid_if1;
+};
+
+static bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+static void build_geom(SegGeom *g, int dtype, int nseg, const int64_t *seg_len, int sm_count) {
+    const int vw = dtype == B2ODE_F64 ? 2 : 4;
+    const int sms = sm_count > 0 ? sm_count : 148;
+    const long long cap = (long long)sms * 8;     // 8 x 256 threads = 2048 resident threads per SM
+    long long need[B2ODE_MAXSEG], tot = 0;
+    for (int s = 0; s < nseg; ++s) {
+        long long nv = (seg_len[s] + vw - 1) / vw;
+        need[s] = (nv + kThreads - 1) / kThreads;
+        if (need[s] < 1) need[s] = 1;
+        tot += need[s];
+    }
+    g->nseg = nseg;
+    g->blk_begin[0] = 0;
+    for (int s = 0; s < nseg; ++s) {
+        long long nb = need[s];
+        if (tot > cap) {
+            nb = (long long)((double)cap * (double)need[s] / (double)tot);
+            if (nb < 1) nb = 1;
+        }
+        g->blk_begin[s + 1] = g->blk_begin[s] + (int)nb;
+        g->n[s] = seg_len[s];
+    }
+    g->vec_mask = 0;
+}
+
+extern "C" int b2ode_version(void) { return B2ODE_ABI_VERSION; }
+extern "C" const char *b2ode_last_error(void) { return g_err; }
+extern "C" size_t b2ode_state_bytes(void) { return sizeof(b2ode_state); }
+extern "C" size_t b2ode_mailbox_bytes(void) { return sizeof(Mailbox); }
+
+extern "C" size_t b2ode_workspace_bytes(const b2ode_adaptive_desc *desc) {
+    if (!desc || desc->nseg < 1 || desc->nseg > B2ODE_MAXSEG) return 0;
+    SegGeom g;
+    build_geom(&g, desc->dtype, desc->nseg, desc->seg_len, desc->sm_count);
+    return (size_t)g.blk_begin[g.nseg] * sizeof(Partial);
+}
+
+extern "C" int b2ode_adaptive_create(b2ode_solver **out, const b2ode_adaptive_desc *desc) {
+    if (!out || !desc) return fail(B2ODE_EINVAL, "null argument");
+    if (desc->dtype != B2ODE_F32 && desc->dtype != B2ODE_F64) return fail(B2ODE_EINVAL, "dtype must be 0 or 1");
+    if (desc->nseg < 1 || desc->nseg > B2ODE_MAXSEG) return fail(B2ODE_EINVAL, "nseg must be in [1, %d]", B2ODE_MAXSEG);
+    if (desc->n_k < 2 || desc->n_k > B2ODE_MAXK) return fail(B2ODE_EINVAL, "n_k must be in [2, %d]", B2ODE_MAXK);
+    for (int s = 0; s < desc->nseg; ++s)
+        if (desc->seg_len[s] < 0) return fail(B2ODE_EINVAL, "negative segment length");
+    if (desc->dense_kind == 1 && desc->n_k != 7) return fail(B2ODE_EINVAL, "tsit5 dense output needs n_k == 7");
+    b2ode_solver *s = new (std::nothrow) b2ode_solver();
+    if (!s) return fail(B2ODE_ENOMEM, "host allocation failed");
+    memset(s, 0, sizeof(*s));
+    s->d = *desc;
+    build_geom(&s->geom, desc->dtype, desc->nseg, desc->seg_len, desc->sm_count);
+    s->grid = s->geom.blk_begin[s->geom.nseg];
+    const int nk = desc->n_k;
+    // stage rows 0..nk-2 from beta; row nk-1 = c_sol (only launched when !fsal)
+    for (int i = 0; i < nk; ++i) {
+        int cnt = 0;
+        const int len = (i < nk - 1) ? i + 1 : nk;
+        for (int j = 0; j < len; ++j) {
+            const double v = (i < nk - 1) ? desc->beta[i][j] : desc->c_sol[j];
+            if (v != 0.0) {
+                s->st_idx[i][cnt] = j;
+                s->st_coef[i][cnt] = v;
+                ++cnt;
+            }
+        }
+        if (cnt == 0) {   // keep at least one (zero-weight) term so the kernel has something to read
+            s->st_idx[i][0] = 0;
+            s->st_coef[i][0] = 0.0;
+            cnt = 1;
+        }
+        s->st_nk[i] = cnt;
+    }
+    s->err_nk = 0;
+    for (int j = 0; j < nk; ++j)
+        if (desc->c_error[j] != 0.0) {
+            s->err_idx[s->err_nk] = j;
+            s->err_coef[s->err_nk] = desc->c_error[j];
+            ++s->err_nk;
+        }
+    if (s->err_nk == 0) {
+        s->err_idx[0] = 0;
+        s->err_coef[0] = 0.0;
+        s->err_nk = 1;
+    }
+    // dense output list: nonzero c_mid, plus f0 and f1
+    s->mid_nk = 0;
+    s->mid_mask = 0;
+    s->mid_if0 = s->mid_if1 = -1;
+    if (desc->dense_kind == 0) {
+        for (int j = 0; j < nk; ++j) {
+            const bool w = desc->c_mid[j] != 0.0;
+            if (w || j == 0 || j == nk - 1) {
+                if (w) s->mid_mask |= 1u << s->mid_nk;
+                if (j == 0) s->mid_if0 = s->mid_nk;
+                if (j == nk - 1) s->mid_if1 = s->mid_nk;
+                s->mid_idx[s->mid_nk] = j;
+                s->mid_coef[s->mid_nk] = desc->c_mid[j];
+                ++s->mid_nk;
+            }
+        }
+    }
+    CtrlParams &c = s->ctrl;
+    c.n_k = nk;
+    c.controller = desc->controller;
+    for (int i = 0; i < B2ODE_MAXK; ++i) c.alpha[i] = desc->alpha[i];
+    for (int i = 0; i < B2ODE_MAXSEG; ++i) {
+        c.rtol[i] = desc->rtol[i];
+        c.atol[i] = desc->atol[i];
+        c.n_global[i] = desc->seg_len[i];
+    }
+    c.safety = desc->safety;
+    c.ifactor = desc->ifactor;
+    c.dfactor = desc->dfactor;
+    c.exponent = desc->exponent;
+    c.max_num_steps = desc->max_num_steps;
+    c.init_order = desc->init_order;
+    s->comm.nranks = 0;
+    *out = s;
+    return 0;
+}
+
+extern "C" void b2ode_adaptive_destroy(b2ode_solver *s) { delete s; }
+
+extern "C" int b2ode_adaptive_bind(b2ode_solver *s, const b2ode_adaptive_buffers *buf, void *cuda_stream) {
+    if (!s || !buf) return fail(B2ODE_EINVAL, "null argument");
+    if (!buf->state || !buf->workspace || !buf->tstage) return fail(B2ODE_EINVAL, "state/workspace/tstage is null");
+    if (buf->workspace_bytes < (size_t)s->grid * sizeof(Partial))
+        return fail(B2ODE_ENOMEM, "workspace too small: %zu < %zu", buf->workspace_bytes, (size_t)s->grid * sizeof(Partial));
+    if (buf->n_out < 1 || (!buf->t_out && buf->n_out > 0)) return fail(B2ODE_EINVAL, "t_out / n_out invalid");
+    for (int i = 0; i < s->d.nseg; ++i) {
+        if (s->d.seg_len[i] > 0 && (!buf->y0[i] || !buf->f0[i] || !buf->ystage[i] || !buf->out[i]))
+            return fail(B2ODE_EINVAL, "segment %d has a null buffer", i);
+    }
+    if (!aligned16(buf->state)) return fail(B2ODE_EINVAL, "state must be 16-byte aligned");
+    s->b = *buf;
+    s->stream = (cudaStream_t)cuda_stream;
+    s->ctrl.n_out = buf->n_out;
+    s->ctrl.t_out = buf->t_out;
+    s->ctrl.tstage = buf->tstage;
+    for (int i = 0; i < s->d.nseg; ++i) s->k[0][i] = buf->f0[i];
+    s->have_prev = false;
+    s->bound = true;
+    return 0;
+}
+
+extern "C" int b2ode_comm_attach(b2ode_solver *s, int rank, int nranks, void *const *mailboxes) {
+    if (!s) return fail(B2ODE_EINVAL, "null solver");
+    if (nranks < 1 || nranks > B2ODE_MAXPEERS || rank < 0 || rank >= nranks) return fail(B2ODE_EINVAL, "bad rank/nranks");
+    if (nranks > 1 && !mailboxes) return fail(B2ODE_EINVAL, "mailboxes is null");
+    s->comm.rank = rank;
+    s->comm.nranks = nranks;
+    for (int r = 0; r < nranks; ++r) {
+        if (nranks > 1 && !mailboxes[r]) return fail(B2ODE_EINVAL, "mailbox %d is null", r);
+        s->comm.box[r] = nranks > 1 ? (Mailbox *)mailboxes[r] : nullptr;
+    }
+    return 0;
+}
+
+// the group-wide element counts (used for the mean in the error ratio) -- set by the host driver after attach
+extern "C" int b2ode_comm_set_global_len(b2ode_solver *s, const int64_t *global_len) {
+    if (!s || !global_len) return fail(B2ODE_EINVAL, "null argument");
+    for (int i = 0; i < s->d.nseg; ++i) {
+        if (global_len[i] < s->d.seg_len[i]) return fail(B2ODE_EINVAL, "global length smaller than the local one");
+        s->ctrl.n_global[i] = global_len[i];
+    }
+    return 0;
+}
+
+#define B2_REQUIRE_BOUND(s)                                              \
+    do {                                                                 \
+        if (!(s)) return fail(B2ODE_EINVAL, "null solver");              \
+        if (!(s)->bound) return fail(B2ODE_ESTATE, "solver is not bound"); \
+    } while (0)
+
+template <typename K, typename P>
+static int launch(K kernel, int grid, cudaStream_t st, const P &p) {
+    if (grid <= 0) return 0;
+    kernel<<<grid, kThreads, 0, st>>>(p);
+    B2_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int b2ode_adaptive_init(b2ode_solver *s, double t_start, double first_step) {
+    B2_REQUIRE_BOUND(s);
+    StateInitParams p;
+    p.st = (b2ode_state *)s->b.state;
+    p.t_start = t_start;
+    p.first_step = first_step;
+    p.have_first_step = (first_step == first_step) ? 1 : 0;
+    p.c = s->ctrl;
+    if (s->d.dtype == B2ODE_F64)
+        k_state_init<double><<<1, 1, 0, s->stream>>>(p);
+    else
+        k_state_init<float><<<1, 1, 0, s->stream>>>(p);
+    B2_CUDA(cudaGetLastError());
+    const size_t esz = s->d.dtype == B2ODE_F64 ? 8 : 4;
+    for (int i = 0; i < s->d.nseg; ++i)
+        if (s->d.seg_len[i] > 0)
+            B2_CUDA(cudaMemcpyAsync(s->b.out[i], s->b.y0[i], (size_t)s->d.seg_len[i] * esz, cudaMemcpyDeviceToDevice, s->stream));
+    s->have_prev = false;
+    for (int i = 0; i < s->d.nseg; ++i) s->k[0][i] = s->b.f0[i];
+    return 0;
+}
+
+static unsigned vec_mask_of(const b2ode_solver *s, const void *const *const *lists, int nlists) {
+    unsigned m = 0;
+    for (int sg = 0; sg < s->d.nseg; ++sg) {
+        bool ok = true;
+        for (int l = 0; l < nlists && ok; ++l)
+            if (lists[l] && lists[l][sg] && !aligned16(lists[l][sg])) ok = false;
+        if (ok) m |= 1u << sg;
+    }
+    return m;
+}
+
+static void fill_init_params(b2ode_solver *s, InitParams *p, const void *const *f1) {
+    p->g = s->geom;
+    p->st = (b2ode_state *)s->b.state;
+    p->part = (Partial *)s->b.workspace;
+    for (int i = 0; i < B2ODE_MAXSEG; ++i) {
+        p->y0[i] = s->b.y0[i];
+        p->f0[i] = s->b.f0[i];
+        p->f1[i] = f1 ? f1[i] : nullptr;
+        p->ystage[i] = s->b.ystage[i];
+    }
+    p->rtol0 = s->d.rtol[0];
+    p->atol0 = s->d.atol[0];
+    p->c = s->ctrl;
+    p->comm = s->comm;
+    const void *const *lists[4] = {(const void *const *)s->b.y0, (const void *const *)s->b.f0,
+                                   (const void *const *)s->b.ystage, f1};
+    p->g.vec_mask = vec_mask_of(s, lists, 4);
+}
+
+extern "C" int b2ode_initial_step_probe(b2ode_solver *s) {
+    B2_REQUIRE_BOUND(s);
+    InitParams p;
+    fill_init_params(s, &p, nullptr);
+    int rc;
+    if (s->d.dtype == B2ODE_F64) {
+        if ((rc = launch(k_init_norms<double>, s->grid, s->stream, p))) return rc;
+        return launch(k_init_probe<double>, s->grid, s->stream, p);
+    }
+    if ((rc = launch(k_init_norms<float>, s->grid, s->stream, p))) return rc;
+    return launch(k_init_probe<float>, s->grid, s->stream, p);
+}
+
+extern "C" int b2ode_initial_step_finish(b2ode_solver *s, const void *const *f1) {
+    B2_REQUIRE_BOUND(s);
+    if (!f1) return fail(B2ODE_EINVAL, "f1 is null");
+    InitParams p;
+    fill_init_params(s, &p, f1);
+    if (s->d.dtype == B2ODE_F64) return launch(k_init_finish<double>, s->grid, s->stream, p);
+    return launch(k_init_finish<float>, s->grid, s->stream, p);
+}
+
+template <typename T, int NK>
+static int launch_stage(b2ode_solver *s, int row) {
+    StageParams<NK> p;
+    p.g = s->geom;
+    p.st = (const b2ode_state *)s->b.state;
+    const void *const *lists[NK + 2];
+    for (int sg = 0; sg < B2ODE_MAXSEG; ++sg) {
+        p.y0[sg] = s->b.y0[sg];
+        p.out[sg] = s->b.ystage[sg];
+    }
+    lists[0] = (const void *const *)s->b.y0;
+    lists[1] = (const void *const *)s->b.ystage;
+    for (int j = 0; j < NK; ++j) {
+        const int kj = s->st_idx[row][j];
+        p.coef[j] = s->st_coef[row][j];
+        for (int sg = 0; sg < B2ODE_MAXSEG; ++sg) p.k[j][sg] = s->k[kj][sg];
+        lists[j + 2] = s->k[kj];
+    }
+    p.g.vec_mask = vec_mask_of(s, lists, NK + 2);
+    return launch(k_rk_stage<T, NK>, s->grid, s->stream, p);
+}
+
+template <typename T>
+static int dispatch_stage(b2ode_solver *s, int row) {
+    switch (s->st_nk[row]) {
+#define B2_CASE(N) \
+    case N:        \
+        return launch_stage<T, N>(s, row);
+        B2_CASE(1) B2_CASE(2) B2_CASE(3) B2_CASE(4) B2_CASE(5) B2_CASE(6) B2_CASE(7) B2_CASE(8) B2_CASE(9) B2_CASE(10)
+        B2_CASE(11) B2_CASE(12) B2_CASE(13) B2_CASE(14)
+#undef B2_CASE
+    }
+    return fail(B2ODE_EINVAL, "unsupported number of stage terms %d", s->st_nk[row]);
+}
+
+extern "C" int b2ode_rk_stage(b2ode_solver *s, int i, const void *const *k_new) {
+    B2_REQUIRE_BOUND(s);
+    const int nk = s->d.n_k;
+    if (i < 0 || i > nk - 1) return fail(B2ODE_EINVAL, "stage index %d out of range", i);
+    if (i == nk - 1 && s->d.fsal) return fail(B2ODE_EINVAL, "solution combine requested for an FSAL tableau");
+    if (i > 0) {
+        if (!k_new) return fail(B2ODE_EINVAL, "k_new is null for stage %d", i);
+        for (int sg = 0; sg < s->d.nseg; ++sg) {
+            if (!k_new[sg] && s->d.seg_len[sg] > 0) return fail(B2ODE_EINVAL, "k_new[%d] is null", sg);
+            s->k[i][sg] = k_new[sg];
+        }
+    }
+    if (i == 0) {
+        Stage0Params p;
+        p.g = s->geom;
+        p.st = (const b2ode_state *)s->b.state;
+        for (int sg = 0; sg < B2ODE_MAXSEG; ++sg) {
+            p.y0[sg] = s->b.y0[sg];
+            p.f0[sg] = s->b.f0[sg];
+            p.ystage[sg] = s->b.ystage[sg];
+            p.klast[sg] = s->have_prev ? s->klast_prev[sg] : nullptr;
+        }
+        p.coef = s->d.beta[0][0];
+        const void *const *lists[4] = {(const void *const *)s->b.y0, (const void *const *)s->b.f0,
+                                       (const void *const *)s->b.ystage, s->have_prev ? s->klast_prev : nullptr};
+        p.g.vec_mask = vec_mask_of(s, lists, 4);
+        if (s->d.dtype == B2ODE_F64) return launch(k_rk_stage0<double>, s->grid, s->stream, p);
+        return launch(k_rk_stage0<float>, s->grid, s->stream, p);
+    }
+    if (s->d.dtype == B2ODE_F64) return dispatch_stage<double>(s, i);
+    return dispatch_stage<float>(s, i);
+}
+
+template <typename T, int NK>
+static int launch_finalize(b2ode_solver *s) {
+    FinalizeParams<NK> p;
+    p.g = s->geom;
+    p.st = (b2ode_state *)s->b.state;
+    p.part = (Partial *)s->b.workspace;
+    const void *const *lists[NK + 2];
+    for (int sg = 0; sg < B2ODE_MAXSEG; ++sg) {
+        p.y0[sg] = s->b.y0[sg];
+        p.y1[sg] = s->b.ystage[sg];
+    }
+    lists[0] = (const void *const *)s->b.y0;
+    lists[1] = (const void *const *)s->b.ystage;
+    for (int j = 0; j < NK; ++j) {
+        const int kj = s->err_idx[j];
+        p.coef[j] = s->err_coef[j];
+        for (int sg = 0; sg < B2ODE_MAXSEG; ++sg) p.k[j][sg] = s->k[kj][sg];
+        lists[j + 2] = s->k[kj];
+    }
+    p.c = s->ctrl;
+    p.comm = s->comm;
+    p.g.vec_mask = vec_mask_of(s, lists, NK + 2);
+    return launch(k_rk_finalize<T, NK>, s->grid, s->stream, p);
+}
+
+template <typename T, int NK>
+static int launch_emit(b2ode_solver *s) {
+    EmitParams<NK> p;
+    p.g = s->geom;
+    p.st = (const b2ode_state *)s->b.state;
+    const void *const *lists[NK + 3];
+    for (int sg = 0; sg < B2ODE_MAXSEG; ++sg) {
+        p.y0[sg] = s->b.y0[sg];
+        p.y1[sg] = s->b.ystage[sg];
+        p.out[sg] = s->b.out[sg];
+    }
+    lists[0] = (const void *const *)s->b.y0;
+    lists[1] = (const void *const *)s->b.ystage;
+    lists[2] = (const void *const *)s->b.out;
+    for (int j = 0; j < NK; ++j) {
+        const int kj = s->mid_idx[j];
+        p.coef[j] = s->mid_coef[j];
+        for (int sg = 0; sg < B2ODE_MAXSEG; ++sg) p.k[j][sg] = s->k[kj][sg];
+        lists[j + 3] = s->k[kj];
+    }
+    p.mid_mask = s->mid_mask;
+    p.t_out = s->b.t_out;
+    p.g.vec_mask = vec_mask_of(s, lists, NK + 3);
+    return launch(k_emit_quartic<T, NK>, s->grid, s->stream, p);
+}
+
+template <typename T>
+static int launch_emit_tsit5(b2ode_solver *s) {
+    EmitTsitParams p;
+    p.g = s->geom;
+    p.st = (const b2ode_state *)s->b.state;
+    const void *const *lists[8];
+    for (int sg = 0; sg < B2ODE_MAXSEG; ++sg) p.out[sg] = s->b.out[sg];
+    lists[0] = (const void *const *)s->b.out;
+    for (int j = 0; j < 7; ++j) {
+        for (int sg = 0; sg < B2ODE_MAXSEG; ++sg) p.k[j][sg] = s->k[j][sg];
+        lists[j + 1] = s->k[j];
+    }
+    p.t_out = s->b.t_out;
+    p.g.vec_mask = vec_mask_of(s, lists, 8);
+    return launch(k_emit_tsit5<T>, s->grid, s->stream, p);
+}
+
+template <typename T>
+static int dispatch_finalize(b2ode_solver *s) {
+    int rc = B2ODE_EINVAL;
+    switch (s->err_nk) {
+#define B2_CASE(N)                      \
+    case N:                             \
+        rc = launch_finalize<T, N>(s);  \
+        break;
+        B2_CASE(1) B2_CASE(2) B2_CASE(3) B2_CASE(4) B2_CASE(5) B2_CASE(6) B2_CASE(7) B2_CASE(8) B2_CASE(9) B2_CASE(10)
+        B2_CASE(11) B2_CASE(12) B2_CASE(13) B2_CASE(14)
+#undef B2_CASE
+    }
+    if (rc) return rc;
+    if (s->d.dense_kind == 1) return launch_emit_tsit5<T>(s);
+    switch (s->mid_nk) {
+#define B2_CASE(N) \
+    case N:        \
+        return launch_emit<T, N>(s);
+        B2_CASE(1) B2_CASE(2) B2_CASE(3) B2_CASE(4) B2_CASE(5) B2_CASE(6) B2_CASE(7) B2_CASE(8) B2_CASE(9) B2_CASE(10)
+        B2_CASE(11) B2_CASE(12) B2_CASE(13) B2_CASE(14)
+#undef B2_CASE
+    }
+    return fail(B2ODE_EINVAL, "unsupported dense-output list length %d", s->mid_nk);
+}
+
+extern "C" int b2ode_rk_finalize(b2ode_solver *s, const void *const *k_last) {
+    B2_REQUIRE_BOUND(s);
+    if (!k_last) return fail(B2ODE_EINVAL, "k_last is null");
+    const int nk = s->d.n_k;
+    for (int sg = 0; sg < s->d.nseg; ++sg) {
+        if (!k_last[sg] && s->d.seg_len[sg] > 0) return fail(B2ODE_EINVAL, "k_last[%d] is null", sg);
+        s->k[nk - 1][sg] = k_last[sg];
+    }
+    int rc = (s->d.dtype == B2ODE_F64) ? dispatch_finalize<double>(s) : dispatch_finalize<float>(s);
+    if (rc) return rc;
+    for (int sg = 0; sg < s->d.nseg; ++sg) s->klast_prev[sg] = k_last[sg];
+    s->have_prev = true;
+    return 0;
+}
+
+extern "C" int b2ode_poll_async(b2ode_solver *s, b2ode_state *host_dst) {
+    B2_REQUIRE_BOUND(s);
+    if (!host_dst) return fail(B2ODE_EINVAL, "host_dst is null");
+    B2_CUDA(cudaMemcpyAsync(host_dst, s->b.state, sizeof(b2ode_state), cudaMemcpyDeviceToHost, s->stream));
+    return 0;
+}
+
+extern "C" int b2ode_poll_sync(b2ode_solver *s, b2ode_state *host_dst) {
+    int rc = b2ode_poll_async(s, host_dst);
+    if (rc) return rc;
+    B2_CUDA(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+// ---- fixed grid --------------------------------------------------------------------------------
+template <typename T>
+static int dispatch_fixed(int op, int grid, cudaStream_t st, const FixedParams &p) {
+    switch (op) {
+#define B2_CASE(OP) \
+    case OP:        \
+        return launch(k_fixed<T, OP>, grid, st, p);
+        B2_CASE(B2ODE_OP_EULER) B2_CASE(B2ODE_OP_HALF_STEP) B2_CASE(B2ODE_OP_HEUN_FINAL) B2_CASE(B2ODE_OP_RK4_S2)
+        B2_CASE(B2ODE_OP_RK4_S3) B2_CASE(B2ODE_OP_RK4_S4) B2_CASE(B2ODE_OP_RK4_FINAL) B2_CASE(B2ODE_OP_LERP)
+#undef B2_CASE
+    }
+    return fail(B2ODE_EINVAL, "unknown fixed-grid op %d", op);
+}
+
+extern "C" int b2ode_fixed_op(int dtype, int op, int nseg, const int64_t *seg_len, void *const *out, const void *const *y,
+                              const void *const *a, const void *const *b, const void *const *c, const void *const *d,
+                              double dt, double s1, double s2, int sm_count, void *cuda_stream) {
+    if (dtype != B2ODE_F32 && dtype != B2ODE_F64) return fail(B2ODE_EINVAL, "dtype must be 0 or 1");
+    if (nseg < 1 || nseg > B2ODE_MAXSEG || !seg_len || !out || !y || !a) return fail(B2ODE_EINVAL, "bad segment arguments");
+    int arity = 1;
+    switch (op) {
+        case B2ODE_OP_HEUN_FINAL:
+        case B2ODE_OP_RK4_S3: arity = 2; break;
+        case B2ODE_OP_RK4_S4: arity = 3; break;
+        case B2ODE_OP_RK4_FINAL: arity = 4; break;
+        default: break;
+    }
+    if ((arity > 1 && !b) || (arity > 2 && !c) || (arity > 3 && !d)) return fail(B2ODE_EINVAL, "op %d needs %d operands", op, arity);
+    FixedParams p;
+    memset(&p, 0, sizeof(p));
+    build_geom(&p.g, dtype, nseg, seg_len, sm_count);
+    p.op = op;
+    unsigned mask = 0;
+    for (int s = 0; s < nseg; ++s) {
+        if (seg_len[s] < 0) return fail(B2ODE_EINVAL, "negative segment length");
+        p.out[s] = out[s];
+        p.y[s] = y[s];
+        p.a[s] = a[s];
+        p.b[s] = arity > 1 ? b[s] : nullptr;
+        p.c[s] = arity > 2 ? c[s] : nullptr;
+        p.d[s] = arity > 3 ? d[s] : nullptr;
+        if (seg_len[s] > 0 && (!p.out[s] || !p.y[s] || !p.a[s] || (arity > 1 && !p.b[s]) || (arity > 2 && !p.c[s]) ||
+                               (arity > 3 && !p.d[s])))
+            return fail(B2ODE_EINVAL, "segment %d has a null operand", s);
+        if (aligned16(p.out[s]) && aligned16(p.y[s]) && aligned16(p.a[s]) && aligned16(p.b[s]) && aligned16(p.c[s]) &&
+            aligned16(p.d[s]))
+            mask |= 1u << s;
+    }
+    p.g.vec_mask = mask;
+    p.dt = dt;
+    p.s1 = s1;
+    p.s2 = s2;
+    const int grid = p.g.blk_begin[nseg];
+    if (dtype == B2ODE_F64) return dispatch_fixed<double>(op, grid, (cudaStream_t)cuda_stream, p);
+    return dispatch_fixed<float>(op, grid, (cudaStream_t)cuda_stream, p);
+}

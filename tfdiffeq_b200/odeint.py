@@ -1,0 +1,49 @@
+"""Public entry point with the reference's signature and dispatch (tfdiffeq/odeint.py:11-81)."""
+from .misc import _check_inputs
+from .solvers import (AdaptiveHeunSolver, Bosh3Solver, Dopri5Solver, Dopri8Solver, Euler, Heun, Midpoint, RK4,
+                      Tsit5Solver)
+
+# tfdiffeq/odeint.py:11-25.  The three multistep Adams solvers of the reference (explicit_adams, fixed_adams,
+# adams) are outside this engine's scope: asking for them raises KeyError
+# exactly like any unknown method name does in the reference (odeint.py:77).
+SOLVERS = {
+    'tsit5': Tsit5Solver,
+    'dopri5': Dopri5Solver,
+    'dopri8': Dopri8Solver,
+    'bosh3': Bosh3Solver,
+    'euler': Euler,
+    'midpoint': Midpoint,
+    'rk4': RK4,
+    'huen': Heun,
+    'heun': Heun,
+    'adaptive_heun': AdaptiveHeunSolver,
+}
+
+
+def odeint(func, y0, t, rtol=1e-7, atol=1e-9, method=None, options=None):
+    """Integrate ``dy/dt = func(t, y), y(t[0]) = y0`` and return ``y`` at every time in ``t``.
+
+    Same contract as the reference (tfdiffeq/odeint.py:28-81): ``y0`` is a tensor of any shape or a tuple of
+    tensors, ``t`` a strictly monotone 1-D tensor (decreasing ``t`` integrates backwards, misc.py:318-321),
+    the result has shape ``(len(t), *y0.shape)`` (a tuple of such for tuple states) in ``y0``'s dtype.
+    ``func(t, y)`` is any callable on torch CUDA tensors, typically an ``nn.Module``; ``t`` reaches it as a
+    0-dim device tensor.  Raises ``ValueError`` if ``options`` is given without ``method``, ``KeyError`` for
+    an unknown ``method``, ``TypeError`` for non-numeric inputs, ``AssertionError`` for non-monotone ``t``,
+    step-size underflow, non-finite states or ``max_num_steps``; unknown option keys only warn.
+    """
+    tensor_input, func, y0, t = _check_inputs(func, y0, t)
+    if options is None:
+        options = {}
+    elif method is None:
+        raise ValueError('cannot supply `options` without specifying `method`')
+    if method is None:
+        method = 'dopri5'
+    solver = SOLVERS[method](func, y0, rtol=rtol, atol=atol, **options)
+    solution = solver.integrate(t)
+    odeint.last_solver = solver
+    if tensor_input:
+        solution = solution[0]
+    return solution
+
+
+odeint.last_solver = None

@@ -1,0 +1,541 @@
+"""Host drivers: the reference's solver protocol (``__init__(func, y0, rtol=, atol=, **options)`` +
+``integrate(t)``, tfdiffeq/odeint.py:77-78) on top of ``libb2ode``.
+
+What stays in Python is what the reference keeps in Python: calling the user's ``func`` and sequencing the
+stages.  Everything numeric is a kernel launch through the C ABI; the step size, the accept/reject decision
+and the output cursor never leave the device, so the loop below enqueues whole attempts without reading
+anything back, polling a 256-byte state asynchronously through pinned memory.
+"""
+import collections
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import tableaus as tb
+from .misc import _assert_increasing, _handle_unused_kwargs, _is_iterable, _tf_f64
+
+_ITEM = {torch.float32: 4, torch.float64: 8}
+_DT = {torch.float32: _lib.F32, torch.float64: _lib.F64}
+
+# statistics of the most recent solve (the reference exposes none; `nfe` mirrors its model-side counters)
+last_stats = {}
+
+
+def _require_cuda(y0):
+    dev = y0[0].device
+    if dev.type != "cuda":
+        raise RuntimeError(
+            "tfdiffeq_b200 runs on CUDA tensors only (got device %s); there is no CPU code path." % dev)
+    dt = y0[0].dtype
+    if dt not in _ITEM:
+        raise TypeError("state dtype must be float32 or float64, got %s" % dt)
+    for y in y0:
+        if y.device != dev or y.dtype != dt:
+            raise TypeError("all state components must share one device and dtype")
+    if len(y0) > _lib.MAXSEG:
+        raise ValueError("at most %d state components are supported" % _lib.MAXSEG)
+    return dev, dt
+
+
+class _Segments(object):
+    """Engine-owned flat buffers: one allocation per role, tuple components at 16-byte aligned offsets."""
+
+    def __init__(self, y0):
+        self.device, self.dtype = _require_cuda(y0)
+        self.item = _ITEM[self.dtype]
+        self.shapes = [tuple(y.shape) for y in y0]
+        self.lens = [int(y.numel()) for y in y0]
+        al = 16 // self.item
+        self.offs, off = [], 0
+        for n in self.lens:
+            self.offs.append(off)
+            off += (n + al - 1) // al * al
+        self.total = max(off, al)
+        self.nseg = len(y0)
+
+    def new(self):
+        return torch.empty(self.total, dtype=self.dtype, device=self.device)
+
+    def views(self, flat):
+        return tuple(flat[o:o + n].view(s) for o, n, s in zip(self.offs, self.lens, self.shapes))
+
+    def ptrs(self, flat):
+        base = flat.data_ptr()
+        return [base + o * self.item for o in self.offs]
+
+    def fill(self, flat, tensors):
+        for v, t in zip(self.views(flat), tensors):
+            v.copy_(t)
+
+
+def _ptr_array(ptrs):
+    arr = _lib.PtrArray()
+    for i, p in enumerate(ptrs):
+        arr[i] = p
+    return arr
+
+
+class _FuncOutputs(object):
+    """Normalises what ``func`` returns into per-segment contiguous tensors the kernels can read in place."""
+
+    def __init__(self, seg, engine_flats):
+        self.seg = seg
+        self.ranges = [(f.data_ptr(), f.data_ptr() + f.numel() * seg.item) for f in engine_flats]
+        self.arr = _lib.PtrArray()
+
+    def collect(self, outs, live):
+        seg = self.seg
+        if isinstance(outs, torch.Tensor):
+            outs = (outs,)
+        if len(outs) != seg.nseg:
+            raise ValueError("func returned %d tensors for a state of %d components" % (len(outs), seg.nseg))
+        res = []
+        for s, o in enumerate(outs):
+            if not isinstance(o, torch.Tensor):
+                o = torch.as_tensor(o, dtype=seg.dtype, device=seg.device)
+            if o.dtype != seg.dtype or o.device != seg.device:
+                o = o.to(device=seg.device, dtype=seg.dtype)
+            if o.numel() != seg.lens[s]:
+                o = o.expand(seg.shapes[s])
+            if not o.is_contiguous():
+                o = o.contiguous()
+            p = o.data_ptr()
+            nbytes = seg.lens[s] * seg.item
+            # a func that returns (a view of) its input, or the same buffer on every call, would be
+            # overwritten by the next stage: give it its own storage
+            if nbytes and (any(p < hi and p + nbytes > lo for lo, hi in self.ranges) or p in live):
+                o = o.clone()
+                p = o.data_ptr()
+            live.add(p)
+            res.append(o)
+        return res
+
+    def pointers(self, tensors):
+        for i, t in enumerate(tensors):
+            self.arr[i] = t.data_ptr()
+        return self.arr
+
+
+class AdaptiveStepsizeODESolver(object):
+    """Adaptive explicit Runge-Kutta driver (tfdiffeq/solvers.py:10-35 + the solver classes that follow it,
+    e.g. tfdiffeq/dopri5.py:48-121), generic over the tableau."""
+
+    tableau = None
+    RUN_AHEAD = 8          # attempts the host may be ahead of the last state it has seen
+
+    def __init__(self, func, y0, rtol, atol, first_step=None, safety=0.9, ifactor=10.0, dfactor=0.2,
+                 max_num_steps=2 ** 31 - 1, **unused_kwargs):
+        self.comm = unused_kwargs.pop("shared_step_group", None)     # extension: SURVEY 8(e)
+        _handle_unused_kwargs(self, unused_kwargs)
+        del unused_kwargs
+        self.func = func
+        self.y0 = y0
+        if self.tableau.controller == "tsit5":
+            # tsit5.py:81-82 keeps scalars; iterables break its arithmetic
+            self.rtol = [rtol] * len(y0)
+            self.atol = [atol] * len(y0)
+        else:
+            self.rtol = list(rtol) if _is_iterable(rtol) else [rtol] * len(y0)
+            self.atol = list(atol) if _is_iterable(atol) else [atol] * len(y0)
+        self.first_step = first_step
+        self.safety = _tf_f64(safety)
+        self.ifactor = _tf_f64(ifactor)
+        self.dfactor = _tf_f64(dfactor)
+        self.max_num_steps = int(max_num_steps)
+        self.stats = {}
+
+    # -- construction of the native solver ---------------------------------------------------------
+    def _describe(self, seg):
+        t = self.tableau
+        d = _lib.AdaptiveDesc()
+        d.dtype = _DT[seg.dtype]
+        d.nseg = seg.nseg
+        for i, n in enumerate(seg.lens):
+            d.seg_len[i] = n
+        d.n_k = t.n_k
+        d.fsal = 1 if t.fsal else 0
+        for i, a in enumerate(t.alpha):
+            d.alpha[i] = a
+        for i, row in enumerate(t.beta):
+            for j, v in enumerate(row):
+                d.beta[i][j] = v
+        for j in range(t.n_k):
+            d.c_sol[j] = t.c_sol[j]
+            d.c_error[j] = t.c_error[j]
+            d.c_mid[j] = t.c_mid[j] if t.c_mid is not None else 0.0
+        d.dense_kind = 0 if t.c_mid is not None else 1
+        d.controller = _lib.CTRL_TSIT5 if t.controller == "tsit5" else _lib.CTRL_REFERENCE
+        for i in range(seg.nseg):
+            d.rtol[i] = float(self.rtol[i])
+            d.atol[i] = float(self.atol[i])
+        d.safety, d.ifactor, d.dfactor = self.safety, self.ifactor, self.dfactor
+        if t.controller == "tsit5":
+            d.exponent = 1.0 / t.ctrl_order                               # tsit5.py:59: exact float64
+        else:
+            d.exponent = float(np.float64(np.float32(1.0 / t.ctrl_order)))   # misc.py:281-282: via float32
+        d.max_num_steps = min(self.max_num_steps, 2 ** 62)
+        d.init_order = t.init_order
+        d.sm_count = torch.cuda.get_device_properties(seg.device).multi_processor_count
+        return d
+
+    def integrate(self, t):
+        _assert_increasing(t)
+        seg = _Segments(self.y0)
+        dev, dtype = seg.device, seg.dtype
+        with torch.cuda.device(dev), torch.no_grad():
+            return self._integrate(t, seg, dev, dtype)
+
+    def _integrate(self, t, seg, dev, dtype):
+        lib, check = _lib.lib, _lib.check
+        tab = self.tableau
+        nk = tab.n_k
+        t_host = t.detach().to("cpu", torch.float64).numpy()                 # solvers.py:30: time is float64
+        t_dev = torch.from_numpy(t_host).to(dev)
+        n_out = int(t_host.shape[0])
+        t_end = float(t_host[-1])
+
+        Y0, F0, S = seg.new(), seg.new(), seg.new()
+        outs = [torch.empty((n_out,) + shp, dtype=dtype, device=dev) for shp in seg.shapes]
+        tstage = torch.zeros(nk, dtype=dtype, device=dev)
+        state_dev = torch.zeros(256, dtype=torch.uint8, device=dev)
+        desc = self._describe(seg)
+        ws_bytes = int(lib.b2ode_workspace_bytes(C.byref(desc)))
+        workspace = torch.empty(max(ws_bytes, 32), dtype=torch.uint8, device=dev)
+
+        handle = C.c_void_p()
+        check(lib.b2ode_adaptive_create(C.byref(handle), C.byref(desc)))
+        try:
+            buf = _lib.AdaptiveBuffers()
+            buf.state = state_dev.data_ptr()
+            buf.workspace = workspace.data_ptr()
+            buf.workspace_bytes = workspace.numel()
+            for i, (a, b, c) in enumerate(zip(seg.ptrs(Y0), seg.ptrs(F0), seg.ptrs(S))):
+                buf.y0[i], buf.f0[i], buf.ystage[i] = a, b, c
+                buf.out[i] = outs[i].data_ptr()
+            buf.tstage = tstage.data_ptr()
+            buf.t_out = t_dev.data_ptr()
+            buf.n_out = n_out
+            stream = torch.cuda.current_stream(dev)
+            check(lib.b2ode_adaptive_bind(handle, C.byref(buf), C.c_void_p(stream.cuda_stream)))
+            if self.comm is not None:
+                self.comm.attach(handle, seg)
+
+            fo = _FuncOutputs(seg, (Y0, F0, S))
+            y0_views, s_views = seg.views(Y0), seg.views(S)
+            nfe = 0
+
+            # ---- before_integrate (dopri5.py:70-78) ----------------------------------------------
+            seg.fill(Y0, self.y0)
+            t0_state = t_dev[0].to(dtype)                                    # tf.cast(t[0], y0.dtype)
+            f0 = fo.collect(self.func(t0_state, y0_views), set())
+            nfe += 1
+            seg.fill(F0, f0)
+            if self.first_step is None:
+                check(lib.b2ode_adaptive_init(handle, float(t_host[0]), float("nan")))
+                check(lib.b2ode_initial_step_probe(handle))
+                f1 = fo.collect(self.func(tstage[0], s_views), set())
+                nfe += 1
+                check(lib.b2ode_initial_step_finish(handle, fo.pointers(f1)))
+                del f1
+            else:
+                check(lib.b2ode_adaptive_init(handle, float(t_host[0]), _tf_f64(self.first_step)))
+            if tab.controller == "tsit5":
+                # tsit5.py:92-98: _select_initial_step computes its own f0 and the state f0 is evaluated
+                # again (with the float64 t[0]); one redundant evaluation, kept so NFE matches
+                if self.first_step is None:
+                    self.func(t_dev[0], y0_views)
+                    nfe += 1
+
+            # ---- pinned ring for asynchronous state polls --------------------------------------------
+            D = self.RUN_AHEAD
+            pinned = torch.empty(256 * (D + 1), dtype=torch.uint8).pin_memory()
+            slots = [_lib.State.from_address(pinned.data_ptr() + 256 * i) for i in range(D + 1)]
+            events = [torch.cuda.Event() for _ in range(D + 1)]
+            check(lib.b2ode_poll_sync(handle, C.c_void_p(pinned.data_ptr() + 256 * D)))
+            known = _lib.State.from_buffer_copy(slots[D])     # snapshots: the ring slots get overwritten
+            known_at = 0
+            n_enq = 0
+            pending = collections.deque()
+            g = self.ifactor
+
+            tstage_views = [tstage[i] for i in range(nk - 1)]
+            func = self.func
+            rk_stage, rk_finalize, poll_async = lib.b2ode_rk_stage, lib.b2ode_rk_finalize, lib.b2ode_poll_async
+            prev_last = None
+            while not known.done:
+                ahead = n_enq - known_at
+                go = ahead == 0
+                if not go and ahead < D:
+                    # every attempt advances t1 by at most dt and grows dt by at most `ifactor`: if even that
+                    # cannot reach the last output time, the next attempt is certainly needed -> no sync
+                    reach = known.dt * (ahead if g == 1.0 else (g ** ahead - 1.0) / (g - 1.0))
+                    go = (known.t1 + reach) < t_end and known.status == 0
+                if go:
+                    live = set()
+                    ks = []           # every k of the attempt stays referenced until its last reader is enqueued
+                    check(rk_stage(handle, 0, None))
+                    k = fo.collect(func(tstage_views[0], s_views), live)
+                    ks.append(k)
+                    for i in range(1, nk - 1):
+                        check(rk_stage(handle, i, fo.pointers(k)))
+                        k = fo.collect(func(tstage_views[i], s_views), live)
+                        ks.append(k)
+                    if not tab.fsal:
+                        check(rk_stage(handle, nk - 1, fo.pointers(k)))
+                    check(rk_finalize(handle, fo.pointers(k)))
+                    prev_last = k     # k_{s-1} is read once more by the next attempt's stage 0 (the commit)
+                    del ks
+                    nfe += nk - 1
+                    slot = n_enq % D
+                    n_enq += 1
+                    check(poll_async(handle, C.c_void_p(pinned.data_ptr() + 256 * slot)))
+                    events[slot].record(stream)
+                    pending.append((n_enq, slot))
+                    while pending and events[pending[0][1]].query():
+                        known_at, slot = pending.popleft()
+                        known = _lib.State.from_buffer_copy(slots[slot])
+                else:
+                    known_at, slot = pending.popleft()
+                    events[slot].synchronize()
+                    known = _lib.State.from_buffer_copy(slots[slot])
+            del prev_last
+            final = known
+            self.stats = dict(n_accepted=int(final.n_acc), n_rejected=int(final.n_rej), nfe=nfe,
+                              attempts_enqueued=n_enq, status=int(final.status))
+            last_stats.clear()
+            last_stats.update(self.stats)
+            if final.status:
+                self._raise(final, s_views, y0_views)
+            stream.synchronize()      # outputs are complete; also keeps Y0/F0/S alive until the kernels ran
+        finally:
+            lib.b2ode_adaptive_destroy(handle)
+        return tuple(outs)
+
+    def _raise(self, st, s_views, y0_views):
+        """Re-raise the device status word with the reference's assertion messages."""
+        if st.status & _lib.ST_NONFINITE:
+            raise AssertionError('non-finite values in state `y`: {}'.format(y0_views[0]))   # dopri5.py:100
+        if st.status & _lib.ST_MAXSTEPS:
+            raise AssertionError('max_num_steps exceeded ({}>={})'.format(                  # dopri5.py:85
+                int(st.n_steps_adv), self.max_num_steps))
+        if st.status & _lib.ST_UNDERFLOW:
+            raise AssertionError('underflow in dt {}'.format(st.dt))                         # dopri5.py:98
+        raise AssertionError('solver status {}'.format(st.status))
+
+
+class Dopri5Solver(AdaptiveStepsizeODESolver):
+    """tfdiffeq/dopri5.py:48 (the ``tableau=`` option of :53 is honoured)"""
+    tableau = tb.DOPRI5
+
+    def __init__(self, func, y0, rtol, atol, tableau=None, **kw):
+        if tableau is not None:
+            self.tableau = tableau
+        super(Dopri5Solver, self).__init__(func, y0, rtol, atol, **kw)
+
+
+class Dopri8Solver(AdaptiveStepsizeODESolver):
+    """tfdiffeq/dopri8.py:100"""
+    tableau = tb.DOPRI8
+
+
+class Bosh3Solver(AdaptiveStepsizeODESolver):
+    """tfdiffeq/bosh3.py:33; ``options={'textbook_tableau': True}`` selects the tableau the reference meant."""
+    tableau = tb.BOSH3
+
+    def __init__(self, func, y0, rtol, atol, textbook_tableau=False, **kw):
+        if textbook_tableau:
+            self.tableau = tb.BOSH3_TEXTBOOK
+        super(Bosh3Solver, self).__init__(func, y0, rtol, atol, **kw)
+
+
+class AdaptiveHeunSolver(AdaptiveStepsizeODESolver):
+    """tfdiffeq/adaptive_huen.py:47"""
+    tableau = tb.ADAPTIVE_HEUN
+
+
+class Tsit5Solver(AdaptiveStepsizeODESolver):
+    """tfdiffeq/tsit5.py:69 (pooled error, sqrt-free controller, k-based dense output as written)"""
+    tableau = tb.TSIT5
+
+
+# ----------------------------------------------------------------------------------------------------
+# fixed grid
+# ----------------------------------------------------------------------------------------------------
+class FixedGridODESolver(object):
+    """tfdiffeq/solvers.py:38-115"""
+
+    method = None
+    order = None
+
+    def __init__(self, func, y0, step_size=None, grid_constructor=None, eps=0.0, **unused_kwargs):
+        unused_kwargs.pop('rtol', None)
+        unused_kwargs.pop('atol', None)
+        _handle_unused_kwargs(self, unused_kwargs)
+        del unused_kwargs
+        self.func = func
+        self.y0 = y0
+        self.eps = eps
+        if step_size is not None and grid_constructor is None:
+            self.grid_constructor = self._grid_constructor_from_step_size(step_size)
+        elif grid_constructor is None:
+            self.grid_constructor = lambda f, y0, t: t
+        else:
+            raise ValueError("step_size and grid_constructor are exclusive arguments.")
+        self.stats = {}
+
+    @staticmethod
+    def _grid_constructor_from_step_size(step_size):
+        # tfdiffeq/solvers.py:58-71 cannot run under TF2 (`tf.ceil`, item assignment); this is its evident
+        # intent: a uniform grid from t[0] whose last point is clamped to t[-1]  
+        def _grid_constructor(func, y0, t):
+            start_time, end_time = t[0], t[-1]
+            niters = int(math.ceil(float((end_time - start_time) / step_size + 1)))
+            t_infer = torch.arange(0, niters, dtype=t.dtype, device=t.device) * step_size + start_time
+            if t_infer[-1] > t[-1]:
+                t_infer[-1] = t[-1]
+            return t_infer
+        return _grid_constructor
+
+    # stage recipes: (time offset as a function of (t0, dt) in the state dtype, kernel op, operand indices)
+    def integrate(self, t):
+        _assert_increasing(t)
+        seg = _Segments(self.y0)
+        with torch.cuda.device(seg.device), torch.no_grad():
+            return self._integrate(t, seg)
+
+    def _integrate(self, t, seg):
+        lib, check = _lib.lib, _lib.check
+        dev, dtype = seg.device, seg.dtype
+        npdt = np.float32 if dtype == torch.float32 else np.float64
+        t = t.to(dtype)                                                        # solvers.py:84
+        time_grid = self.grid_constructor(self.func, self.y0, t)
+        t_np = t.detach().cpu().numpy().astype(npdt)
+        g_np = time_grid.detach().cpu().numpy().astype(npdt)
+        assert g_np[0] == t_np[0] and g_np[-1] == t_np[-1]                     # solvers.py:86
+        n_out, n_steps = int(t_np.shape[0]), int(g_np.shape[0]) - 1
+        outs = [torch.empty((n_out,) + shp, dtype=dtype, device=dev) for shp in seg.shapes]
+        for o, y in zip(outs, self.y0):
+            o[0].copy_(y)
+        stream = torch.cuda.current_stream(dev)
+        sm = torch.cuda.get_device_properties(dev).multi_processor_count
+        dcode = _DT[dtype]
+        lens = _lib.LenArray(*seg.lens)
+        nseg = seg.nseg
+        item = seg.item
+        sptr = C.c_void_p(stream.cuda_stream)
+
+        # stage times for every step, computed on the host in the state dtype with the reference's operation
+        # order, uploaded once; func receives 0-dim device views
+        eps = npdt(self.eps)
+        t0s, dts = g_np[:-1], g_np[1:] - g_np[:-1]
+        m = self.method
+        if m == "euler":
+            times = np.stack([t0s + eps], 1)                                   # fixed_grid.py:7
+        elif m == "midpoint":
+            times = np.stack([t0s + eps, t0s + dts / npdt(2)], 1)              # fixed_grid.py:17-18
+        elif m == "heun":
+            times = np.stack([t0s + eps, t0s + dts], 1)                        # fixed_grid.py:29-31
+        else:
+            te = t0s + eps                                                     # fixed_grid.py:42
+            times = np.stack([te, te + dts / npdt(3), te + dts * npdt(2) / npdt(3), te + dts], 1)  # rk_common.py:76-79
+        times_dev = torch.from_numpy(np.ascontiguousarray(times.astype(npdt))).to(dev)
+
+        # two scratch states: the stage input, and y1 for grid cells whose end is not an output time
+        S, Y1a, Y1b = seg.new(), seg.new(), seg.new()
+        fo = _FuncOutputs(seg, (S, Y1a, Y1b) + tuple(outs))
+        s_views, s_ptrs = seg.views(S), _ptr_array(seg.ptrs(S))
+        scratch = [(seg.views(Y1a), _ptr_array(seg.ptrs(Y1a))), (seg.views(Y1b), _ptr_array(seg.ptrs(Y1b)))]
+
+        def op(code, out_p, y_p, a, b=None, c=None, d=None, dt=0.0, s1=0.0, s2=0.0):
+            check(lib.b2ode_fixed_op(dcode, code, nseg, lens, out_p, y_p, a, b, c, d, float(dt), float(s1), float(s2),
+                                     sm, sptr))
+
+        def row_ptrs(j):
+            return _ptr_array([o.data_ptr() + j * n * item for o, n in zip(outs, seg.lens)])
+
+        def row_views(j):
+            return tuple(o[j] for o in outs)
+
+        y_views, y_ptrs = row_views(0), row_ptrs(0)
+        j = 1
+        nfe = 0
+        func = self.func
+        flip = 0
+        for i in range(n_steps):
+            t0, t1, dt = g_np[i], g_np[i + 1], dts[i]
+            # outputs inside this cell (solvers.py:97): t0 < t[j] <= t1
+            j_hi = j
+            while j_hi < n_out and t1 >= t_np[j_hi]:
+                j_hi += 1
+            ends_on_output = j_hi > j and t_np[j_hi - 1] == t1
+            if ends_on_output:
+                y1_views, y1_ptrs = row_views(j_hi - 1), row_ptrs(j_hi - 1)   # y1 lands straight in the slab
+            else:
+                y1_views, y1_ptrs = scratch[flip]
+                flip ^= 1
+            tv = times_dev[i]
+            live = set()
+            if m == "euler":
+                k1 = fo.collect(func(tv[0], y_views), live)
+                op(_lib.OP_EULER, y1_ptrs, y_ptrs, fo.pointers(k1), dt=dt)
+                nfe += 1
+            elif m == "midpoint":
+                k1 = fo.collect(func(tv[0], y_views), live)
+                op(_lib.OP_HALF_STEP, s_ptrs, y_ptrs, fo.pointers(k1), dt=dt)
+                k2 = fo.collect(func(tv[1], s_views), live)
+                op(_lib.OP_EULER, y1_ptrs, y_ptrs, fo.pointers(k2), dt=dt)
+                nfe += 2
+            elif m == "heun":
+                k1 = fo.collect(func(tv[0], y_views), live)
+                op(_lib.OP_EULER, s_ptrs, y_ptrs, fo.pointers(k1), dt=dt)
+                k2 = fo.collect(func(tv[1], s_views), live)
+                op(_lib.OP_HEUN_FINAL, y1_ptrs, y_ptrs, _ptr_array([x.data_ptr() for x in k1]),
+                   _ptr_array([x.data_ptr() for x in k2]), dt=dt)
+                nfe += 2
+            else:   # rk4, 3/8 rule (rk_common.py:73-81)
+                k1 = fo.collect(func(tv[0], y_views), live)
+                p1 = _ptr_array([x.data_ptr() for x in k1])
+                op(_lib.OP_RK4_S2, s_ptrs, y_ptrs, p1, dt=dt)
+                k2 = fo.collect(func(tv[1], s_views), live)
+                p2 = _ptr_array([x.data_ptr() for x in k2])
+                op(_lib.OP_RK4_S3, s_ptrs, y_ptrs, p1, p2, dt=dt)
+                k3 = fo.collect(func(tv[2], s_views), live)
+                p3 = _ptr_array([x.data_ptr() for x in k3])
+                op(_lib.OP_RK4_S4, s_ptrs, y_ptrs, p1, p2, p3, dt=dt)
+                k4 = fo.collect(func(tv[3], s_views), live)
+                p4 = _ptr_array([x.data_ptr() for x in k4])
+                op(_lib.OP_RK4_FINAL, y1_ptrs, y_ptrs, p1, p2, p3, p4, dt=dt)
+                nfe += 4
+            # interior outputs: linear interpolation (solvers.py:106-115)
+            for jj in range(j, j_hi - (1 if ends_on_output else 0)):
+                op(_lib.OP_LERP, row_ptrs(jj), y_ptrs, y1_ptrs, s1=npdt(t1) - npdt(t0), s2=npdt(t_np[jj]) - npdt(t0))
+            j = j_hi
+            y_views, y_ptrs = y1_views, y1_ptrs
+        self.stats = dict(n_accepted=n_steps, n_rejected=0, nfe=nfe, status=0)
+        last_stats.clear()
+        last_stats.update(self.stats)
+        stream.synchronize()
+        return tuple(outs)
+
+
+class Euler(FixedGridODESolver):
+    """tfdiffeq/fixed_grid.py:4"""
+    method, order = "euler", 1
+
+
+class Midpoint(FixedGridODESolver):
+    """tfdiffeq/fixed_grid.py:14"""
+    method, order = "midpoint", 2
+
+
+class Heun(FixedGridODESolver):
+    """tfdiffeq/fixed_grid.py:26"""
+    method, order = "heun", 2
+
+
+class RK4(FixedGridODESolver):
+    """tfdiffeq/fixed_grid.py:39 (the 3/8 rule, rk_common.py:73-81)"""
+    method, order = "rk4", 4
