@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's metric on BASELINE.json's configuration.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+metric   : accepted RK steps/s x state elements (fp64)
+workload : configs[1] = Lorenz attractor, batch 65 536 x dim 3, fp64, dopri5 adaptive (rtol 1e-7, atol 1e-9),
+           1 000 output points t = arange(1000) * 0.01, synthetic seeded initial states (cfg 2).
+step     : ONE full odeint() solve of that workload (all accepted + rejected attempts, the dense output of
+           all 1 000 points).  value = accepted_steps * state_elements / seconds, aggregated over ranks.
+N > 1    : weak scaling -- every rank integrates its own 65 536-trajectory shard; the shards form ONE ODE
+           system with a shared step size (reference semantics), the per-attempt error-norm exchange runs
+           inside the finalize kernel over NVLink peer memory.
+
+Extra objects on the JSON line: `roofline` (fused error/finalize kernel at this workload),
+`roofline_headline` (the same kernel family at the north-star size 65 536 x 128 fp64, all buffers > L2),
+`cpu_baseline` (the oracle port on the host cores), `e2e` (host buffers in, host buffers out through the
+public odeint API), `clocks`, `gpu_launches`.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "tests")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+METRIC = "accepted_rk_steps_x_state_elements_per_s"
+UNIT = "element-steps/s"
+B, DIM, NPTS = 65536, 3, 1000
+RTOL, ATOL = 1e-7, 1e-9
+BYTES_PER_ELEM_STEP_FP64 = 352          # Dopri5 accepted step, 44 elements x 8 B
+FINALIZE_ELEMS = 8                      # y0, y1, k1, k3..k7 read once by the fused finalize kernel
+
+
+def lorenz_y0(batch, seed):
+    rng = np.random.default_rng(seed)
+    return np.array([1.0, 1.0, 1.0]) + 0.1 * rng.standard_normal((batch, 3))
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (recipe in B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx = float(r[2])
+            except (ValueError, IndexError):
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port on torch-CPU tensors, all host threads
+# ------------------------------------------------------------------------------------------------------
+def cpu_sample(npts, batch=B, repeats=1):
+    """A bounded sample of the same workload: the first `npts` output points of the full batch, through the
+    oracle (oracle/np_ref.py, op-for-op eager like the reference) on torch-CPU with every host thread."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import np_ref
+    from problems import PROBLEMS
+    torch.set_num_threads(os.cpu_count() or 1)
+    f = PROBLEMS["lorenz"](backend="torch")
+    y0 = torch.from_numpy(lorenz_y0(batch, 0))
+    t = np.arange(npts) * 0.01
+    best, acc = None, 0
+    for _ in range(repeats):
+        st = np_ref.Stats()
+        t0 = time.perf_counter()
+        np_ref.odeint(f, y0, t, rtol=RTOL, atol=ATOL, method="dopri5", stats=st)
+        dt = time.perf_counter() - t0
+        if best is None or dt < best:
+            best, acc = dt, st.n_acc
+    return dict(seconds=best, n_acc=acc, n_elem=batch * DIM, threads=torch.get_num_threads(),
+                sample="first %d of %d output points of the full %dx%d batch" % (npts, NPTS, batch, DIM))
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    vals, secs = [], []
+    npts = 60
+    for i in range(args.warmup + args.steps):
+        s = cpu_sample(npts)
+        if i >= args.warmup:
+            vals.append(s["n_acc"] * s["n_elem"] / s["seconds"])
+            secs.append(s["seconds"])
+    v = float(np.mean(vals))
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(secs)), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "lorenz_b65536x3_f64_dopri5_1000pts", "sample": s["sample"]},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": s["threads"], "kind": "port", "sample": s["sample"]},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------------
+def headline_kernel_roofline(dev, peak):
+    """The fused finalize kernel at the north-star size: 65 536 x 128 fp64 (64 MiB per buffer, 8 read streams
+    = 512 MiB per launch, far beyond the 126 MB L2), timed with CUDA events around each launch."""
+    import tfdiffeq_b200 as tfd
+    from tfdiffeq_b200 import _lib
+    import ctypes as C
+    torch.manual_seed(0)
+    n_b, n_d = 65536, 128
+    y0 = torch.randn(n_b, n_d, dtype=torch.float64, device=dev)
+    A = (-0.5 * torch.eye(n_d, dtype=torch.float64, device=dev)
+         + 0.05 * torch.randn(n_d, n_d, dtype=torch.float64, device=dev))
+    f = lambda t, y: y @ A                                          # noqa: E731
+    t = torch.linspace(0., 2., 11, dtype=torch.float64)
+    tfd.odeint(f, y0, t, method="dopri5", rtol=1e-6, atol=1e-9)    # warm-up
+    _lib.check(_lib.lib.b2ode_timing_enable((1 << _lib.FAM_FINALIZE) | (1 << _lib.FAM_STAGE) | (1 << _lib.FAM_STAGE0)))
+    tfd.odeint(f, y0, t, method="dopri5", rtol=1e-6, atol=1e-9)
+    torch.cuda.synchronize(dev)
+    out = {}
+    n = n_b * n_d
+    for fam, name, elems in ((_lib.FAM_FINALIZE, "finalize", FINALIZE_ELEMS), (_lib.FAM_STAGE, "stages_1_to_5", 25.0 / 5),
+                             (_lib.FAM_STAGE0, "stage_0", 3.0)):
+        ms, cnt = C.c_double(), C.c_int()
+        _lib.check(_lib.lib.b2ode_timing_read(fam, C.byref(ms), C.byref(cnt)))
+        if cnt.value:
+            avg = ms.value / cnt.value
+            gbs = elems * n * 8 / (avg * 1e-3) / 1e9
+            out[name] = {"launches": cnt.value, "avg_ms": avg, "algorithmic_bytes": int(elems * n * 8),
+                         "achieved": gbs, "frac": gbs / peak}
+    _lib.check(_lib.lib.b2ode_timing_enable(0))
+    st = dict(tfd.last_stats)
+    fin = out.get("finalize", {})
+    return {"bound": "hbm", "kernel": "k_rk_finalize<double,6>", "workload": "linear_b65536x128_f64_dopri5",
+            "achieved": fin.get("achieved"), "peak": peak, "unit": "GB/s", "frac": fin.get("frac"),
+            "traffic": None, "per_kernel": out, "n_accepted": st.get("n_accepted"), "n_rejected": st.get("n_rejected")}
+
+
+def run_ours(args, rank, world, local_rank):
+    import ctypes as C
+    import tfdiffeq_b200 as tfd
+    from tfdiffeq_b200 import _lib
+    from problems import PROBLEMS
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    group = None
+    if world > 1:
+        import torch.distributed as dist
+        from tfdiffeq_b200.comm import SharedStepGroup
+        dist.init_process_group("nccl", device_id=dev)
+        group = SharedStepGroup()
+    peak, peak_src = peaks()
+    f = PROBLEMS["lorenz"](backend="torch", device=dev)
+    # weak scaling: every rank owns a full 65 536-trajectory shard (different seed per rank)
+    y0_host = torch.from_numpy(lorenz_y0(B, rank)).pin_memory()
+    t_host = torch.arange(NPTS, dtype=torch.float64) * 0.01
+    out_host = torch.empty((NPTS, B, DIM), dtype=torch.float64).pin_memory()
+    y0_dev = y0_host.to(dev)
+    opts = {"shared_step_group": group} if group is not None else None
+    kw = dict(rtol=RTOL, atol=ATOL, method="dopri5", options=opts)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)     # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize(dev)
+
+    def solve_resident():
+        return tfd.odeint(f, y0_dev, t_host, **kw)
+
+    def solve_e2e():
+        y = y0_host.to(dev, non_blocking=True)                    # H2D inside the timed region
+        sol = tfd.odeint(f, y, t_host, **kw)
+        out_host.copy_(sol, non_blocking=True)                    # D2H of the result inside the timed region
+        torch.cuda.synchronize(dev)
+        return sol
+
+    for _ in range(max(args.warmup, 3)):
+        solve_resident()
+    torch.cuda.synchronize(dev)
+
+    # ---- timed region 1: inputs resident in HBM ------------------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    _lib.check(_lib.lib.b2ode_timing_enable(1 << _lib.FAM_FINALIZE))
+    launches0 = int(_lib.lib.b2ode_launch_count())
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    n_acc = n_rej = 0
+    barrier()
+    wall0 = time.perf_counter()
+    for i in range(args.steps):
+        flush.fill_(i & 0xFF)                                     # L2 flush between timed iterations (untimed)
+        ev[i][0].record()
+        solve_resident()
+        ev[i][1].record()
+        n_acc += tfd.last_stats["n_accepted"]
+        n_rej += tfd.last_stats["n_rejected"]
+    barrier()
+    wall1 = time.perf_counter()
+    launches = int(_lib.lib.b2ode_launch_count()) - launches0
+    ms = sum(a.elapsed_time(b) for a, b in ev)
+    fin_ms, fin_cnt = C.c_double(), C.c_int()
+    _lib.check(_lib.lib.b2ode_timing_read(_lib.FAM_FINALIZE, C.byref(fin_ms), C.byref(fin_cnt)))
+    _lib.check(_lib.lib.b2ode_timing_enable(0))
+
+    # ---- timed region 2: end to end through the public API with host buffers -----------------------------------
+    solve_e2e()
+    ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    e2e_acc = 0
+    barrier()
+    for i in range(args.steps):
+        flush.fill_(i & 0xFF)
+        ev2[i][0].record()
+        solve_e2e()
+        ev2[i][1].record()
+        e2e_acc += tfd.last_stats["n_accepted"]
+    barrier()
+    ms2 = sum(a.elapsed_time(b) for a, b in ev2)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- aggregate over ranks: max time, summed work ---------------------------------------------------------
+    work = float(n_acc) * B * DIM
+    work2 = float(e2e_acc) * B * DIM
+    if world > 1:
+        import torch.distributed as dist
+        tt = torch.tensor([ms, ms2], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ww = torch.tensor([work, work2, float(launches)], dtype=torch.float64, device=dev)
+        dist.all_reduce(ww, op=dist.ReduceOp.SUM)
+        ms, ms2 = float(tt[0]), float(tt[1])
+        work, work2, launches = float(ww[0]), float(ww[1]), int(ww[2])
+    value = work / (ms * 1e-3)
+    e2e_value = work2 / (ms2 * 1e-3)
+
+    if rank == 0:
+        n = B * DIM
+        fin_avg_ms = fin_ms.value / max(fin_cnt.value, 1)
+        fin_bytes = FINALIZE_ELEMS * n * 8
+        fin_gbs = fin_bytes / (fin_avg_ms * 1e-3) / 1e9 if fin_cnt.value else None
+        attempts = (n_acc + n_rej) / float(args.steps)
+        headline = None
+        cpu = None
+        if world == 1:
+            try:
+                headline = headline_kernel_roofline(dev, peak)
+            except Exception as e:                                 # noqa: BLE001  (never lose the main line)
+                headline = {"error": repr(e)[:200]}
+            if not args.no_cpu_baseline:
+                s = cpu_sample(60)
+                cpu = {"value": s["n_acc"] * s["n_elem"] / s["seconds"], "unit": UNIT, "cores": s["threads"],
+                       "kind": "port", "sample": s["sample"], "seconds": s["seconds"]}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "lorenz_b65536x3_f64_dopri5_1000pts", "per_gpu_batch": B, "dim": DIM, "rtol": RTOL,
+                       "atol": ATOL, "n_out": NPTS, "func": "torch eager nn-style callable (external func)",
+                       "l2": "flushed between timed iterations (256 MiB write)",
+                       "parallelism": "batch shards, shared step via in-kernel NVLink mailbox exchange" if world > 1 else "single GPU",
+                       "accepted_per_solve": n_acc / float(args.steps), "rejected_per_solve": n_rej / float(args.steps)},
+            "roofline": {"bound": "hbm", "kernel": "k_rk_finalize<double,6> (error combine + norm + controller)",
+                         "achieved": fin_gbs, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                         "frac": (fin_gbs / peak) if fin_gbs else None, "traffic": None,
+                         "algorithmic_bytes_per_launch": fin_bytes, "avg_launch_ms": fin_avg_ms, "launches_timed": fin_cnt.value,
+                         "note": "8 x 1.5 MiB read streams per launch: L2-resident and launch-latency bound at this "
+                                 "workload size; see roofline_headline for the HBM-bound size",
+                         "step_algorithmic_GBps": BYTES_PER_ELEM_STEP_FP64 * value / 1e9},
+            "roofline_headline": headline,
+            "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms2 / args.steps,
+                    "h2d_bytes_per_step": int(B * DIM * 8 + NPTS * 8), "d2h_bytes_per_step": int(NPTS * B * DIM * 8)},
+            "gpu_launches": launches,
+            "attempts_per_solve": attempts,
+            "wall_s_timed_region": wall1 - wall0,
+            "clocks": clocks,
+        }
+        print(json.dumps(line))
+    if group is not None:
+        group.close()
+        torch.distributed.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -175,6 +175,20 @@ int b2ode_poll_sync(b2ode_solver *s, b2ode_state *host_dst);
 size_t b2ode_mailbox_bytes(void);
 int b2ode_comm_attach(b2ode_solver *s, int rank, int nranks, void *const *mailboxes);
 
+/* Mailbox memory is the one thing the library allocates itself (cudaMalloc, so that a CUDA IPC handle can be
+ * taken): create on each rank, exchange the 64-byte handles out of band, open the peers', attach. */
+int b2ode_mailbox_create(void **dev_ptr, unsigned char handle_out[64]);
+int b2ode_mailbox_open(const unsigned char handle[64], void **peer_ptr);
+int b2ode_mailbox_close(void *peer_ptr);
+int b2ode_mailbox_destroy(void *dev_ptr);
+/* element count of every segment over the WHOLE group (the mean in misc.py:262 is over all ranks' elements) */
+int b2ode_comm_set_global_len(b2ode_solver *s, const int64_t *global_len);
+
+/* ---- measurement hooks (bench.py) --------------------------------------------------------------------- */
+unsigned long long b2ode_launch_count(void);            /* kernels launched by this library so far          */
+int b2ode_timing_enable(unsigned family_mask);          /* CUDA-event timing per kernel family; 0 = off     */
+int b2ode_timing_read(int family, double *total_ms, int *count);
+
 /* ---- fixed-grid steppers (tfdiffeq/solvers.py:82-115, fixed_grid.py, rk_common.py:73-81) ------------ */
 
 #define B2ODE_OP_EULER 0        /* out = y + dt*a                                  fixed_grid.py:6-7 + solvers.py:95 */

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     raw = C.CDLL(_lib.LIB_PATH)
     for name in sorted(declared):
         assert hasattr(raw, name), "libb2ode.so does not export %s" % name
-    assert declared <= set(_lib.EXPORTS) | {"b2ode_comm_set_global_len"}
+    assert declared == set(_lib.EXPORTS)
     assert _lib.lib.b2ode_version() == 1
     assert _lib.lib.b2ode_state_bytes() == 256 == C.sizeof(_lib.State)
 

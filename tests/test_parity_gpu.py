@@ -312,3 +312,17 @@ def test_full_size_linear_scaling_is_exact_for_power_of_two():
     # and it is an actual solution: compare with the matrix exponential
     exact = y0 @ torch.linalg.matrix_exp(A * 1.0)
     assert float((a[-1] - exact).abs().max() / exact.abs().max()) < 1e-4
+
+
+@pytest.mark.parametrize("method", ["euler", "midpoint", "heun", "rk4"])
+def test_fixed_grid_func_reusing_its_output_buffer(method):
+    y0 = torch.linspace(0.5, 1.5, 37, dtype=torch.float64, device=DEV)
+    t = torch.linspace(0., 1., 9)
+    buf = torch.empty_like(y0)
+
+    def reuse(t, y):
+        torch.mul(y, -0.7, out=buf)
+        return buf
+    a = tfd().odeint(lambda t, y: y * -0.7, y0, t, method=method)
+    b = tfd().odeint(reuse, y0, t, method=method)
+    assert torch.equal(a, b)

@@ -12,6 +12,7 @@ MAXPEERS = 8
 F32, F64 = 0, 1
 ST_UNDERFLOW, ST_NONFINITE, ST_MAXSTEPS = 1, 2, 4
 CTRL_REFERENCE, CTRL_TSIT5 = 0, 1
+FAM_STAGE0, FAM_STAGE, FAM_FINALIZE, FAM_EMIT, FAM_INIT, FAM_FIXED = range(6)
 OP_EULER, OP_HALF_STEP, OP_HEUN_FINAL, OP_RK4_S2, OP_RK4_S3, OP_RK4_S4, OP_RK4_FINAL, OP_LERP = range(8)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -70,6 +71,13 @@ _SIGNATURES = {
     "b2ode_poll_sync": (C.c_int, [C.c_void_p, C.c_void_p]),
     "b2ode_comm_attach": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "b2ode_comm_set_global_len": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
+    "b2ode_mailbox_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_char_p]),
+    "b2ode_mailbox_open": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "b2ode_mailbox_close": (C.c_int, [C.c_void_p]),
+    "b2ode_mailbox_destroy": (C.c_int, [C.c_void_p]),
+    "b2ode_launch_count": (C.c_ulonglong, []),
+    "b2ode_timing_enable": (C.c_int, [C.c_uint]),
+    "b2ode_timing_read": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "b2ode_fixed_op": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_void_p),
                                  C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                  C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_double, C.c_double, C.c_double,

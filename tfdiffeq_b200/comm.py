@@ -1,0 +1,115 @@
+"""Shared-step groups: independent batch shards on several GPUs taking ONE step sequence.
+
+The reference has no distributed code; it folds every batch axis into one ODE system with a single step
+size and a tolerance that is a *global scalar* over the whole tensor (tfdiffeq/misc.py:257).  To keep that
+semantics when the batch is sharded across GPUs, every attempt needs, per tuple component,
+``{sum err^2, max|y0|, max|y1|, non-finite}`` over all ranks -- 32 bytes per rank.  ``libb2ode`` exchanges
+them inside the finalize kernel itself: the last block of each rank stores its totals into every peer's
+mailbox over NVLink (peer-mapped through CUDA IPC), spins on the arrival flags, and combines in rank
+order, so all ranks take bit-identical accept / dt decisions with no host involvement and no NCCL call on
+the hot path.  ``torch.distributed`` (NCCL or gloo) is used once, at setup, to exchange the IPC handles.
+
+Usage (one process per GPU)::
+
+    group = SharedStepGroup()                       # uses the default process group
+    y_local = odeint(func, y0_local, t, method='dopri5', options={'shared_step_group': group})
+
+``shard_batch`` gives the contiguous split of the leading batch axis the benchmarks use.
+"""
+import ctypes as C
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+
+
+def shard_bounds(n, world_size, rank):
+    """Contiguous, balanced split of ``n`` items: the first ``n % world_size`` ranks get one extra."""
+    base, extra = divmod(n, world_size)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def shard_batch(y, world_size, rank):
+    lo, hi = shard_bounds(y.shape[0], world_size, rank)
+    return y[lo:hi]
+
+
+def combine_partials(per_rank):
+    """Host-side statement of what the kernel's ``group_combine`` computes (rank order, NaN-propagating max);
+    used by the CPU tests to check the sharded error norm against the unsharded one.
+
+    per_rank: list over ranks of (sum_sq, max0, max1, bad) tuples."""
+    tot = [0.0, 0.0, 0.0, 0.0]
+    for q, (s, m0, m1, bad) in enumerate(per_rank):
+        if q == 0:
+            tot = [s, m0, m1, bad]
+            continue
+        tot[0] = tot[0] + s
+        for c, v in ((1, m0), (2, m1), (3, bad)):
+            tot[c] = float("nan") if (tot[c] != tot[c] or v != v) else max(tot[c], v)
+    return tuple(tot)
+
+
+class SharedStepGroup(object):
+    """Owns this rank's mailbox and the peer mappings; attach()es them to each native solver."""
+
+    def __init__(self, group=None, device=None):
+        if not dist.is_initialized():
+            raise RuntimeError("SharedStepGroup needs an initialised torch.distributed process group")
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        if self.world > _lib.MAXPEERS:
+            raise ValueError("a shared-step group spans at most %d GPUs (one NVSwitch box)" % _lib.MAXPEERS)
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self._own = C.c_void_p()
+        self._peers = []
+        lib, check = _lib.lib, _lib.check
+        with torch.cuda.device(self.device):
+            handle = C.create_string_buffer(64)
+            check(lib.b2ode_mailbox_create(C.byref(self._own), handle))
+            mine = torch.tensor(list(handle.raw), dtype=torch.uint8)
+            backend = dist.get_backend(group)
+            if backend == "nccl":
+                mine = mine.to(self.device)
+            gathered = [torch.empty_like(mine) for _ in range(self.world)]
+            dist.all_gather(gathered, mine, group=group)
+            self._ptrs = _lib.PtrArray()
+            for r in range(self.world):
+                if r == self.rank:
+                    self._ptrs[r] = self._own.value
+                    self._peers.append(None)
+                else:
+                    p = C.c_void_p()
+                    check(lib.b2ode_mailbox_open(bytes(gathered[r].cpu().tolist()), C.byref(p)))
+                    self._ptrs[r] = p.value
+                    self._peers.append(p)
+            dist.barrier(group=group)
+
+    def attach(self, handle, seg):
+        """Called by the solver after ``b2ode_adaptive_bind``."""
+        lib, check = _lib.lib, _lib.check
+        # group-wide element count per component: the mean in misc.py:262 runs over every rank's elements
+        lens = torch.tensor(seg.lens, dtype=torch.int64)
+        if dist.get_backend(self.group) == "nccl":
+            lens = lens.to(self.device)
+        dist.all_reduce(lens, group=self.group)
+        glob = _lib.LenArray(*[int(v) for v in lens.cpu().tolist()])
+        check(lib.b2ode_comm_attach(handle, self.rank, self.world, self._ptrs))
+        check(lib.b2ode_comm_set_global_len(handle, glob))
+
+    def close(self):
+        lib = _lib.lib
+        with torch.cuda.device(self.device):
+            torch.cuda.synchronize()
+            if dist.is_initialized():
+                dist.barrier(group=self.group)
+            for p in self._peers:
+                if p is not None:
+                    lib.b2ode_mailbox_close(p)
+            self._peers = []
+            if self._own:
+                lib.b2ode_mailbox_destroy(self._own)
+                self._own = C.c_void_p()

@@ -223,6 +223,8 @@ struct MailSlot {
 };
 struct Mailbox {
     MailSlot slot[2][B2ODE_MAXPEERS];
+    unsigned long long local_seq;   // exchanges completed by the owning rank; persists across solves
+    unsigned long long pad[7];
 };
 
 struct CommParams {
@@ -254,7 +256,7 @@ template <unsigned MM>
 __device__ void group_combine(const CommParams &cp, b2ode_state *st, Partial *tot, int nseg) {
     if (cp.nranks <= 1) return;
     __shared__ unsigned long long seq_sh;
-    if (threadIdx.x == 0) seq_sh = st->xseq + 1;
+    if (threadIdx.x == 0) seq_sh = cp.box[cp.rank]->local_seq + 1;
     __syncthreads();
     const unsigned long long seq = seq_sh;
     const int par = (int)(seq & 1ull);
@@ -283,6 +285,7 @@ __device__ void group_combine(const CommParams &cp, b2ode_state *st, Partial *to
             }
             tot[s] = p;
         }
+        cp.box[cp.rank]->local_seq = seq;
         st->xseq = seq;
     }
     __syncthreads();
@@ -1174,11 +1177,104 @@ extern "C" int b2ode_comm_set_global_len(b2ode_solver *s, const int64_t *global_
         if (!(s)->bound) return fail(B2ODE_ESTATE, "solver is not bound"); \
     } while (0)
 
+// ---- launch accounting (bench.py's gpu_launches) and optional per-kernel-family event timing -------------
+static unsigned long long g_launches = 0;
+
+enum { B2_FAM_STAGE0 = 0, B2_FAM_STAGE = 1, B2_FAM_FINALIZE = 2, B2_FAM_EMIT = 3, B2_FAM_INIT = 4, B2_FAM_FIXED = 5, B2_NFAM = 6 };
+constexpr int kMaxTimed = 2048;   // event pairs per family
+
+struct Timing {
+    unsigned mask;
+    int n[B2_NFAM];
+    cudaEvent_t ev[B2_NFAM][kMaxTimed][2];
+    bool created[B2_NFAM];
+};
+static Timing *g_timing = nullptr;
+
 template <typename K, typename P>
-static int launch(K kernel, int grid, cudaStream_t st, const P &p) {
+static int launch(K kernel, int grid, cudaStream_t st, const P &p, int fam = -1) {
     if (grid <= 0) return 0;
+    Timing *tm = g_timing;
+    const bool timed = tm && fam >= 0 && ((tm->mask >> fam) & 1u) && tm->n[fam] < kMaxTimed;
+    if (timed) B2_CUDA(cudaEventRecord(tm->ev[fam][tm->n[fam]][0], st));
     kernel<<<grid, kThreads, 0, st>>>(p);
     B2_CUDA(cudaGetLastError());
+    if (timed) {
+        B2_CUDA(cudaEventRecord(tm->ev[fam][tm->n[fam]][1], st));
+        tm->n[fam] += 1;
+    }
+    ++g_launches;
+    return 0;
+}
+
+extern "C" unsigned long long b2ode_launch_count(void) { return g_launches; }
+
+// Enable CUDA-event timing of the kernel families in `family_mask` (bit f = family f: 0 stage0, 1 stage,
+// 2 finalize, 3 dense output, 4 initial step, 5 fixed grid); 0 disables.  Resets the counters.
+extern "C" int b2ode_timing_enable(unsigned family_mask) {
+    if (!g_timing) {
+        g_timing = new (std::nothrow) Timing();
+        if (!g_timing) return fail(B2ODE_ENOMEM, "host allocation failed");
+        memset(g_timing, 0, sizeof(Timing));
+    }
+    for (int f = 0; f < B2_NFAM; ++f) {
+        if (((family_mask >> f) & 1u) && !g_timing->created[f]) {
+            for (int i = 0; i < kMaxTimed; ++i) {
+                B2_CUDA(cudaEventCreate(&g_timing->ev[f][i][0]));
+                B2_CUDA(cudaEventCreate(&g_timing->ev[f][i][1]));
+            }
+            g_timing->created[f] = true;
+        }
+        g_timing->n[f] = 0;
+    }
+    g_timing->mask = family_mask;
+    return 0;
+}
+
+// Sum of the recorded launch durations of one family (synchronises on the last recorded event).
+extern "C" int b2ode_timing_read(int family, double *total_ms, int *count) {
+    if (!g_timing || family < 0 || family >= B2_NFAM || !total_ms || !count) return fail(B2ODE_EINVAL, "bad timing query");
+    double tot = 0.0;
+    const int n = g_timing->n[family];
+    for (int i = 0; i < n; ++i) {
+        float ms = 0.f;
+        B2_CUDA(cudaEventSynchronize(g_timing->ev[family][i][1]));
+        B2_CUDA(cudaEventElapsedTime(&ms, g_timing->ev[family][i][0], g_timing->ev[family][i][1]));
+        tot += (double)ms;
+    }
+    *total_ms = tot;
+    *count = n;
+    return 0;
+}
+
+// ---- mailboxes of a shared-step group: the one place the library owns device memory ---------------------
+// (cudaMalloc'ed so that a CUDA IPC handle can be taken; 5 KB per rank)
+extern "C" int b2ode_mailbox_create(void **dev_ptr, unsigned char handle_out[64]) {
+    if (!dev_ptr || !handle_out) return fail(B2ODE_EINVAL, "null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle is 64 bytes");
+    void *p = nullptr;
+    B2_CUDA(cudaMalloc(&p, sizeof(Mailbox)));
+    B2_CUDA(cudaMemset(p, 0, sizeof(Mailbox)));
+    B2_CUDA(cudaDeviceSynchronize());
+    cudaIpcMemHandle_t h;
+    B2_CUDA(cudaIpcGetMemHandle(&h, p));
+    memcpy(handle_out, &h, 64);
+    *dev_ptr = p;
+    return 0;
+}
+extern "C" int b2ode_mailbox_open(const unsigned char handle[64], void **peer_ptr) {
+    if (!handle || !peer_ptr) return fail(B2ODE_EINVAL, "null argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    B2_CUDA(cudaIpcOpenMemHandle(peer_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+extern "C" int b2ode_mailbox_close(void *peer_ptr) {
+    if (peer_ptr) B2_CUDA(cudaIpcCloseMemHandle(peer_ptr));
+    return 0;
+}
+extern "C" int b2ode_mailbox_destroy(void *dev_ptr) {
+    if (dev_ptr) B2_CUDA(cudaFree(dev_ptr));
     return 0;
 }
 
@@ -1195,6 +1291,7 @@ extern "C" int b2ode_adaptive_init(b2ode_solver *s, double t_start, double first
     else
         k_state_init<float><<<1, 1, 0, s->stream>>>(p);
     B2_CUDA(cudaGetLastError());
+    ++g_launches;
     const size_t esz = s->d.dtype == B2ODE_F64 ? 8 : 4;
     for (int i = 0; i < s->d.nseg; ++i)
         if (s->d.seg_len[i] > 0)
@@ -1240,11 +1337,11 @@ extern "C" int b2ode_initial_step_probe(b2ode_solver *s) {
     fill_init_params(s, &p, nullptr);
     int rc;
     if (s->d.dtype == B2ODE_F64) {
-        if ((rc = launch(k_init_norms<double>, s->grid, s->stream, p))) return rc;
-        return launch(k_init_probe<double>, s->grid, s->stream, p);
+        if ((rc = launch(k_init_norms<double>, s->grid, s->stream, p, B2_FAM_INIT))) return rc;
+        return launch(k_init_probe<double>, s->grid, s->stream, p, B2_FAM_INIT);
     }
-    if ((rc = launch(k_init_norms<float>, s->grid, s->stream, p))) return rc;
-    return launch(k_init_probe<float>, s->grid, s->stream, p);
+    if ((rc = launch(k_init_norms<float>, s->grid, s->stream, p, B2_FAM_INIT))) return rc;
+    return launch(k_init_probe<float>, s->grid, s->stream, p, B2_FAM_INIT);
 }
 
 extern "C" int b2ode_initial_step_finish(b2ode_solver *s, const void *const *f1) {
@@ -1252,8 +1349,8 @@ extern "C" int b2ode_initial_step_finish(b2ode_solver *s, const void *const *f1)
     if (!f1) return fail(B2ODE_EINVAL, "f1 is null");
     InitParams p;
     fill_init_params(s, &p, f1);
-    if (s->d.dtype == B2ODE_F64) return launch(k_init_finish<double>, s->grid, s->stream, p);
-    return launch(k_init_finish<float>, s->grid, s->stream, p);
+    if (s->d.dtype == B2ODE_F64) return launch(k_init_finish<double>, s->grid, s->stream, p, B2_FAM_INIT);
+    return launch(k_init_finish<float>, s->grid, s->stream, p, B2_FAM_INIT);
 }
 
 template <typename T, int NK>
@@ -1275,7 +1372,7 @@ static int launch_stage(b2ode_solver *s, int row) {
         lists[j + 2] = s->k[kj];
     }
     p.g.vec_mask = vec_mask_of(s, lists, NK + 2);
-    return launch(k_rk_stage<T, NK>, s->grid, s->stream, p);
+    return launch(k_rk_stage<T, NK>, s->grid, s->stream, p, B2_FAM_STAGE);
 }
 
 template <typename T>
@@ -1317,8 +1414,8 @@ extern "C" int b2ode_rk_stage(b2ode_solver *s, int i, const void *const *k_new) 
         const void *const *lists[4] = {(const void *const *)s->b.y0, (const void *const *)s->b.f0,
                                        (const void *const *)s->b.ystage, s->have_prev ? s->klast_prev : nullptr};
         p.g.vec_mask = vec_mask_of(s, lists, 4);
-        if (s->d.dtype == B2ODE_F64) return launch(k_rk_stage0<double>, s->grid, s->stream, p);
-        return launch(k_rk_stage0<float>, s->grid, s->stream, p);
+        if (s->d.dtype == B2ODE_F64) return launch(k_rk_stage0<double>, s->grid, s->stream, p, B2_FAM_STAGE0);
+        return launch(k_rk_stage0<float>, s->grid, s->stream, p, B2_FAM_STAGE0);
     }
     if (s->d.dtype == B2ODE_F64) return dispatch_stage<double>(s, i);
     return dispatch_stage<float>(s, i);
@@ -1346,7 +1443,7 @@ static int launch_finalize(b2ode_solver *s) {
     p.c = s->ctrl;
     p.comm = s->comm;
     p.g.vec_mask = vec_mask_of(s, lists, NK + 2);
-    return launch(k_rk_finalize<T, NK>, s->grid, s->stream, p);
+    return launch(k_rk_finalize<T, NK>, s->grid, s->stream, p, B2_FAM_FINALIZE);
 }
 
 template <typename T, int NK>
@@ -1372,7 +1469,7 @@ static int launch_emit(b2ode_solver *s) {
     p.mid_mask = s->mid_mask;
     p.t_out = s->b.t_out;
     p.g.vec_mask = vec_mask_of(s, lists, NK + 3);
-    return launch(k_emit_quartic<T, NK>, s->grid, s->stream, p);
+    return launch(k_emit_quartic<T, NK>, s->grid, s->stream, p, B2_FAM_EMIT);
 }
 
 template <typename T>
@@ -1389,7 +1486,7 @@ static int launch_emit_tsit5(b2ode_solver *s) {
     }
     p.t_out = s->b.t_out;
     p.g.vec_mask = vec_mask_of(s, lists, 8);
-    return launch(k_emit_tsit5<T>, s->grid, s->stream, p);
+    return launch(k_emit_tsit5<T>, s->grid, s->stream, p, B2_FAM_EMIT);
 }
 
 template <typename T>
@@ -1452,7 +1549,7 @@ static int dispatch_fixed(int op, int grid, cudaStream_t st, const FixedParams &
     switch (op) {
 #define B2_CASE(OP) \
     case OP:        \
-        return launch(k_fixed<T, OP>, grid, st, p);
+        return launch(k_fixed<T, OP>, grid, st, p, B2_FAM_FIXED);
         B2_CASE(B2ODE_OP_EULER) B2_CASE(B2ODE_OP_HALF_STEP) B2_CASE(B2ODE_OP_HEUN_FINAL) B2_CASE(B2ODE_OP_RK4_S2)
         B2_CASE(B2ODE_OP_RK4_S3) B2_CASE(B2ODE_OP_RK4_S4) B2_CASE(B2ODE_OP_RK4_FINAL) B2_CASE(B2ODE_OP_LERP)
 #undef B2_CASE

@@ -85,6 +85,10 @@ class _FuncOutputs(object):
         self.seg = seg
         self.ranges = [(f.data_ptr(), f.data_ptr() + f.numel() * seg.item) for f in engine_flats]
         self.arr = _lib.PtrArray()
+        self.always_clone = False     # set once func is seen handing back the same storage twice
+        self.alias_events = 0
+        self._last = []               # outputs of the previous call, kept referenced so that pointer equality
+                                      # with a new output can only mean shared storage, never allocator reuse
 
     def collect(self, outs, live):
         seg = self.seg
@@ -104,13 +108,19 @@ class _FuncOutputs(object):
                 o = o.contiguous()
             p = o.data_ptr()
             nbytes = seg.lens[s] * seg.item
-            # a func that returns (a view of) its input, or the same buffer on every call, would be
-            # overwritten by the next stage: give it its own storage
-            if nbytes and (any(p < hi and p + nbytes > lo for lo, hi in self.ranges) or p in live):
-                o = o.clone()
-                p = o.data_ptr()
+            if nbytes:
+                # a func that hands back the storage of its previous result (a preallocated output buffer) will
+                # overwrite earlier k's: from the second call on, every result gets its own storage
+                if not self.always_clone and (p in live or any(p == q.data_ptr() for q in self._last)):
+                    self.always_clone = True
+                    self.alias_events += 1
+                # a func that returns (a view of) its input would be overwritten by the next stage
+                if self.always_clone or any(p < hi and p + nbytes > lo for lo, hi in self.ranges):
+                    o = o.clone()
+                    p = o.data_ptr()
             live.add(p)
             res.append(o)
+        self._last = res
         return res
 
     def pointers(self, tensors):
@@ -477,38 +487,44 @@ class FixedGridODESolver(object):
                 y1_views, y1_ptrs = scratch[flip]
                 flip ^= 1
             tv = times_dev[i]
-            live = set()
-            if m == "euler":
-                k1 = fo.collect(func(tv[0], y_views), live)
-                op(_lib.OP_EULER, y1_ptrs, y_ptrs, fo.pointers(k1), dt=dt)
-                nfe += 1
-            elif m == "midpoint":
-                k1 = fo.collect(func(tv[0], y_views), live)
-                op(_lib.OP_HALF_STEP, s_ptrs, y_ptrs, fo.pointers(k1), dt=dt)
-                k2 = fo.collect(func(tv[1], s_views), live)
-                op(_lib.OP_EULER, y1_ptrs, y_ptrs, fo.pointers(k2), dt=dt)
-                nfe += 2
-            elif m == "heun":
-                k1 = fo.collect(func(tv[0], y_views), live)
-                op(_lib.OP_EULER, s_ptrs, y_ptrs, fo.pointers(k1), dt=dt)
-                k2 = fo.collect(func(tv[1], s_views), live)
-                op(_lib.OP_HEUN_FINAL, y1_ptrs, y_ptrs, _ptr_array([x.data_ptr() for x in k1]),
-                   _ptr_array([x.data_ptr() for x in k2]), dt=dt)
-                nfe += 2
-            else:   # rk4, 3/8 rule (rk_common.py:73-81)
-                k1 = fo.collect(func(tv[0], y_views), live)
-                p1 = _ptr_array([x.data_ptr() for x in k1])
-                op(_lib.OP_RK4_S2, s_ptrs, y_ptrs, p1, dt=dt)
-                k2 = fo.collect(func(tv[1], s_views), live)
-                p2 = _ptr_array([x.data_ptr() for x in k2])
-                op(_lib.OP_RK4_S3, s_ptrs, y_ptrs, p1, p2, dt=dt)
-                k3 = fo.collect(func(tv[2], s_views), live)
-                p3 = _ptr_array([x.data_ptr() for x in k3])
-                op(_lib.OP_RK4_S4, s_ptrs, y_ptrs, p1, p2, p3, dt=dt)
-                k4 = fo.collect(func(tv[3], s_views), live)
-                p4 = _ptr_array([x.data_ptr() for x in k4])
-                op(_lib.OP_RK4_FINAL, y1_ptrs, y_ptrs, p1, p2, p3, p4, dt=dt)
-                nfe += 4
+            while True:
+                live = set()
+                alias0 = fo.alias_events
+                if m == "euler":
+                    k1 = fo.collect(func(tv[0], y_views), live)
+                    op(_lib.OP_EULER, y1_ptrs, y_ptrs, fo.pointers(k1), dt=dt)
+                    nfe += 1
+                elif m == "midpoint":
+                    k1 = fo.collect(func(tv[0], y_views), live)
+                    op(_lib.OP_HALF_STEP, s_ptrs, y_ptrs, fo.pointers(k1), dt=dt)
+                    k2 = fo.collect(func(tv[1], s_views), live)
+                    op(_lib.OP_EULER, y1_ptrs, y_ptrs, fo.pointers(k2), dt=dt)
+                    nfe += 2
+                elif m == "heun":
+                    k1 = fo.collect(func(tv[0], y_views), live)
+                    op(_lib.OP_EULER, s_ptrs, y_ptrs, fo.pointers(k1), dt=dt)
+                    k2 = fo.collect(func(tv[1], s_views), live)
+                    op(_lib.OP_HEUN_FINAL, y1_ptrs, y_ptrs, _ptr_array([x.data_ptr() for x in k1]),
+                       _ptr_array([x.data_ptr() for x in k2]), dt=dt)
+                    nfe += 2
+                else:   # rk4, 3/8 rule (rk_common.py:73-81)
+                    k1 = fo.collect(func(tv[0], y_views), live)
+                    p1 = _ptr_array([x.data_ptr() for x in k1])
+                    op(_lib.OP_RK4_S2, s_ptrs, y_ptrs, p1, dt=dt)
+                    k2 = fo.collect(func(tv[1], s_views), live)
+                    p2 = _ptr_array([x.data_ptr() for x in k2])
+                    op(_lib.OP_RK4_S3, s_ptrs, y_ptrs, p1, p2, dt=dt)
+                    k3 = fo.collect(func(tv[2], s_views), live)
+                    p3 = _ptr_array([x.data_ptr() for x in k3])
+                    op(_lib.OP_RK4_S4, s_ptrs, y_ptrs, p1, p2, p3, dt=dt)
+                    k4 = fo.collect(func(tv[3], s_views), live)
+                    p4 = _ptr_array([x.data_ptr() for x in k4])
+                    op(_lib.OP_RK4_FINAL, y1_ptrs, y_ptrs, p1, p2, p3, p4, dt=dt)
+                    nfe += 4
+                if fo.alias_events == alias0:
+                    break
+                # func turned out to reuse its output storage inside this step: earlier k's were overwritten;
+                # from now on results are cloned -- redo the step once (y0 of the cell is untouched)
             # interior outputs: linear interpolation (solvers.py:106-115)
             for jj in range(j, j_hi - (1 if ends_on_output else 0)):
                 op(_lib.OP_LERP, row_ptrs(jj), y_ptrs, y1_ptrs, s1=npdt(t1) - npdt(t0), s2=npdt(t_np[jj]) - npdt(t0))
