@@ -77,7 +77,9 @@ typedef struct b2ode_state {
     uint32_t ticket;        /* last-block-done counter of the reduction kernels          */
     uint32_t reserved_u;
     uint64_t xseq;          /* cross-GPU exchange sequence number                        */
-    double reserved_t[15];
+    uint64_t klast[B2ODE_MAXSEG]; /* device address of k_{s-1} of the attempt just finalized, per segment:
+                                     read by the next attempt's stage 0 when it commits an accepted step  */
+    double reserved_t[7];
 } b2ode_state;
 
 /* Description of an adaptive Runge-Kutta solve.  Restates `_ButcherTableau` (tfdiffeq/rk_common.py:5) plus
@@ -130,6 +132,9 @@ size_t b2ode_workspace_bytes(const b2ode_adaptive_desc *desc);
 int b2ode_adaptive_create(b2ode_solver **out, const b2ode_adaptive_desc *desc);
 void b2ode_adaptive_destroy(b2ode_solver *s);
 int b2ode_adaptive_bind(b2ode_solver *s, const b2ode_adaptive_buffers *buf, void *cuda_stream);
+/* Redirect subsequent launches to another stream (e.g. the stream a CUDA graph of one attempt is captured on:
+ * no kernel argument changes between attempts, so an attempt -- func included -- can be captured once and replayed). */
+int b2ode_set_stream(b2ode_solver *s, void *cuda_stream);
 
 /* Replaces Dopri5Solver.before_integrate's state construction (dopri5.py:78): zero the state, set
  * t0 = t1 = t_start (= t_out[0]), copy y0 into out[.][0], write the stage-time scalars.  If first_step is not NaN it

@@ -235,7 +235,12 @@ def test_nonfinite_state_and_underflow_raise_like_the_reference():
     t = torch.tensor([0., 1.])
     bad = y0.clone()
     bad[3] = float("inf")
+    # with a given first step the first assertion that can fail is the finite check (dopri5.py:100) ...
     with pytest.raises(AssertionError, match="non-finite values in state"):
+        tfd().odeint(lambda t, y: -y, bad, t, method="dopri5", options=dict(first_step=0.1))
+    # ... without it, the initial-step heuristic already produces dt = NaN and the reference's FIRST assertion,
+    # `t0 + dt > t0` (dopri5.py:98), is the one that fires
+    with pytest.raises(AssertionError, match="underflow in dt"):
         tfd().odeint(lambda t, y: -y, bad, t, method="dopri5")
     with pytest.raises(AssertionError, match="underflow in dt"):
         # a derivative that is NaN makes every error ratio NaN -> dt becomes NaN -> `t0 + dt > t0` fails
@@ -326,3 +331,30 @@ def test_fixed_grid_func_reusing_its_output_buffer(method):
     a = tfd().odeint(lambda t, y: y * -0.7, y0, t, method=method)
     b = tfd().odeint(reuse, y0, t, method=method)
     assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("method,kw", [("dopri5", {}), ("dopri8", dict(rtol=1e-9, atol=1e-9)), ("adaptive_heun", dict(rtol=1e-3, atol=1e-5))])
+def test_cuda_graph_replay_is_bit_identical_to_eager(method, kw):
+    """options={'cuda_graph': True} captures one attempt (func included) and replays it; every address and
+    every kernel argument is static, so the results must be identical to the eager path bit for bit."""
+    rng = np.random.default_rng(11)
+    y0 = torch.tensor(np.array([1., 1., 1.]) + 0.1 * rng.standard_normal((2048, 3)), device=DEV)
+    t = torch.arange(41, dtype=torch.float64) * (0.01 if method != "adaptive_heun" else 0.001)
+    f = PROBLEMS["lorenz"](backend="torch", device=DEV)
+    a = tfd().odeint(f, y0, t, method=method, **kw)
+    sa = dict(tfd().last_stats)
+    b = tfd().odeint(f, y0, t, method=method, options=dict(cuda_graph=True), **kw)
+    sb = dict(tfd().last_stats)
+    assert sb["cuda_graph"] and not sa["cuda_graph"]
+    assert (sa["n_accepted"], sa["n_rejected"], sa["nfe"]) == (sb["n_accepted"], sb["n_rejected"], sb["nfe"])
+    assert torch.equal(a, b)
+
+
+def test_cuda_graph_with_tuple_state_and_reverse_time():
+    f = PROBLEMS["tuple_decay"]()
+    y0 = (torch.linspace(1., 2., 7, dtype=torch.float64, device=DEV), torch.linspace(0.5, 1.5, 33, dtype=torch.float64, device=DEV))
+    t = torch.linspace(1., 0., 5)
+    a = tfd().odeint(f, y0, t, method="dopri5")
+    b = tfd().odeint(f, y0, t, method="dopri5", options=dict(cuda_graph=True))
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)

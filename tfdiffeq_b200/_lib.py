@@ -26,7 +26,7 @@ class State(C.Structure):
                 ("n_acc", C.c_uint64), ("n_rej", C.c_uint64), ("attempt", C.c_uint64), ("n_steps_adv", C.c_int64),
                 ("accept", C.c_int32), ("done", C.c_int32), ("status", C.c_uint32), ("cursor", C.c_int32),
                 ("emit_j0", C.c_int32), ("emit_j1", C.c_int32), ("ticket", C.c_uint32), ("reserved_u", C.c_uint32),
-                ("xseq", C.c_uint64), ("reserved_t", C.c_double * 15)]
+                ("xseq", C.c_uint64), ("klast", C.c_uint64 * MAXSEG), ("reserved_t", C.c_double * 7)]
 
 
 class AdaptiveDesc(C.Structure):
@@ -62,6 +62,7 @@ _SIGNATURES = {
     "b2ode_adaptive_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(AdaptiveDesc)]),
     "b2ode_adaptive_destroy": (None, [C.c_void_p]),
     "b2ode_adaptive_bind": (C.c_int, [C.c_void_p, C.POINTER(AdaptiveBuffers), C.c_void_p]),
+    "b2ode_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "b2ode_adaptive_init": (C.c_int, [C.c_void_p, C.c_double, C.c_double]),
     "b2ode_initial_step_probe": (C.c_int, [C.c_void_p]),
     "b2ode_initial_step_finish": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),

@@ -381,7 +381,6 @@ struct Stage0Params {
     void *y0[B2ODE_MAXSEG];
     void *f0[B2ODE_MAXSEG];
     void *ystage[B2ODE_MAXSEG];
-    const void *klast[B2ODE_MAXSEG];   // k_{s-1} of the previous attempt (may be null before the first attempt)
     double coef;
 };
 
@@ -390,11 +389,14 @@ __global__ void __launch_bounds__(kThreads) k_rk_stage0(const __grid_constant__ 
     const int s = find_seg(p.g, blockIdx.x);
     const int bl = blockIdx.x - p.g.blk_begin[s], nb = p.g.blk_begin[s + 1] - p.g.blk_begin[s];
     const T c = Ar<T>::mul((T)p.st->dt, (T)p.coef);
-    const bool commit = p.st->accept != 0 && p.klast[s] != nullptr;
+    // k_{s-1} of the previous attempt: its address was left in the state by that attempt's finalize kernel
+    const T *kl = reinterpret_cast<const T *>(p.st->klast[s]);
+    const bool commit = p.st->accept != 0 && kl != nullptr;
     T *y0 = (T *)p.y0[s], *f0 = (T *)p.f0[s], *ys = (T *)p.ystage[s];
-    const T *kl = (const T *)p.klast[s];
+    // kl is a func output whose address the host never sees here: check its 16-byte alignment on the device
+    const bool vec_ok = ((p.g.vec_mask >> s) & 1u) && ((reinterpret_cast<unsigned long long>(kl) & 15ull) == 0);
     if (commit) {
-        seg_for_each<T>(p.g.n[s], (p.g.vec_mask >> s) & 1u, bl, nb, [&](auto vt, long long i) {
+        seg_for_each<T>(p.g.n[s], vec_ok, bl, nb, [&](auto vt, long long i) {
             constexpr int V = decltype(vt)::value;
             Pack<T, V> yv = ld_pack<T, V>(ys, i);
             Pack<T, V> fv = ld_pack<T, V>(kl, i);
@@ -430,16 +432,26 @@ struct FinalizeParams {
     const void *y1[B2ODE_MAXSEG];
     const void *k[NK][B2ODE_MAXSEG];
     double coef[NK];
+    const void *klast[B2ODE_MAXSEG];   // k_{s-1} (= f1) of this attempt, recorded in the state for the next stage 0
     CtrlParams c;
     CommParams comm;
 };
 
-// misc.py:250-264 + dopri5.py:106-120 + misc.py:267-287 (or tsit5.py:53-62,134-138), one thread.
+// misc.py:250-264 + dopri5.py:106-120 + misc.py:267-287 (or tsit5.py:53-62,134-138).
+// Called by ONE WARP (the first warp of the last block): every lane evaluates the (cheap) scalar controller
+// redundantly, the output-cursor search and the stage-time writes are spread over the lanes, lane 0 stores.
+// The state is read once, up front, so the serial tail of the finalize kernel is two dependent memory
+// round trips (state, then t_out) instead of a dozen.
 template <typename T>
-__device__ void control_step(b2ode_state *st, const CtrlParams &c, const Partial *tot, int nseg) {
+__device__ void control_step(b2ode_state *st, const CtrlParams &c, const Partial *tot, int nseg,
+                             const void *const *klast) {
+    const int lane = threadIdx.x & 31;
     const double dt = st->dt;
     const double t_cur = st->t1;
     unsigned status = st->status;
+    int cur = st->cursor;
+    const long long nadv0 = st->n_steps_adv;
+    const unsigned long long n_acc = st->n_acc, n_rej = st->n_rej, attempt = st->attempt;
     bool accept = true;
     double m = 0.0;
     double pooled = 0.0;
@@ -477,39 +489,53 @@ __device__ void control_step(b2ode_state *st, const CtrlParams &c, const Partial
         dt_next = dt / factor;
     }
     if (bad0) status |= B2ODE_ST_NONFINITE;   // the reference asserts this before taking the step
-    st->dt_last = dt;
-    st->msr_max = m;
-    if (accept) {
-        st->t0 = t_cur;
-        st->t1 = t_cur + dt;
-        st->n_acc += 1;
-    } else {
-        st->n_rej += 1;
-    }
-    st->accept = accept ? 1 : 0;
-    st->attempt += 1;
-    st->dt = dt_next;
-    // outputs inside the accepted step: every t_out[j] with t_out[j] <= t1 (advance(): `while next_t > t1`)
-    int cur = st->cursor;
+    const double t1_new = accept ? t_cur + dt : t_cur;
+    // outputs inside the accepted step: every t_out[j] with t_out[j] <= t1 (advance(): `while next_t > t1`);
+    // t_out is increasing, so each 32-wide ballot is a run of ones followed by zeros
     const int j0 = cur;
     if (accept && !bad0) {
-        const double t1 = st->t1;
-        while (cur < c.n_out && c.t_out[cur] <= t1) ++cur;
+        for (;;) {
+            const int j = cur + lane;
+            const bool in = (j < c.n_out) && (c.t_out[j] <= t1_new);
+            const unsigned b = __ballot_sync(0xffffffffu, in);
+            const int cnt = (b == 0xffffffffu) ? 32 : (__ffs((int)~b) - 1);
+            cur += cnt;
+            if (cnt < 32) break;
+        }
     }
-    st->cursor = cur;
-    st->emit_j0 = j0;
-    st->emit_j1 = cur;
-    long long nadv = (cur > j0) ? 0 : st->n_steps_adv + 1;
-    st->n_steps_adv = nadv;
+    const long long nadv = (cur > j0) ? 0 : nadv0 + 1;
     int done = (cur >= c.n_out) ? 1 : 0;
     if (!done) {
         if (nadv >= c.max_num_steps) status |= B2ODE_ST_MAXSTEPS;        // dopri5.py:85
-        if (!(st->t1 + dt_next > st->t1)) status |= B2ODE_ST_UNDERFLOW;  // dopri5.py:98 (NaN dt lands here too)
+        if (!(t1_new + dt_next > t1_new)) status |= B2ODE_ST_UNDERFLOW;  // dopri5.py:98 (NaN dt lands here too)
     }
     if (status) done = 1;
-    st->status = status;
-    st->done = done;
-    write_stage_times<T>(c, st->t1, dt_next);
+    if (lane == 0) {
+        st->dt_last = dt;
+        st->msr_max = m;
+        if (accept) {
+            st->t0 = t_cur;
+            st->t1 = t1_new;
+            st->n_acc = n_acc + 1;
+        } else {
+            st->n_rej = n_rej + 1;
+        }
+        st->accept = accept ? 1 : 0;
+        st->attempt = attempt + 1;
+        st->dt = dt_next;
+        st->cursor = cur;
+        st->emit_j0 = j0;
+        st->emit_j1 = cur;
+        st->n_steps_adv = nadv;
+        st->status = status;
+        st->done = done;
+    }
+    if (lane < nseg) st->klast[lane] = reinterpret_cast<unsigned long long>(klast[lane]);
+    // stage times of the next attempt (rk_common.py:45-50), one lane each
+    if (lane + 1 < c.n_k) {
+        T *ts = reinterpret_cast<T *>(c.tstage);
+        ts[lane] = Ar<T>::add((T)t1_new, Ar<T>::mul((T)c.alpha[lane], (T)dt_next));
+    }
 }
 
 template <typename T, int NK>
@@ -559,9 +585,9 @@ __global__ void __launch_bounds__(kThreads) k_rk_finalize(const __grid_constant_
     __shared__ Partial tot[B2ODE_MAXSEG];
     reduce_partials<MM>(p.g, p.part, tot);
     group_combine<MM>(p.comm, p.st, tot, p.g.nseg);
-    if (threadIdx.x == 0) {
-        control_step<T>(p.st, p.c, tot, p.g.nseg);
-        p.st->ticket = 0;
+    if (threadIdx.x < 32) {
+        control_step<T>(p.st, p.c, tot, p.g.nseg, p.klast);
+        if (threadIdx.x == 0) p.st->ticket = 0;
     }
 }
 
@@ -986,8 +1012,6 @@ struct b2ode_solver {
     CtrlParams ctrl;
     CommParams comm;
     const void *k[B2ODE_MAXK][B2ODE_MAXSEG];   // k pointers of the current attempt (k[0] = f0)
-    const void *klast_prev[B2ODE_MAXSEG];      // k_{s-1} of the previous attempt
-    bool have_prev;
     // compacted (zero-skipping) coefficient lists
     int st_nk[B2ODE_MAXK];
     int st_idx[B2ODE_MAXK][B2ODE_MAXK];
@@ -1143,8 +1167,13 @@ extern "C" int b2ode_adaptive_bind(b2ode_solver *s, const b2ode_adaptive_buffers
     s->ctrl.t_out = buf->t_out;
     s->ctrl.tstage = buf->tstage;
     for (int i = 0; i < s->d.nseg; ++i) s->k[0][i] = buf->f0[i];
-    s->have_prev = false;
     s->bound = true;
+    return 0;
+}
+
+extern "C" int b2ode_set_stream(b2ode_solver *s, void *cuda_stream) {
+    if (!s) return fail(B2ODE_EINVAL, "null solver");
+    s->stream = (cudaStream_t)cuda_stream;
     return 0;
 }
 
@@ -1195,7 +1224,11 @@ template <typename K, typename P>
 static int launch(K kernel, int grid, cudaStream_t st, const P &p, int fam = -1) {
     if (grid <= 0) return 0;
     Timing *tm = g_timing;
-    const bool timed = tm && fam >= 0 && ((tm->mask >> fam) & 1u) && tm->n[fam] < kMaxTimed;
+    bool timed = tm && fam >= 0 && ((tm->mask >> fam) & 1u) && tm->n[fam] < kMaxTimed;
+    if (timed) {   // event pairs cannot be read back from a captured graph: only time eager launches
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) timed = false;
+    }
     if (timed) B2_CUDA(cudaEventRecord(tm->ev[fam][tm->n[fam]][0], st));
     kernel<<<grid, kThreads, 0, st>>>(p);
     B2_CUDA(cudaGetLastError());
@@ -1296,7 +1329,6 @@ extern "C" int b2ode_adaptive_init(b2ode_solver *s, double t_start, double first
     for (int i = 0; i < s->d.nseg; ++i)
         if (s->d.seg_len[i] > 0)
             B2_CUDA(cudaMemcpyAsync(s->b.out[i], s->b.y0[i], (size_t)s->d.seg_len[i] * esz, cudaMemcpyDeviceToDevice, s->stream));
-    s->have_prev = false;
     for (int i = 0; i < s->d.nseg; ++i) s->k[0][i] = s->b.f0[i];
     return 0;
 }
@@ -1408,12 +1440,11 @@ extern "C" int b2ode_rk_stage(b2ode_solver *s, int i, const void *const *k_new) 
             p.y0[sg] = s->b.y0[sg];
             p.f0[sg] = s->b.f0[sg];
             p.ystage[sg] = s->b.ystage[sg];
-            p.klast[sg] = s->have_prev ? s->klast_prev[sg] : nullptr;
         }
         p.coef = s->d.beta[0][0];
-        const void *const *lists[4] = {(const void *const *)s->b.y0, (const void *const *)s->b.f0,
-                                       (const void *const *)s->b.ystage, s->have_prev ? s->klast_prev : nullptr};
-        p.g.vec_mask = vec_mask_of(s, lists, 4);
+        const void *const *lists[3] = {(const void *const *)s->b.y0, (const void *const *)s->b.f0,
+                                       (const void *const *)s->b.ystage};
+        p.g.vec_mask = vec_mask_of(s, lists, 3);
         if (s->d.dtype == B2ODE_F64) return launch(k_rk_stage0<double>, s->grid, s->stream, p, B2_FAM_STAGE0);
         return launch(k_rk_stage0<float>, s->grid, s->stream, p, B2_FAM_STAGE0);
     }
@@ -1440,6 +1471,7 @@ static int launch_finalize(b2ode_solver *s) {
         for (int sg = 0; sg < B2ODE_MAXSEG; ++sg) p.k[j][sg] = s->k[kj][sg];
         lists[j + 2] = s->k[kj];
     }
+    for (int sg = 0; sg < B2ODE_MAXSEG; ++sg) p.klast[sg] = s->k[s->d.n_k - 1][sg];
     p.c = s->ctrl;
     p.comm = s->comm;
     p.g.vec_mask = vec_mask_of(s, lists, NK + 2);
@@ -1523,10 +1555,7 @@ extern "C" int b2ode_rk_finalize(b2ode_solver *s, const void *const *k_last) {
         s->k[nk - 1][sg] = k_last[sg];
     }
     int rc = (s->d.dtype == B2ODE_F64) ? dispatch_finalize<double>(s) : dispatch_finalize<float>(s);
-    if (rc) return rc;
-    for (int sg = 0; sg < s->d.nseg; ++sg) s->klast_prev[sg] = k_last[sg];
-    s->have_prev = true;
-    return 0;
+    return rc;
 }
 
 extern "C" int b2ode_poll_async(b2ode_solver *s, b2ode_state *host_dst) {

@@ -139,6 +139,9 @@ class AdaptiveStepsizeODESolver(object):
     def __init__(self, func, y0, rtol, atol, first_step=None, safety=0.9, ifactor=10.0, dfactor=0.2,
                  max_num_steps=2 ** 31 - 1, **unused_kwargs):
         self.comm = unused_kwargs.pop("shared_step_group", None)     # extension: SURVEY 8(e)
+        # extension: capture one attempt (the func calls included) into a CUDA graph and replay it.  Opt-in,
+        # because python-side effects of func (e.g. an `nfe` counter on the module) happen once, at capture.
+        self.cuda_graph = bool(unused_kwargs.pop("cuda_graph", False))
         _handle_unused_kwargs(self, unused_kwargs)
         del unused_kwargs
         self.func = func
@@ -274,7 +277,27 @@ class AdaptiveStepsizeODESolver(object):
             tstage_views = [tstage[i] for i in range(nk - 1)]
             func = self.func
             rk_stage, rk_finalize, poll_async = lib.b2ode_rk_stage, lib.b2ode_rk_finalize, lib.b2ode_poll_async
-            prev_last = None
+
+            def run_attempt():
+                """Enqueue one attempt: stage i -> func -> ... -> finalize (+ dense output).  No kernel argument
+                depends on dt / accept / the output cursor: they live in the device state."""
+                live = set()
+                ks = []           # every k of the attempt stays referenced until its last reader is enqueued
+                check(rk_stage(handle, 0, None))
+                k = fo.collect(func(tstage_views[0], s_views), live)
+                ks.append(k)
+                for i in range(1, nk - 1):
+                    check(rk_stage(handle, i, fo.pointers(k)))
+                    k = fo.collect(func(tstage_views[i], s_views), live)
+                    ks.append(k)
+                if not tab.fsal:
+                    check(rk_stage(handle, nk - 1, fo.pointers(k)))
+                check(rk_finalize(handle, fo.pointers(k)))
+                return ks
+
+            graph = None          # torch.cuda.CUDAGraph of one attempt (cuda_graph=True), captured after attempt 1
+            graph_ks = None
+            prev_last = None      # k_{s-1}: read once more by the next attempt's stage 0 (the commit)
             while not known.done:
                 ahead = n_enq - known_at
                 go = ahead == 0
@@ -284,20 +307,20 @@ class AdaptiveStepsizeODESolver(object):
                     reach = known.dt * (ahead if g == 1.0 else (g ** ahead - 1.0) / (g - 1.0))
                     go = (known.t1 + reach) < t_end and known.status == 0
                 if go:
-                    live = set()
-                    ks = []           # every k of the attempt stays referenced until its last reader is enqueued
-                    check(rk_stage(handle, 0, None))
-                    k = fo.collect(func(tstage_views[0], s_views), live)
-                    ks.append(k)
-                    for i in range(1, nk - 1):
-                        check(rk_stage(handle, i, fo.pointers(k)))
-                        k = fo.collect(func(tstage_views[i], s_views), live)
-                        ks.append(k)
-                    if not tab.fsal:
-                        check(rk_stage(handle, nk - 1, fo.pointers(k)))
-                    check(rk_finalize(handle, fo.pointers(k)))
-                    prev_last = k     # k_{s-1} is read once more by the next attempt's stage 0 (the commit)
-                    del ks
+                    if graph is not None:
+                        graph.replay()
+                    elif self.cuda_graph and n_enq >= 1:
+                        # attempt 1 ran eagerly (warm-up); capture attempt 2 and replay it from now on
+                        graph = torch.cuda.CUDAGraph()
+                        try:
+                            with torch.cuda.graph(graph):
+                                check(lib.b2ode_set_stream(handle, C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+                                graph_ks = run_attempt()
+                        finally:
+                            check(lib.b2ode_set_stream(handle, C.c_void_p(stream.cuda_stream)))
+                        graph.replay()
+                    else:
+                        prev_last = run_attempt()[-1]
                     nfe += nk - 1
                     slot = n_enq % D
                     n_enq += 1
@@ -311,15 +334,15 @@ class AdaptiveStepsizeODESolver(object):
                     known_at, slot = pending.popleft()
                     events[slot].synchronize()
                     known = _lib.State.from_buffer_copy(slots[slot])
-            del prev_last
             final = known
             self.stats = dict(n_accepted=int(final.n_acc), n_rejected=int(final.n_rej), nfe=nfe,
-                              attempts_enqueued=n_enq, status=int(final.status))
+                              attempts_enqueued=n_enq, status=int(final.status), cuda_graph=graph is not None)
             last_stats.clear()
             last_stats.update(self.stats)
             if final.status:
                 self._raise(final, s_views, y0_views)
             stream.synchronize()      # outputs are complete; also keeps Y0/F0/S alive until the kernels ran
+            del prev_last, graph_ks, graph
         finally:
             lib.b2ode_adaptive_destroy(handle)
         return tuple(outs)
