@@ -1,0 +1,135 @@
+"""GPU: odeint_adjoint (reference tfdiffeq/adjoint.py).  Gradients from the adjoint solve -- the
+same kernels on the augmented tuple state (y, adj_y, adj_t, adj_params) -- are checked against central finite
+differences of the loss computed with the forward engine (the reference's own gradient tests compare the
+adjoint against tape back-propagation, tests/gradient_tests.py:69-165, with tolerances 1.2e-7 .. 2e-3)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device("cuda:0")
+
+
+def tfd():
+    import tfdiffeq_b200
+    return tfdiffeq_b200
+
+
+class Spiral3(nn.Module):
+    """tests/gradient_tests.py:106-123: y' = (y**3) @ A with a trainable A."""
+
+    def __init__(self):
+        super().__init__()
+        self.A = nn.Parameter(torch.tensor([[-0.1, 2.0], [-2.0, -0.1]], dtype=torch.float64))
+        self.unused = nn.Parameter(torch.zeros(3, dtype=torch.float64))    # gets a zero gradient (reference: None)
+
+    def forward(self, t, y):
+        return (y ** 3) @ self.A
+
+
+class TimeDep(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.w = nn.Parameter(torch.tensor([0.7, -0.3, 0.2], dtype=torch.float64))
+
+    def forward(self, t, y):
+        return torch.tanh(y * self.w) * torch.cos(t) - 0.1 * y
+
+
+def _loss(model, y0, t, adjoint, **kw):
+    if adjoint:
+        ys = tfd().odeint_adjoint(model, y0, t, **kw)
+    else:
+        with torch.no_grad():
+            ys = tfd().odeint(model, y0, t, **kw)
+    return (ys[-1] ** 2).sum() + (ys[1] * 0.5).sum()
+
+
+def _fd(fn, x, idx, eps):
+    old = x.data[idx].item()
+    x.data[idx] = old + eps
+    p = float(fn())
+    x.data[idx] = old - eps
+    m = float(fn())
+    x.data[idx] = old
+    return (p - m) / (2 * eps)
+
+
+def test_adjoint_forward_equals_odeint():
+    m = Spiral3().to(DEV)
+    y0 = torch.tensor([[2.0, 0.0]], dtype=torch.float64, device=DEV)
+    t = torch.linspace(0., 2., 5, dtype=torch.float64)
+    a = tfd().odeint_adjoint(m, y0, t, rtol=1e-8, atol=1e-10, method="dopri5")
+    b = tfd().odeint(m, y0, t, rtol=1e-8, atol=1e-10, method="dopri5")
+    assert torch.equal(a.detach(), b)
+    with pytest.raises(ValueError):
+        tfd().odeint_adjoint(lambda t, y: y, y0, t)
+
+
+@pytest.mark.parametrize("method", ["dopri5", "dopri8", "rk4"])
+def test_adjoint_gradients_match_finite_differences(method):
+    torch.manual_seed(0)
+    m = Spiral3().to(DEV)
+    y0 = torch.tensor([[2.0, 0.0], [1.0, 0.5]], dtype=torch.float64, device=DEV, requires_grad=True)
+    t = torch.linspace(0., 1.5, 4 if method != "rk4" else 61, dtype=torch.float64)
+    kw = dict(rtol=1e-10, atol=1e-12, method=method)
+    loss = _loss(m, y0, t, True, **kw)
+    loss.backward()
+    gA, gy = m.A.grad.clone(), y0.grad.clone()
+    assert m.unused.grad is None or float(m.unused.grad.abs().max()) == 0.0
+    fn = lambda: _loss(m, y0.detach(), t, False, **kw)            # noqa: E731
+    tol = 2e-6 if method != "rk4" else 2e-3       # rk4's adjoint is discretise-then-... no: optimise-then-discretise
+    for idx in [(0, 0), (0, 1), (1, 0), (1, 1)]:
+        fd = _fd(fn, m.A, idx, 1e-5)
+        assert abs(fd - gA[idx].item()) <= tol * max(1.0, abs(fd)), ("A", idx, fd, gA[idx].item())
+    y0d = y0.detach().clone()
+    fn2 = lambda: _loss(m, y0d, t, False, **kw)                   # noqa: E731
+    for idx in [(0, 0), (1, 1)]:
+        fd = _fd(fn2, y0d, idx, 1e-5)
+        assert abs(fd - gy[idx].item()) <= tol * max(1.0, abs(fd)), ("y0", idx, fd, gy[idx].item())
+
+
+def test_adjoint_time_gradients_and_time_dependent_func():
+    m = TimeDep().to(DEV)
+    y0 = torch.tensor([0.5, -1.0, 2.0], dtype=torch.float64, device=DEV, requires_grad=True)
+    t = torch.tensor([0.0, 0.4, 1.1, 1.7], dtype=torch.float64, device=DEV, requires_grad=True)
+    kw = dict(rtol=1e-10, atol=1e-12, method="dopri5")
+    loss = _loss(m, y0, t, True, **kw)
+    loss.backward()
+    gt, gw = t.grad.clone(), m.w.grad.clone()
+    td = t.detach().clone()
+    fn = lambda: _loss(m, y0.detach(), td, False, **kw)           # noqa: E731
+    for j in range(4):
+        fd = _fd(fn, td, (j,), 1e-5)
+        assert abs(fd - gt[j].item()) <= 5e-6 * max(1.0, abs(fd)), ("t", j, fd, gt[j].item())
+    for j in range(3):
+        fd = _fd(fn, m.w, (j,), 1e-5)
+        assert abs(fd - gw[j].item()) <= 5e-6 * max(1.0, abs(fd)), ("w", j, fd, gw[j].item())
+
+
+def test_adjoint_tuple_state():
+    class Two(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.a = nn.Parameter(torch.tensor(0.3, dtype=torch.float64))
+
+        def forward(self, t, yz):
+            y, z = yz
+            return (-self.a * y + z.mean(), -2.0 * z * self.a)
+    m = Two().to(DEV)
+    y0 = (torch.tensor([1.0, 2.0], dtype=torch.float64, device=DEV, requires_grad=True),
+          torch.tensor([0.5, 0.1, -0.2], dtype=torch.float64, device=DEV, requires_grad=True))
+    t = torch.linspace(0., 1., 3, dtype=torch.float64)
+    kw = dict(rtol=1e-10, atol=1e-12, method="dopri5")
+    ys = tfd().odeint_adjoint(m, y0, t, **kw)
+    loss = (ys[0][-1] ** 2).sum() + ys[1][-1].sum()
+    loss.backward()
+    ga = m.a.grad.item()
+
+    def fn():
+        with torch.no_grad():
+            o = tfd().odeint(m, tuple(v.detach() for v in y0), t, **kw)
+        return (o[0][-1] ** 2).sum() + o[1][-1].sum()
+    fd = _fd(fn, m.a, (), 1e-5)
+    assert abs(fd - ga) <= 5e-6 * max(1.0, abs(fd)), (fd, ga)
