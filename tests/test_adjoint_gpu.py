@@ -79,7 +79,11 @@ def test_adjoint_gradients_match_finite_differences(method):
     gA, gy = m.A.grad.clone(), y0.grad.clone()
     assert m.unused.grad is None or float(m.unused.grad.abs().max()) == 0.0
     fn = lambda: _loss(m, y0.detach(), t, False, **kw)            # noqa: E731
-    tol = 2e-6 if method != "rk4" else 2e-3       # rk4's adjoint is discretise-then-... no: optimise-then-discretise
+    # dopri5 at rtol 1e-10 agrees to ~1e-7.  dopri8's dense output is only 4th order (dopri8.py:82-87): with its
+    # large steps the interior output ys[1] carries ~1e-5 interpolation error that the continuous adjoint does
+    # not differentiate; rk4 is optimise-then-discretise on a fixed grid.  The reference's own adjoint tests
+    # use 1e-4 .. 2e-3 (tests/gradient_tests.py:163-165).
+    tol = {"dopri5": 2e-6, "dopri8": 1e-4, "rk4": 2e-3}[method]
     for idx in [(0, 0), (0, 1), (1, 0), (1, 1)]:
         fd = _fd(fn, m.A, idx, 1e-5)
         assert abs(fd - gA[idx].item()) <= tol * max(1.0, abs(fd)), ("A", idx, fd, gA[idx].item())
