@@ -189,6 +189,24 @@ int b2ode_mailbox_destroy(void *dev_ptr);
 /* element count of every segment over the WHOLE group (the mean in misc.py:262 is over all ranks' elements) */
 int b2ode_comm_set_global_len(b2ode_solver *s, const int64_t *global_len);
 
+/* ---- built-in right-hand sides: the whole adaptive solve in one persistent kernel ---------- */
+
+#define B2ODE_RHS_LORENZ 0          /* (B,3): s(y-x), x(r-z)-y, xy-bz ; params {sigma, beta, rho}   examples/lorenz_attractor.py:20-37 */
+#define B2ODE_RHS_LOTKA_VOLTERRA 1  /* (B,2): ax-bxz, -cz+dxz        ; params {a, b, c, d}          README.md:67-81                   */
+
+/* Replaces the WHOLE of AdaptiveStepsizeODESolver.integrate (tfdiffeq/solvers.py:27-35) for a func the library
+ * knows: every trajectory stays in one thread's registers (state + all k's) for the entire solve, one grid-wide
+ * reduction per attempt keeps the reference's single shared step / global scalar tolerance; HBM traffic is the
+ * (n_out, B, D) solution slab only.  Same arithmetic and operation order as the generic kernels.  `desc` must
+ * describe ONE segment of B*D elements and a quartic dense output; `state` receives the final b2ode_state.
+ * Returns B2ODE_ENOMEM when the batch exceeds what the device can keep co-resident (caller falls back to the
+ * generic path).  time_sign = -1 integrates the reversed system of tfdiffeq/misc.py:318-321. */
+size_t b2ode_fused_workspace_bytes(int64_t n_trajectories);
+int b2ode_fused_solve(const b2ode_adaptive_desc *desc, int rhs_kind, const double *rhs_params, int n_rhs_params,
+                      double time_sign, const void *y0, void *out, const double *t_out, int n_out, double t_start,
+                      double first_step, void *state, void *workspace, size_t workspace_bytes, int rank, int nranks,
+                      void *const *mailboxes, int64_t n_traj_global, void *cuda_stream);
+
 /* ---- measurement hooks (bench.py) --------------------------------------------------------------------- */
 unsigned long long b2ode_launch_count(void);            /* kernels launched by this library so far          */
 int b2ode_timing_enable(unsigned family_mask);          /* CUDA-event timing per kernel family; 0 = off     */

@@ -42,6 +42,15 @@ def _worker(rank, world, port, q):
         s_part = dict(tfd.last_stats)
         err = float((part - full[:, lo:hi]).abs().max())
         res[method] = (err, s_full["n_accepted"], s_full["n_rejected"], s_part["n_accepted"], s_part["n_rejected"])
+    # the persistent fused kernel (built-in right-hand side) with the same group
+    fb = tfd.rhs.Lorenz()
+    full = tfd.odeint(fb, torch.tensor(y0, device=dev), t, method="dopri5")
+    s_full = dict(tfd.last_stats)
+    part = tfd.odeint(fb, torch.tensor(y0[lo:hi], device=dev), t, method="dopri5", options={"shared_step_group": group})
+    s_part = dict(tfd.last_stats)
+    assert s_full["fused_rhs"] and s_part["fused_rhs"]
+    res["fused_dopri5"] = (float((part - full[:, lo:hi]).abs().max()), s_full["n_accepted"], s_full["n_rejected"],
+                           s_part["n_accepted"], s_part["n_rejected"])
     group.close()
     q.put((rank, res))
     dist.destroy_process_group()

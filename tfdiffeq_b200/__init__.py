@@ -7,6 +7,7 @@ tensors in place of TF tensors and ``func`` a PyTorch callable.  Importing this 
 from .odeint import SOLVERS, odeint            # noqa: F401
 from .adjoint import odeint_adjoint            # noqa: F401
 from .solvers import last_stats                # noqa: F401
+from . import rhs                               # noqa: F401
 
-__all__ = ['odeint', 'odeint_adjoint', 'SOLVERS', 'last_stats']
+__all__ = ['odeint', 'odeint_adjoint', 'SOLVERS', 'last_stats', 'rhs']
 __version__ = '0.1.0'

@@ -100,6 +100,14 @@ class SharedStepGroup(object):
         check(lib.b2ode_comm_attach(handle, self.rank, self.world, self._ptrs))
         check(lib.b2ode_comm_set_global_len(handle, glob))
 
+    def global_count(self, n):
+        """Sum of a per-rank count over the group (e.g. trajectories, for the mean in the error norm)."""
+        v = torch.tensor([int(n)], dtype=torch.int64)
+        if dist.get_backend(self.group) == "nccl":
+            v = v.to(self.device)
+        dist.all_reduce(v, group=self.group)
+        return int(v.item())
+
     def close(self):
         lib = _lib.lib
         with torch.cuda.device(self.device):

@@ -17,315 +17,16 @@
 //  * the dense output is evaluated for every output time inside the accepted step from registers; the
 //    quartic's coefficients are never written to HBM.
 
-#include "b2ode.h"
+#include "b2ode_dev.cuh"
 
-#include <cuda_runtime.h>
-#include <math.h>
-#include <stdarg.h>
-#include <stdio.h>
-#include <string.h>
-
-#include <new>
-#include <type_traits>
-
-static_assert(sizeof(b2ode_state) == 256, "b2ode_state must stay 256 bytes");
-
-// ------------------------------------------------------------------------------------------------
-// host-side error plumbing
-// ------------------------------------------------------------------------------------------------
 static thread_local char g_err[512] = "";
 
-static int fail(int code, const char *fmt, ...) {
+int b2_fail(int code, const char *fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
     return code;
-}
-
-#define B2_CUDA(x)                                                                         \
-    do {                                                                                   \
-        cudaError_t e_ = (x);                                                              \
-        if (e_ != cudaSuccess) return fail((int)e_, "%s -> %s", #x, cudaGetErrorString(e_)); \
-    } while (0)
-
-// ------------------------------------------------------------------------------------------------
-// device helpers
-// ------------------------------------------------------------------------------------------------
-constexpr int kThreads = 256;
-constexpr int kWarps = kThreads / 32;
-
-template <typename T>
-struct Ar;
-template <>
-struct Ar<double> {
-    static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
-    static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
-    static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
-    static __device__ __forceinline__ double div(double a, double b) { return __ddiv_rn(a, b); }
-    static __device__ __forceinline__ double abs(double a) { return fabs(a); }
-    static __device__ __forceinline__ double sqrt(double a) { return __dsqrt_rn(a); }
-    static __device__ __forceinline__ double pow(double a, double b) { return ::pow(a, b); }
-};
-template <>
-struct Ar<float> {
-    static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
-    static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
-    static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
-    static __device__ __forceinline__ float div(float a, float b) { return __fdiv_rn(a, b); }
-    static __device__ __forceinline__ float abs(float a) { return fabsf(a); }
-    static __device__ __forceinline__ float sqrt(float a) { return __fsqrt_rn(a); }
-    static __device__ __forceinline__ float pow(float a, float b) { return ::powf(a, b); }
-};
-
-// V elements of T; V*sizeof(T) is 16 (vector path) or sizeof(T) (scalar path)
-template <typename T, int V>
-struct alignas(sizeof(T) * V) Pack {
-    T v[V];
-};
-
-template <typename T, int V>
-__device__ __forceinline__ Pack<T, V> ld_pack(const T *p, long long i) {
-    Pack<T, V> r;
-    if constexpr (V == 1) {
-        r.v[0] = p[i];
-    } else {
-        static_assert(sizeof(T) * V == 16, "vector path is 16 bytes");
-        *reinterpret_cast<int4 *>(&r) = *reinterpret_cast<const int4 *>(p + i * V);
-    }
-    return r;
-}
-
-template <typename T, int V>
-__device__ __forceinline__ void st_pack(T *p, long long i, const Pack<T, V> &r) {
-    if constexpr (V == 1) {
-        p[i] = r.v[0];
-    } else {
-        *reinterpret_cast<int4 *>(p + i * V) = *reinterpret_cast<const int4 *>(&r);
-    }
-}
-
-// geometry of a launch: blocks [blk_begin[s], blk_begin[s+1]) work on segment s
-struct SegGeom {
-    int nseg;
-    int blk_begin[B2ODE_MAXSEG + 1];
-    long long n[B2ODE_MAXSEG];
-    unsigned vec_mask;  // bit s: every pointer of segment s is 16-byte aligned
-};
-
-__device__ __forceinline__ int find_seg(const SegGeom &g, int b) {
-    int s = 0;
-    while (s + 1 < g.nseg && b >= g.blk_begin[s + 1]) ++s;
-    return s;
-}
-
-template <int V>
-using IC = std::integral_constant<int, V>;
-
-// Run body(IC<V>, pack_index) over one segment: 16-byte packs + scalar tail, or all-scalar.
-template <typename T, typename F>
-__device__ __forceinline__ void seg_for_each(long long n, bool vec_ok, int bl, int nb, F &&body) {
-    constexpr int VW = 16 / sizeof(T);
-    const long long stride = (long long)nb * kThreads;
-    const long long first = (long long)bl * kThreads + threadIdx.x;
-    if (vec_ok) {
-        const long long nv = n / VW;
-        for (long long i = first; i < nv; i += stride) body(IC<VW>{}, i);
-        const long long tail = nv * VW + threadIdx.x;
-        if (bl == 0 && tail < n) body(IC<1>{}, tail);
-    } else {
-        for (long long i = first; i < n; i += stride) body(IC<1>{}, i);
-    }
-}
-
-// One record per block, written once, reduced by the last block in block order.  Four columns; the
-// template mask MM says which columns combine with a NaN-propagating max (bit set) instead of a sum.
-struct Partial {
-    double v[4];
-};
-
-__device__ __forceinline__ double nan_max(double a, double b) { return (a != a || b != b) ? (double)NAN : fmax(a, b); }
-__device__ __forceinline__ double nan_min(double a, double b) { return (a != a || b != b) ? (double)NAN : fmin(a, b); }
-
-template <unsigned MM>
-__device__ __forceinline__ Partial combine(const Partial &a, const Partial &b) {
-    Partial r;
-#pragma unroll
-    for (int c = 0; c < 4; ++c) r.v[c] = ((MM >> c) & 1u) ? nan_max(a.v[c], b.v[c]) : a.v[c] + b.v[c];
-    return r;
-}
-
-template <unsigned MM>
-__device__ __forceinline__ Partial identity() {
-    Partial r;
-#pragma unroll
-    for (int c = 0; c < 4; ++c) r.v[c] = 0.0;   // sums start at 0; the maxima are of absolute values (>= 0)
-    return r;
-}
-
-// block-wide reduction, fixed order (xor butterfly inside a warp, then warps 0..7); result valid in thread 0
-template <unsigned MM>
-__device__ __forceinline__ Partial block_reduce(Partial x) {
-    __shared__ Partial sh[kWarps];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        Partial y;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) y.v[c] = __shfl_xor_sync(0xffffffffu, x.v[c], o);
-        x = combine<MM>(x, y);
-    }
-    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-    __syncthreads();   // protect sh[] against a previous use
-    if (l == 0) sh[w] = x;
-    __syncthreads();
-    Partial r = identity<MM>();
-    if (threadIdx.x == 0) {
-        r = sh[0];
-        for (int i = 1; i < kWarps; ++i) r = combine<MM>(r, sh[i]);
-    }
-    return r;
-}
-
-// NaN-aware abs-max accumulation: fmax() drops NaN, so NaN is tracked separately and re-injected.
-template <typename T>
-struct AbsMax {
-    T mx = T(0);
-    bool nan = false;
-    __device__ __forceinline__ void see(T v) {
-        T a = Ar<T>::abs(v);
-        nan |= (a != a);
-        mx = (a > mx) ? a : mx;
-    }
-    __device__ __forceinline__ double value() const { return nan ? (double)NAN : (double)mx; }
-};
-
-// returns true in every thread of exactly one block: the last one to arrive
-__device__ __forceinline__ bool last_block_arrives(unsigned *ticket) {
-    __shared__ bool is_last;
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        unsigned t = atomicAdd(ticket, 1u);
-        is_last = (t == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (is_last) __threadfence();
-    return is_last;
-}
-
-// ------------------------------------------------------------------------------------------------
-// cross-GPU exchange of the per-segment partials (shared-step groups; new)
-// ------------------------------------------------------------------------------------------------
-struct MailSlot {
-    double vals[B2ODE_MAXSEG][4];
-    unsigned long long seq;
-    unsigned long long pad[7];
-};
-struct Mailbox {
-    MailSlot slot[2][B2ODE_MAXPEERS];
-    unsigned long long local_seq;   // exchanges completed by the owning rank; persists across solves
-    unsigned long long pad[7];
-};
-
-struct CommParams {
-    int rank;
-    int nranks;  // 0 or 1: no exchange
-    Mailbox *box[B2ODE_MAXPEERS];
-};
-
-__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ double ld_relaxed_sys(const double *p) {
-    double v;
-    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_relaxed_sys(double *p, double v) {
-    asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
-}
-
-// Called by ALL threads of the last block.  tot[s] (shared memory, [nseg]) holds this rank's totals on
-// entry and the group totals (combined in rank order: deterministic and identical on every rank) on exit.
-template <unsigned MM>
-__device__ void group_combine(const CommParams &cp, b2ode_state *st, Partial *tot, int nseg) {
-    if (cp.nranks <= 1) return;
-    __shared__ unsigned long long seq_sh;
-    if (threadIdx.x == 0) seq_sh = cp.box[cp.rank]->local_seq + 1;
-    __syncthreads();
-    const unsigned long long seq = seq_sh;
-    const int par = (int)(seq & 1ull);
-    if (threadIdx.x < cp.nranks) {
-        // push my totals into peer q's mailbox, slot [par][my rank], then release the sequence number
-        const int q = threadIdx.x;
-        MailSlot *dst = &cp.box[q]->slot[par][cp.rank];
-        for (int s = 0; s < nseg; ++s)
-            for (int c = 0; c < 4; ++c) st_relaxed_sys(&dst->vals[s][c], tot[s].v[c]);
-        __threadfence_system();
-        st_release_sys(&dst->seq, seq);
-        // wait for rank q's totals in MY mailbox
-        const MailSlot *src = &cp.box[cp.rank]->slot[par][q];
-        while (ld_acquire_sys(&src->seq) != seq) __nanosleep(20);
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const Mailbox *mine = cp.box[cp.rank];
-        for (int s = 0; s < nseg; ++s) {
-            Partial p = identity<MM>();
-            for (int q = 0; q < cp.nranks; ++q) {
-                const MailSlot *src = &mine->slot[par][q];
-                Partial x;
-                for (int c = 0; c < 4; ++c) x.v[c] = ld_relaxed_sys(&src->vals[s][c]);
-                p = (q == 0) ? x : combine<MM>(p, x);
-            }
-            tot[s] = p;
-        }
-        cp.box[cp.rank]->local_seq = seq;
-        st->xseq = seq;
-    }
-    __syncthreads();
-}
-
-// Last block: reduce the per-block partials of every segment in block order into tot[] (shared).
-template <unsigned MM>
-__device__ void reduce_partials(const SegGeom &g, const Partial *part, Partial *tot) {
-    for (int s = 0; s < g.nseg; ++s) {
-        Partial acc = identity<MM>();
-        for (int b = g.blk_begin[s] + threadIdx.x; b < g.blk_begin[s + 1]; b += kThreads) acc = combine<MM>(acc, part[b]);
-        Partial r = block_reduce<MM>(acc);
-        if (threadIdx.x == 0) tot[s] = r;
-    }
-    __syncthreads();
-}
-
-// ------------------------------------------------------------------------------------------------
-// controller parameters shared by the kernels that end an attempt / the initial step
-// ------------------------------------------------------------------------------------------------
-struct CtrlParams {
-    int n_k;                      // s
-    int controller;               // B2ODE_CTRL_*
-    double alpha[B2ODE_MAXK];     // s-1 entries
-    double rtol[B2ODE_MAXSEG], atol[B2ODE_MAXSEG];
-    double safety, ifactor, dfactor, exponent;
-    long long max_num_steps;
-    int init_order;
-    int n_out;
-    const double *t_out;
-    void *tstage;                 // n_k scalars of the state dtype
-    long long n_global[B2ODE_MAXSEG];   // element count of the segment over the whole shared-step group
-};
-
-// rk_common.py:45-50: t0 and dt are cast to the state dtype, ti = t0 + alpha_i * dt in that dtype
-template <typename T>
-__device__ void write_stage_times(const CtrlParams &c, double t_cur, double dt) {
-    T *ts = reinterpret_cast<T *>(c.tstage);
-    const T t0 = (T)t_cur, d = (T)dt;
-    for (int i = 0; i + 1 < c.n_k; ++i) ts[i] = Ar<T>::add(t0, Ar<T>::mul((T)c.alpha[i], d));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -452,42 +153,9 @@ __device__ void control_step(b2ode_state *st, const CtrlParams &c, const Partial
     int cur = st->cursor;
     const long long nadv0 = st->n_steps_adv;
     const unsigned long long n_acc = st->n_acc, n_rej = st->n_rej, attempt = st->attempt;
-    bool accept = true;
-    double m = 0.0;
-    double pooled = 0.0;
-    long long pooled_n = 0;
-    bool bad0 = false;
-    for (int s = 0; s < nseg; ++s) {
-        bad0 |= (tot[s].v[3] > 0.0);
-        // tol = atol + rtol * reduce_max([|y0|, |y1|]): ONE scalar per segment (misc.py:257)
-        const double mm = nan_max(tot[s].v[1], tot[s].v[2]);
-        const T tol = Ar<T>::add((T)c.atol[s], Ar<T>::mul((T)c.rtol[s], (T)mm));
-        const double ssq = tot[s].v[0] / ((double)tol * (double)tol);
-        if (c.controller == B2ODE_CTRL_TSIT5) {
-            pooled += ssq;
-            pooled_n += c.n_global[s];
-        } else {
-            const T msr = (T)(ssq / (double)c.n_global[s]);
-            accept = accept && (msr <= T(1));
-            m = (s == 0) ? (double)msr : nan_max(m, (double)msr);
-        }
-    }
-    if (c.controller == B2ODE_CTRL_TSIT5) {
-        const T msr = (T)(pooled / (double)pooled_n);
-        accept = (msr <= T(1));
-        m = (double)msr;
-    }
-    // _optimal_step_size
-    double dt_next;
-    if (m == 0.0) {
-        dt_next = dt * c.ifactor;
-    } else {
-        const double df = (m < 1.0) ? 1.0 : c.dfactor;
-        const double er = (c.controller == B2ODE_CTRL_TSIT5) ? m : (double)Ar<T>::sqrt((T)m);
-        const double cand = pow(er, c.exponent) / c.safety;
-        const double factor = nan_max(1.0 / c.ifactor, nan_min(cand, 1.0 / df));
-        dt_next = dt / factor;
-    }
+    const CtrlDecision dec = ctrl_decide<T>(c, tot, nseg, dt);
+    const bool accept = dec.accept, bad0 = dec.bad0;
+    const double m = dec.m, dt_next = dec.dt_next;
     if (bad0) status |= B2ODE_ST_NONFINITE;   // the reference asserts this before taking the step
     const double t1_new = accept ? t_cur + dt : t_cur;
     // outputs inside the accepted step: every t_out[j] with t_out[j] <= t1 (advance(): `while next_t > t1`);
@@ -804,26 +472,8 @@ __global__ void __launch_bounds__(kThreads) k_init_norms(const __grid_constant__
     group_combine<0u>(p.comm, p.st, tot, p.g.nseg);
     if (threadIdx.x == 0) {
         b2ode_state *st = p.st;
-        T d0max = T(0), d1max = T(0), ratio = T(0);
-        bool first = true;
-        for (int sg = 0; sg < p.g.nseg; ++sg) {
-            const T rn = Ar<T>::sqrt((T)(double)p.c.n_global[sg]);               // numel ** 0.5, misc.py:173
-            const T d0 = Ar<T>::div((T)sqrt(tot[sg].v[0]), rn), d1 = Ar<T>::div((T)sqrt(tot[sg].v[1]), rn);
-            const T q = Ar<T>::div(d0, d1);
-            if (first) {
-                d0max = d0;
-                d1max = d1;
-                ratio = q;
-                first = false;
-            } else {
-                d0max = (d0 > d0max) ? d0 : d0max;     // python max(): keeps the first unless strictly greater
-                d1max = (d1 > d1max) ? d1 : d1max;
-                ratio = (q > ratio) ? q : ratio;
-            }
-        }
-        T h0;
-        if ((double)d0max < 1e-5 || (double)d1max < 1e-5) h0 = (T)1e-6;           // misc.py:231-232
-        else h0 = Ar<T>::mul((T)0.01, ratio);                                     // misc.py:234
+        T d1max;
+        const T h0 = init_h0<T>(p.c, tot, p.g.nseg, &d1max);
         st->h0 = (double)h0;
         st->reserved_d[0] = (double)d1max;
         T *ts = reinterpret_cast<T *>(p.c.tstage);
@@ -884,22 +534,7 @@ __global__ void __launch_bounds__(kThreads) k_init_finish(const __grid_constant_
         b2ode_state *st = p.st;
         const T h0 = (T)st->h0;
         const T d1max = (T)st->reserved_d[0];
-        T d2max = T(0);
-        for (int sg = 0; sg < p.g.nseg; ++sg) {
-            const T rn = Ar<T>::sqrt((T)(double)p.c.n_global[sg]);
-            const T d2 = Ar<T>::div(Ar<T>::div((T)sqrt(tot[sg].v[0]), rn), h0);
-            d2max = (sg == 0 || d2 > d2max) ? d2 : d2max;
-        }
-        T h1;
-        if ((double)d1max <= 1e-15 && (double)d2max <= 1e-15) {
-            const T alt = Ar<T>::mul(h0, (T)1e-3);
-            h1 = ((T)1e-6 > alt) ? (T)1e-6 : alt;                                 // misc.py:242-243
-        } else {
-            const T mx = (d2max > d1max) ? d2max : d1max;                         // max(d1 + d2): tuple concat
-            h1 = Ar<T>::pow(Ar<T>::div((T)0.01, mx), (T)(1.0 / (double)(p.c.init_order + 1)));   // misc.py:245
-        }
-        const T h100 = Ar<T>::mul(T(100), h0);
-        const T dt0 = (h1 < h100) ? h1 : h100;                                    // misc.py:247
+        const T dt0 = init_dt<T>(p.c, tot, p.g.nseg, h0, d1max);
         st->dt = (double)dt0;                                                     // cast to float64, dopri5.py:75
         if (!(st->t1 + st->dt > st->t1) && st->cursor < p.c.n_out) {
             st->status |= B2ODE_ST_UNDERFLOW;
@@ -1066,15 +701,15 @@ extern "C" size_t b2ode_workspace_bytes(const b2ode_adaptive_desc *desc) {
 }
 
 extern "C" int b2ode_adaptive_create(b2ode_solver **out, const b2ode_adaptive_desc *desc) {
-    if (!out || !desc) return fail(B2ODE_EINVAL, "null argument");
-    if (desc->dtype != B2ODE_F32 && desc->dtype != B2ODE_F64) return fail(B2ODE_EINVAL, "dtype must be 0 or 1");
-    if (desc->nseg < 1 || desc->nseg > B2ODE_MAXSEG) return fail(B2ODE_EINVAL, "nseg must be in [1, %d]", B2ODE_MAXSEG);
-    if (desc->n_k < 2 || desc->n_k > B2ODE_MAXK) return fail(B2ODE_EINVAL, "n_k must be in [2, %d]", B2ODE_MAXK);
+    if (!out || !desc) return b2_fail(B2ODE_EINVAL, "null argument");
+    if (desc->dtype != B2ODE_F32 && desc->dtype != B2ODE_F64) return b2_fail(B2ODE_EINVAL, "dtype must be 0 or 1");
+    if (desc->nseg < 1 || desc->nseg > B2ODE_MAXSEG) return b2_fail(B2ODE_EINVAL, "nseg must be in [1, %d]", B2ODE_MAXSEG);
+    if (desc->n_k < 2 || desc->n_k > B2ODE_MAXK) return b2_fail(B2ODE_EINVAL, "n_k must be in [2, %d]", B2ODE_MAXK);
     for (int s = 0; s < desc->nseg; ++s)
-        if (desc->seg_len[s] < 0) return fail(B2ODE_EINVAL, "negative segment length");
-    if (desc->dense_kind == 1 && desc->n_k != 7) return fail(B2ODE_EINVAL, "tsit5 dense output needs n_k == 7");
+        if (desc->seg_len[s] < 0) return b2_fail(B2ODE_EINVAL, "negative segment length");
+    if (desc->dense_kind == 1 && desc->n_k != 7) return b2_fail(B2ODE_EINVAL, "tsit5 dense output needs n_k == 7");
     b2ode_solver *s = new (std::nothrow) b2ode_solver();
-    if (!s) return fail(B2ODE_ENOMEM, "host allocation failed");
+    if (!s) return b2_fail(B2ODE_ENOMEM, "host allocation failed");
     memset(s, 0, sizeof(*s));
     s->d = *desc;
     build_geom(&s->geom, desc->dtype, desc->nseg, desc->seg_len, desc->sm_count);
@@ -1151,16 +786,16 @@ extern "C" int b2ode_adaptive_create(b2ode_solver **out, const b2ode_adaptive_de
 extern "C" void b2ode_adaptive_destroy(b2ode_solver *s) { delete s; }
 
 extern "C" int b2ode_adaptive_bind(b2ode_solver *s, const b2ode_adaptive_buffers *buf, void *cuda_stream) {
-    if (!s || !buf) return fail(B2ODE_EINVAL, "null argument");
-    if (!buf->state || !buf->workspace || !buf->tstage) return fail(B2ODE_EINVAL, "state/workspace/tstage is null");
+    if (!s || !buf) return b2_fail(B2ODE_EINVAL, "null argument");
+    if (!buf->state || !buf->workspace || !buf->tstage) return b2_fail(B2ODE_EINVAL, "state/workspace/tstage is null");
     if (buf->workspace_bytes < (size_t)s->grid * sizeof(Partial))
-        return fail(B2ODE_ENOMEM, "workspace too small: %zu < %zu", buf->workspace_bytes, (size_t)s->grid * sizeof(Partial));
-    if (buf->n_out < 1 || (!buf->t_out && buf->n_out > 0)) return fail(B2ODE_EINVAL, "t_out / n_out invalid");
+        return b2_fail(B2ODE_ENOMEM, "workspace too small: %zu < %zu", buf->workspace_bytes, (size_t)s->grid * sizeof(Partial));
+    if (buf->n_out < 1 || (!buf->t_out && buf->n_out > 0)) return b2_fail(B2ODE_EINVAL, "t_out / n_out invalid");
     for (int i = 0; i < s->d.nseg; ++i) {
         if (s->d.seg_len[i] > 0 && (!buf->y0[i] || !buf->f0[i] || !buf->ystage[i] || !buf->out[i]))
-            return fail(B2ODE_EINVAL, "segment %d has a null buffer", i);
+            return b2_fail(B2ODE_EINVAL, "segment %d has a null buffer", i);
     }
-    if (!aligned16(buf->state)) return fail(B2ODE_EINVAL, "state must be 16-byte aligned");
+    if (!aligned16(buf->state)) return b2_fail(B2ODE_EINVAL, "state must be 16-byte aligned");
     s->b = *buf;
     s->stream = (cudaStream_t)cuda_stream;
     s->ctrl.n_out = buf->n_out;
@@ -1172,19 +807,19 @@ extern "C" int b2ode_adaptive_bind(b2ode_solver *s, const b2ode_adaptive_buffers
 }
 
 extern "C" int b2ode_set_stream(b2ode_solver *s, void *cuda_stream) {
-    if (!s) return fail(B2ODE_EINVAL, "null solver");
+    if (!s) return b2_fail(B2ODE_EINVAL, "null solver");
     s->stream = (cudaStream_t)cuda_stream;
     return 0;
 }
 
 extern "C" int b2ode_comm_attach(b2ode_solver *s, int rank, int nranks, void *const *mailboxes) {
-    if (!s) return fail(B2ODE_EINVAL, "null solver");
-    if (nranks < 1 || nranks > B2ODE_MAXPEERS || rank < 0 || rank >= nranks) return fail(B2ODE_EINVAL, "bad rank/nranks");
-    if (nranks > 1 && !mailboxes) return fail(B2ODE_EINVAL, "mailboxes is null");
+    if (!s) return b2_fail(B2ODE_EINVAL, "null solver");
+    if (nranks < 1 || nranks > B2ODE_MAXPEERS || rank < 0 || rank >= nranks) return b2_fail(B2ODE_EINVAL, "bad rank/nranks");
+    if (nranks > 1 && !mailboxes) return b2_fail(B2ODE_EINVAL, "mailboxes is null");
     s->comm.rank = rank;
     s->comm.nranks = nranks;
     for (int r = 0; r < nranks; ++r) {
-        if (nranks > 1 && !mailboxes[r]) return fail(B2ODE_EINVAL, "mailbox %d is null", r);
+        if (nranks > 1 && !mailboxes[r]) return b2_fail(B2ODE_EINVAL, "mailbox %d is null", r);
         s->comm.box[r] = nranks > 1 ? (Mailbox *)mailboxes[r] : nullptr;
     }
     return 0;
@@ -1192,9 +827,9 @@ extern "C" int b2ode_comm_attach(b2ode_solver *s, int rank, int nranks, void *co
 
 // the group-wide element counts (used for the mean in the error ratio) -- set by the host driver after attach
 extern "C" int b2ode_comm_set_global_len(b2ode_solver *s, const int64_t *global_len) {
-    if (!s || !global_len) return fail(B2ODE_EINVAL, "null argument");
+    if (!s || !global_len) return b2_fail(B2ODE_EINVAL, "null argument");
     for (int i = 0; i < s->d.nseg; ++i) {
-        if (global_len[i] < s->d.seg_len[i]) return fail(B2ODE_EINVAL, "global length smaller than the local one");
+        if (global_len[i] < s->d.seg_len[i]) return b2_fail(B2ODE_EINVAL, "global length smaller than the local one");
         s->ctrl.n_global[i] = global_len[i];
     }
     return 0;
@@ -1202,12 +837,13 @@ extern "C" int b2ode_comm_set_global_len(b2ode_solver *s, const int64_t *global_
 
 #define B2_REQUIRE_BOUND(s)                                              \
     do {                                                                 \
-        if (!(s)) return fail(B2ODE_EINVAL, "null solver");              \
-        if (!(s)->bound) return fail(B2ODE_ESTATE, "solver is not bound"); \
+        if (!(s)) return b2_fail(B2ODE_EINVAL, "null solver");              \
+        if (!(s)->bound) return b2_fail(B2ODE_ESTATE, "solver is not bound"); \
     } while (0)
 
 // ---- launch accounting (bench.py's gpu_launches) and optional per-kernel-family event timing -------------
 static unsigned long long g_launches = 0;
+void b2_count_launch(void) { ++g_launches; }
 
 enum { B2_FAM_STAGE0 = 0, B2_FAM_STAGE = 1, B2_FAM_FINALIZE = 2, B2_FAM_EMIT = 3, B2_FAM_INIT = 4, B2_FAM_FIXED = 5, B2_NFAM = 6 };
 constexpr int kMaxTimed = 2048;   // event pairs per family
@@ -1247,7 +883,7 @@ extern "C" unsigned long long b2ode_launch_count(void) { return g_launches; }
 extern "C" int b2ode_timing_enable(unsigned family_mask) {
     if (!g_timing) {
         g_timing = new (std::nothrow) Timing();
-        if (!g_timing) return fail(B2ODE_ENOMEM, "host allocation failed");
+        if (!g_timing) return b2_fail(B2ODE_ENOMEM, "host allocation failed");
         memset(g_timing, 0, sizeof(Timing));
     }
     for (int f = 0; f < B2_NFAM; ++f) {
@@ -1266,7 +902,7 @@ extern "C" int b2ode_timing_enable(unsigned family_mask) {
 
 // Sum of the recorded launch durations of one family (synchronises on the last recorded event).
 extern "C" int b2ode_timing_read(int family, double *total_ms, int *count) {
-    if (!g_timing || family < 0 || family >= B2_NFAM || !total_ms || !count) return fail(B2ODE_EINVAL, "bad timing query");
+    if (!g_timing || family < 0 || family >= B2_NFAM || !total_ms || !count) return b2_fail(B2ODE_EINVAL, "bad timing query");
     double tot = 0.0;
     const int n = g_timing->n[family];
     for (int i = 0; i < n; ++i) {
@@ -1283,7 +919,7 @@ extern "C" int b2ode_timing_read(int family, double *total_ms, int *count) {
 // ---- mailboxes of a shared-step group: the one place the library owns device memory ---------------------
 // (cudaMalloc'ed so that a CUDA IPC handle can be taken; 5 KB per rank)
 extern "C" int b2ode_mailbox_create(void **dev_ptr, unsigned char handle_out[64]) {
-    if (!dev_ptr || !handle_out) return fail(B2ODE_EINVAL, "null argument");
+    if (!dev_ptr || !handle_out) return b2_fail(B2ODE_EINVAL, "null argument");
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle is 64 bytes");
     void *p = nullptr;
     B2_CUDA(cudaMalloc(&p, sizeof(Mailbox)));
@@ -1296,7 +932,7 @@ extern "C" int b2ode_mailbox_create(void **dev_ptr, unsigned char handle_out[64]
     return 0;
 }
 extern "C" int b2ode_mailbox_open(const unsigned char handle[64], void **peer_ptr) {
-    if (!handle || !peer_ptr) return fail(B2ODE_EINVAL, "null argument");
+    if (!handle || !peer_ptr) return b2_fail(B2ODE_EINVAL, "null argument");
     cudaIpcMemHandle_t h;
     memcpy(&h, handle, 64);
     B2_CUDA(cudaIpcOpenMemHandle(peer_ptr, h, cudaIpcMemLazyEnablePeerAccess));
@@ -1378,7 +1014,7 @@ extern "C" int b2ode_initial_step_probe(b2ode_solver *s) {
 
 extern "C" int b2ode_initial_step_finish(b2ode_solver *s, const void *const *f1) {
     B2_REQUIRE_BOUND(s);
-    if (!f1) return fail(B2ODE_EINVAL, "f1 is null");
+    if (!f1) return b2_fail(B2ODE_EINVAL, "f1 is null");
     InitParams p;
     fill_init_params(s, &p, f1);
     if (s->d.dtype == B2ODE_F64) return launch(k_init_finish<double>, s->grid, s->stream, p, B2_FAM_INIT);
@@ -1417,18 +1053,18 @@ static int dispatch_stage(b2ode_solver *s, int row) {
         B2_CASE(11) B2_CASE(12) B2_CASE(13) B2_CASE(14)
 #undef B2_CASE
     }
-    return fail(B2ODE_EINVAL, "unsupported number of stage terms %d", s->st_nk[row]);
+    return b2_fail(B2ODE_EINVAL, "unsupported number of stage terms %d", s->st_nk[row]);
 }
 
 extern "C" int b2ode_rk_stage(b2ode_solver *s, int i, const void *const *k_new) {
     B2_REQUIRE_BOUND(s);
     const int nk = s->d.n_k;
-    if (i < 0 || i > nk - 1) return fail(B2ODE_EINVAL, "stage index %d out of range", i);
-    if (i == nk - 1 && s->d.fsal) return fail(B2ODE_EINVAL, "solution combine requested for an FSAL tableau");
+    if (i < 0 || i > nk - 1) return b2_fail(B2ODE_EINVAL, "stage index %d out of range", i);
+    if (i == nk - 1 && s->d.fsal) return b2_fail(B2ODE_EINVAL, "solution combine requested for an FSAL tableau");
     if (i > 0) {
-        if (!k_new) return fail(B2ODE_EINVAL, "k_new is null for stage %d", i);
+        if (!k_new) return b2_fail(B2ODE_EINVAL, "k_new is null for stage %d", i);
         for (int sg = 0; sg < s->d.nseg; ++sg) {
-            if (!k_new[sg] && s->d.seg_len[sg] > 0) return fail(B2ODE_EINVAL, "k_new[%d] is null", sg);
+            if (!k_new[sg] && s->d.seg_len[sg] > 0) return b2_fail(B2ODE_EINVAL, "k_new[%d] is null", sg);
             s->k[i][sg] = k_new[sg];
         }
     }
@@ -1543,15 +1179,15 @@ static int dispatch_finalize(b2ode_solver *s) {
         B2_CASE(11) B2_CASE(12) B2_CASE(13) B2_CASE(14)
 #undef B2_CASE
     }
-    return fail(B2ODE_EINVAL, "unsupported dense-output list length %d", s->mid_nk);
+    return b2_fail(B2ODE_EINVAL, "unsupported dense-output list length %d", s->mid_nk);
 }
 
 extern "C" int b2ode_rk_finalize(b2ode_solver *s, const void *const *k_last) {
     B2_REQUIRE_BOUND(s);
-    if (!k_last) return fail(B2ODE_EINVAL, "k_last is null");
+    if (!k_last) return b2_fail(B2ODE_EINVAL, "k_last is null");
     const int nk = s->d.n_k;
     for (int sg = 0; sg < s->d.nseg; ++sg) {
-        if (!k_last[sg] && s->d.seg_len[sg] > 0) return fail(B2ODE_EINVAL, "k_last[%d] is null", sg);
+        if (!k_last[sg] && s->d.seg_len[sg] > 0) return b2_fail(B2ODE_EINVAL, "k_last[%d] is null", sg);
         s->k[nk - 1][sg] = k_last[sg];
     }
     int rc = (s->d.dtype == B2ODE_F64) ? dispatch_finalize<double>(s) : dispatch_finalize<float>(s);
@@ -1560,7 +1196,7 @@ extern "C" int b2ode_rk_finalize(b2ode_solver *s, const void *const *k_last) {
 
 extern "C" int b2ode_poll_async(b2ode_solver *s, b2ode_state *host_dst) {
     B2_REQUIRE_BOUND(s);
-    if (!host_dst) return fail(B2ODE_EINVAL, "host_dst is null");
+    if (!host_dst) return b2_fail(B2ODE_EINVAL, "host_dst is null");
     B2_CUDA(cudaMemcpyAsync(host_dst, s->b.state, sizeof(b2ode_state), cudaMemcpyDeviceToHost, s->stream));
     return 0;
 }
@@ -1583,14 +1219,14 @@ static int dispatch_fixed(int op, int grid, cudaStream_t st, const FixedParams &
         B2_CASE(B2ODE_OP_RK4_S3) B2_CASE(B2ODE_OP_RK4_S4) B2_CASE(B2ODE_OP_RK4_FINAL) B2_CASE(B2ODE_OP_LERP)
 #undef B2_CASE
     }
-    return fail(B2ODE_EINVAL, "unknown fixed-grid op %d", op);
+    return b2_fail(B2ODE_EINVAL, "unknown fixed-grid op %d", op);
 }
 
 extern "C" int b2ode_fixed_op(int dtype, int op, int nseg, const int64_t *seg_len, void *const *out, const void *const *y,
                               const void *const *a, const void *const *b, const void *const *c, const void *const *d,
                               double dt, double s1, double s2, int sm_count, void *cuda_stream) {
-    if (dtype != B2ODE_F32 && dtype != B2ODE_F64) return fail(B2ODE_EINVAL, "dtype must be 0 or 1");
-    if (nseg < 1 || nseg > B2ODE_MAXSEG || !seg_len || !out || !y || !a) return fail(B2ODE_EINVAL, "bad segment arguments");
+    if (dtype != B2ODE_F32 && dtype != B2ODE_F64) return b2_fail(B2ODE_EINVAL, "dtype must be 0 or 1");
+    if (nseg < 1 || nseg > B2ODE_MAXSEG || !seg_len || !out || !y || !a) return b2_fail(B2ODE_EINVAL, "bad segment arguments");
     int arity = 1;
     switch (op) {
         case B2ODE_OP_HEUN_FINAL:
@@ -1599,14 +1235,14 @@ extern "C" int b2ode_fixed_op(int dtype, int op, int nseg, const int64_t *seg_le
         case B2ODE_OP_RK4_FINAL: arity = 4; break;
         default: break;
     }
-    if ((arity > 1 && !b) || (arity > 2 && !c) || (arity > 3 && !d)) return fail(B2ODE_EINVAL, "op %d needs %d operands", op, arity);
+    if ((arity > 1 && !b) || (arity > 2 && !c) || (arity > 3 && !d)) return b2_fail(B2ODE_EINVAL, "op %d needs %d operands", op, arity);
     FixedParams p;
     memset(&p, 0, sizeof(p));
     build_geom(&p.g, dtype, nseg, seg_len, sm_count);
     p.op = op;
     unsigned mask = 0;
     for (int s = 0; s < nseg; ++s) {
-        if (seg_len[s] < 0) return fail(B2ODE_EINVAL, "negative segment length");
+        if (seg_len[s] < 0) return b2_fail(B2ODE_EINVAL, "negative segment length");
         p.out[s] = out[s];
         p.y[s] = y[s];
         p.a[s] = a[s];
@@ -1615,7 +1251,7 @@ extern "C" int b2ode_fixed_op(int dtype, int op, int nseg, const int64_t *seg_le
         p.d[s] = arity > 3 ? d[s] : nullptr;
         if (seg_len[s] > 0 && (!p.out[s] || !p.y[s] || !p.a[s] || (arity > 1 && !p.b[s]) || (arity > 2 && !p.c[s]) ||
                                (arity > 3 && !p.d[s])))
-            return fail(B2ODE_EINVAL, "segment %d has a null operand", s);
+            return b2_fail(B2ODE_EINVAL, "segment %d has a null operand", s);
         if (aligned16(p.out[s]) && aligned16(p.y[s]) && aligned16(p.a[s]) && aligned16(p.b[s]) && aligned16(p.c[s]) &&
             aligned16(p.d[s]))
             mask |= 1u << s;

@@ -1,0 +1,528 @@
+// b2ode_fused.cu -- whole adaptive solve in ONE persistent kernel for built-in right-hand sides.
+//
+// SURVEY.md 8(f)-2.  When `func` is one of the library's own right-hand sides (tfdiffeq_b200/rhs.py), the user
+// callable does not have to be called from the host at all: every trajectory of the batch lives in the
+// registers of one thread -- state, all s stage derivatives -- for the entire solve; the only HBM traffic is
+// the (T, B, D) solution slab, written once.  The reference semantics are kept exactly: ONE step size for
+// the whole batch and a tolerance that is a global scalar over the whole tensor (tfdiffeq/misc.py:257), so
+// every attempt needs one grid-wide reduction; it is done with a sense-reversing grid barrier (cooperative
+// launch guarantees co-residency) and evaluated redundantly -- and bit-identically -- by every thread.
+// The arithmetic is the same as the generic path's kernels (same helpers from b2ode_dev.cuh, same operation
+// order: rk_common.py:49-60, misc.py:250-287, interp.py:6-67), only the reduction order differs.
+
+#include "b2ode_dev.cuh"
+
+constexpr int kFThreads = 128;
+constexpr int kFWarps = kFThreads / 32;
+
+// ------------------------------------------------------------------------------------------------
+// built-in right-hand sides: explicit mul/add in the order of the torch expressions in rhs.py
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+struct RhsLorenz {   // examples/lorenz_attractor.py:20-37 ; params {sigma, beta, rho}
+    static constexpr int D = 3;
+    static __device__ __forceinline__ void eval(const double *prm, T /*t*/, const T (&y)[3], T (&dy)[3]) {
+        using A = Ar<T>;
+        const T sigma = (T)prm[0], beta = (T)prm[1], rho = (T)prm[2];
+        dy[0] = A::mul(sigma, A::sub(y[1], y[0]));                          // sigma * (y - x)
+        dy[1] = A::sub(A::mul(y[0], A::sub(rho, y[2])), y[1]);              // x * (rho - z) - y
+        dy[2] = A::sub(A::mul(y[0], y[1]), A::mul(beta, y[2]));             // x * y - beta * z
+    }
+};
+
+template <typename T>
+struct RhsLotkaVolterra {   // README.md:67-81 ; params {a, b, c, d}
+    static constexpr int D = 2;
+    static __device__ __forceinline__ void eval(const double *prm, T /*t*/, const T (&y)[2], T (&dy)[2]) {
+        using A = Ar<T>;
+        const T a = (T)prm[0], b = (T)prm[1], c = (T)prm[2], d = (T)prm[3];
+        dy[0] = A::sub(A::mul(a, y[0]), A::mul(A::mul(b, y[0]), y[1]));     // a*x - b*x*z
+        dy[1] = A::add(A::mul(-c, y[1]), A::mul(A::mul(d, y[0]), y[1]));    // -c*z + d*x*z
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// grid-wide reduction: block tree -> partial per block -> grid barrier -> every block re-reduces all partials
+// ------------------------------------------------------------------------------------------------
+struct FusedParams {
+    b2ode_state *st;
+    Partial *part;          // [2][gridDim.x], double buffered by reduction parity
+    unsigned *bar;          // bar[0] = arrival counter, bar[1] = generation
+    Partial *gtot;          // [2]: group totals published by block 0 when a shared-step group is attached
+    unsigned long long *gflag;
+    const void *y0;
+    void *out;
+    long long n_traj;       // trajectories on this rank
+    int have_first_step;
+    double t_start, first_step;
+    double time_sign;       // -1 when integrating the reversed system (misc.py:318-321)
+    double rhs[8];
+    // tableau (runtime values; structural zeros are skipped exactly like the generic path does)
+    double beta[B2ODE_MAXK][B2ODE_MAXK];
+    double c_sol[B2ODE_MAXK], c_error[B2ODE_MAXK], c_mid[B2ODE_MAXK];
+    int fsal;
+    double rtol0, atol0;
+    CtrlParams c;
+    CommParams comm;
+};
+
+__device__ __forceinline__ void grid_barrier(unsigned *bar) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        volatile unsigned *gen = bar + 1;
+        const unsigned g = *gen;
+        __threadfence();
+        if (atomicAdd(bar, 1u) == gridDim.x - 1) {
+            bar[0] = 0;
+            __threadfence();
+            atomicAdd(bar + 1, 1u);
+        } else {
+            while (*gen == g) {
+            }
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+template <unsigned MM>
+__device__ __forceinline__ Partial fblock_reduce(Partial x, Partial *sh /*[kFWarps]*/) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        Partial y;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) y.v[c] = __shfl_xor_sync(0xffffffffu, x.v[c], o);
+        x = combine<MM>(x, y);
+    }
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();
+    if (l == 0) sh[w] = x;
+    __syncthreads();
+    Partial r = sh[0];
+#pragma unroll
+    for (int i = 1; i < kFWarps; ++i) r = combine<MM>(r, sh[i]);
+    return r;   // valid in EVERY thread
+}
+
+// All threads of the grid call this with their own contribution; all return the same (group-wide) totals.
+template <unsigned MM>
+__device__ Partial grid_reduce(const FusedParams &p, Partial mine, unsigned &parity, Partial *sh, Partial *sh_tot) {
+    Partial *part = p.part + (size_t)(parity & 1u) * gridDim.x;
+    Partial b = fblock_reduce<MM>(mine, sh);
+    if (threadIdx.x == 0) part[blockIdx.x] = b;
+    grid_barrier(p.bar);
+    Partial acc = identity<MM>();
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += kFThreads) acc = combine<MM>(acc, part[i]);
+    Partial tot = fblock_reduce<MM>(acc, sh);
+    if (p.comm.nranks > 1) {
+        // block 0 exchanges with the peer GPUs and publishes the group totals; the others wait for them
+        const unsigned long long want = (unsigned long long)(parity + 1u);
+        if (blockIdx.x == 0) {
+            if (threadIdx.x == 0) sh_tot[0] = tot;
+            __syncthreads();
+            group_combine<MM>(p.comm, p.st, sh_tot, 1);
+            if (threadIdx.x == 0) {
+                p.gtot[parity & 1u] = sh_tot[0];
+                __threadfence();
+                atomicExch(p.gflag, want);
+            }
+            __syncthreads();
+            tot = sh_tot[0];
+        } else {
+            if (threadIdx.x == 0) {
+                volatile unsigned long long *f = p.gflag;
+                while (*f < want) {
+                }
+                __threadfence();
+                sh_tot[0] = p.gtot[parity & 1u];
+            }
+            __syncthreads();
+            tot = sh_tot[0];
+            __syncthreads();
+        }
+    }
+    parity += 1u;
+    return tot;
+}
+
+// ------------------------------------------------------------------------------------------------
+// the persistent solve
+// ------------------------------------------------------------------------------------------------
+template <typename T, typename RHS, int S>
+__global__ void __launch_bounds__(kFThreads) k_fused_adaptive(const __grid_constant__ FusedParams p) {
+    using A = Ar<T>;
+    constexpr int D = RHS::D;
+    __shared__ Partial sh[kFWarps];
+    __shared__ Partial sh_tot[1];
+    const long long i = (long long)blockIdx.x * kFThreads + threadIdx.x;
+    const bool live = i < p.n_traj;
+    const long long N = p.n_traj * D;
+    const T *y0g = (const T *)p.y0;
+    T *out = (T *)p.out;
+    const T tsign = (T)p.time_sign;
+    unsigned parity = 0;
+
+    T y[D], f0[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) y[d] = live ? y0g[i * D + d] : T(0);
+    if (live) {
+#pragma unroll
+        for (int d = 0; d < D; ++d) out[i * D + d] = y[d];                 // solution[0] = y0 (solvers.py:29)
+    }
+    auto rhs = [&](T t, const T(&yy)[D], T(&dy)[D]) {
+        // reverse-time wrapper of misc.py:318-321: f'(t, y) = -f(-t, y)
+        if (tsign < T(0)) {
+            RHS::eval(p.rhs, -t, yy, dy);
+#pragma unroll
+            for (int d = 0; d < D; ++d) dy[d] = -dy[d];
+        } else {
+            RHS::eval(p.rhs, t, yy, dy);
+        }
+    };
+    double t_cur = p.t_start;
+    rhs((T)t_cur, y, f0);                                                    // dopri5.py:71
+
+    // ---- first step: given (dopri5.py:76) or _select_initial_step (misc.py:183-247) ----------------------
+    double dt;
+    unsigned status = 0;
+    int cur = 1;
+    if (p.have_first_step) {
+        dt = p.first_step;
+    } else {
+        const T rtol = (T)p.rtol0, atol = (T)p.atol0;
+        T scale[D];
+        Partial mine = identity<0u>();
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            scale[d] = A::add(atol, A::mul(A::abs(y[d]), rtol));
+            if (live) {
+                const double q0 = (double)A::div(y[d], scale[d]), q1 = (double)A::div(f0[d], scale[d]);
+                mine.v[0] += q0 * q0;
+                mine.v[1] += q1 * q1;
+            }
+        }
+        Partial tot = grid_reduce<0u>(p, mine, parity, sh, sh_tot);
+        T d1max;
+        const T h0 = init_h0<T>(p.c, &tot, 1, &d1max);
+        T y1[D], f1[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) y1[d] = A::add(y[d], A::mul(h0, f0[d]));
+        rhs(A::add((T)t_cur, h0), y1, f1);
+        mine = identity<0u>();
+        if (live) {
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+                const double q = (double)A::div(A::sub(f1[d], f0[d]), scale[d]);
+                mine.v[0] += q * q;
+            }
+        }
+        tot = grid_reduce<0u>(p, mine, parity, sh, sh_tot);
+        dt = (double)init_dt<T>(p.c, &tot, 1, h0, d1max);
+    }
+    int done = (p.c.n_out <= 1) ? 1 : 0;
+    if (!done && !(t_cur + dt > t_cur)) {
+        status |= B2ODE_ST_UNDERFLOW;
+        done = 1;
+    }
+    unsigned long long n_acc = 0, n_rej = 0, attempts = 0;
+    long long nadv = 0;
+    double t_prev = t_cur, dt_last = 0.0, msr = 0.0;
+
+    // ---- attempts -------------------------------------------------------------------------------------
+    while (!done) {
+        const T t0c = (T)t_cur, dtc = (T)dt;                               // rk_common.py:45-46
+        T k[S][D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) k[0][d] = f0[d];
+        T yi[D];
+#pragma unroll
+        for (int s = 0; s < S - 1; ++s) {
+            const T ti = A::add(t0c, A::mul((T)p.c.alpha[s], dtc));
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+                T acc = T(0);
+                bool first = true;
+#pragma unroll
+                for (int j = 0; j <= s; ++j) {
+                    const double bj = p.beta[s][j];
+                    if (bj != 0.0) {
+                        const T term = A::mul(A::mul(dtc, (T)bj), k[j][d]);
+                        acc = first ? term : A::add(acc, term);
+                        first = false;
+                    }
+                }
+                yi[d] = A::add(y[d], acc);
+            }
+            rhs(ti, yi, k[s + 1]);
+        }
+        if (!p.fsal) {                                                     // rk_common.py:54-56
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+                T acc = T(0);
+                bool first = true;
+#pragma unroll
+                for (int j = 0; j < S; ++j) {
+                    const double cj = p.c_sol[j];
+                    if (cj != 0.0) {
+                        const T term = A::mul(A::mul(dtc, (T)cj), k[j][d]);
+                        acc = first ? term : A::add(acc, term);
+                        first = false;
+                    }
+                }
+                yi[d] = A::add(y[d], acc);
+            }
+        }
+        // error estimate + this thread's share of the reduction (rk_common.py:60, misc.py:256-263)
+        Partial mine = identity<0xEu>();
+        if (live) {
+            AbsMax<T> m0, m1;
+            bool bad = false;
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+                T err = T(0);
+                bool first = true;
+#pragma unroll
+                for (int j = 0; j < S; ++j) {
+                    const double cj = p.c_error[j];
+                    if (cj != 0.0) {
+                        const T term = A::mul(A::mul(dtc, (T)cj), k[j][d]);
+                        err = first ? term : A::add(err, term);
+                        first = false;
+                    }
+                }
+                const double ed = (double)err;
+                mine.v[0] += ed * ed;
+                m0.see(y[d]);
+                m1.see(yi[d]);
+                bad |= !isfinite((double)y[d]);
+            }
+            mine.v[1] = m0.value();
+            mine.v[2] = m1.value();
+            mine.v[3] = bad ? 1.0 : 0.0;
+        }
+        const Partial tot = grid_reduce<0xEu>(p, mine, parity, sh, sh_tot);
+        const CtrlDecision dec = ctrl_decide<T>(p.c, &tot, 1, dt);
+        const bool accept = dec.accept && true;
+        if (dec.bad0) status |= B2ODE_ST_NONFINITE;
+        const double t1_new = accept ? t_cur + dt : t_cur;
+        const int j0 = cur;
+        if (accept && !dec.bad0) {
+            while (cur < p.c.n_out && p.c.t_out[cur] <= t1_new) ++cur;      // advance(): `while next_t > t1`
+        }
+        if (accept && cur > j0 && live) {
+            // dense output for every output time inside the step (dopri5.py:39-45, interp.py:22-67)
+            const T t0s = t0c, t1s = (T)t1_new;
+            const T den = A::sub(t1s, t0s);
+            const T m2dt = A::mul(T(-2), dtc), p2dt = A::mul(T(2), dtc), p5dt = A::mul(T(5), dtc);
+            const T m3dt = A::mul(T(-3), dtc), m4dt = A::mul(T(-4), dtc);
+            T ca[D], cb[D], cc[D], cd[D];
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+                T acc = T(0);
+                bool first = true;
+#pragma unroll
+                for (int j = 0; j < S; ++j) {
+                    const double cj = p.c_mid[j];
+                    if (cj != 0.0) {
+                        const T term = A::mul(A::mul(dtc, (T)cj), k[j][d]);
+                        acc = first ? term : A::add(acc, term);
+                        first = false;
+                    }
+                }
+                const T ymid = A::add(y[d], acc);
+                const T f0e = k[0][d], f1e = k[S - 1][d], y0e = y[d], y1e = yi[d];
+                T a = A::mul(m2dt, f0e);
+                a = A::add(a, A::mul(p2dt, f1e));
+                a = A::add(a, A::mul(T(-8), y0e));
+                a = A::add(a, A::mul(T(-8), y1e));
+                a = A::add(a, A::mul(T(16), ymid));
+                T b = A::mul(p5dt, f0e);
+                b = A::add(b, A::mul(m3dt, f1e));
+                b = A::add(b, A::mul(T(18), y0e));
+                b = A::add(b, A::mul(T(14), y1e));
+                b = A::add(b, A::mul(T(-32), ymid));
+                T cq = A::mul(m4dt, f0e);
+                cq = A::add(cq, A::mul(dtc, f1e));
+                cq = A::add(cq, A::mul(T(-11), y0e));
+                cq = A::add(cq, A::mul(T(-5), y1e));
+                cq = A::add(cq, A::mul(T(16), ymid));
+                ca[d] = a;
+                cb[d] = b;
+                cc[d] = cq;
+                cd[d] = A::mul(dtc, f0e);
+            }
+            for (int j = j0; j < cur; ++j) {
+                const T x = A::div(A::sub((T)p.c.t_out[j], t0s), den);
+                const T x2 = A::mul(x, x), x3 = A::mul(x2, x), x4 = A::mul(x3, x);
+                T *row = out + (long long)j * N + i * D;
+#pragma unroll
+                for (int d = 0; d < D; ++d) {
+                    T r = A::mul(ca[d], x4);
+                    r = A::add(r, A::mul(cb[d], x3));
+                    r = A::add(r, A::mul(cc[d], x2));
+                    r = A::add(r, A::mul(cd[d], x));
+                    r = A::add(r, y[d]);
+                    row[d] = r;
+                }
+            }
+        }
+        // state update (dopri5.py:113-120)
+        dt_last = dt;
+        msr = dec.m;
+        attempts += 1;
+        if (accept) {
+            n_acc += 1;
+            t_prev = t_cur;
+            t_cur = t1_new;
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+                y[d] = yi[d];
+                f0[d] = k[S - 1][d];
+            }
+        } else {
+            n_rej += 1;
+        }
+        dt = dec.dt_next;
+        nadv = (cur > j0) ? 0 : nadv + 1;
+        done = (cur >= p.c.n_out) ? 1 : 0;
+        if (!done) {
+            if (nadv >= p.c.max_num_steps) status |= B2ODE_ST_MAXSTEPS;
+            if (!(t_cur + dt > t_cur)) status |= B2ODE_ST_UNDERFLOW;
+        }
+        if (status) done = 1;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        b2ode_state z;
+        memset(&z, 0, sizeof(z));
+        z.t0 = t_prev;
+        z.t1 = t_cur;
+        z.dt = dt;
+        z.dt_last = dt_last;
+        z.msr_max = msr;
+        z.n_acc = n_acc;
+        z.n_rej = n_rej;
+        z.attempt = attempts;
+        z.n_steps_adv = nadv;
+        z.done = 1;
+        z.status = status;
+        z.cursor = cur;
+        z.xseq = p.st->xseq;
+        *p.st = z;
+    }
+}
+
+// ================================================================================================
+// host side
+// ================================================================================================
+template <typename T, typename RHS, int S>
+static int fused_launch(const FusedParams &p, int grid, cudaStream_t st) {
+    void *args[] = {(void *)&p};
+    int dev = 0, coop = 0, nsm = 0, per_sm = 0;
+    B2_CUDA(cudaGetDevice(&dev));
+    B2_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+    B2_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+    B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused_adaptive<T, RHS, S>, kFThreads, 0));
+    if (!coop) return b2_fail(B2ODE_ESTATE, "device does not support cooperative launch");
+    if (grid > per_sm * nsm)
+        return b2_fail(B2ODE_ENOMEM, "batch needs %d co-resident blocks, device holds %d", grid, per_sm * nsm);
+    B2_CUDA(cudaLaunchCooperativeKernel((const void *)k_fused_adaptive<T, RHS, S>, dim3(grid), dim3(kFThreads), args, 0, st));
+    b2_count_launch();
+    return 0;
+}
+
+template <typename T, typename RHS>
+static int fused_dispatch_s(const FusedParams &p, int n_k, int grid, cudaStream_t st) {
+    switch (n_k) {
+        case 2: return fused_launch<T, RHS, 2>(p, grid, st);
+        case 4: return fused_launch<T, RHS, 4>(p, grid, st);
+        case 7: return fused_launch<T, RHS, 7>(p, grid, st);
+        case 14: return fused_launch<T, RHS, 14>(p, grid, st);
+    }
+    return b2_fail(B2ODE_EINVAL, "fused solve supports tableaus with 2, 4, 7 or 14 k's (got %d)", n_k);
+}
+
+template <typename T>
+static int fused_dispatch_rhs(const FusedParams &p, int rhs_kind, int n_k, int grid, cudaStream_t st) {
+    switch (rhs_kind) {
+        case B2ODE_RHS_LORENZ: return fused_dispatch_s<T, RhsLorenz<T>>(p, n_k, grid, st);
+        case B2ODE_RHS_LOTKA_VOLTERRA: return fused_dispatch_s<T, RhsLotkaVolterra<T>>(p, n_k, grid, st);
+    }
+    return b2_fail(B2ODE_EINVAL, "unknown built-in right-hand side %d", rhs_kind);
+}
+
+static int rhs_dim(int kind) { return kind == B2ODE_RHS_LORENZ ? 3 : kind == B2ODE_RHS_LOTKA_VOLTERRA ? 2 : -1; }
+
+extern "C" size_t b2ode_fused_workspace_bytes(int64_t n_traj) {
+    const long long grid = (n_traj + kFThreads - 1) / kFThreads;
+    // [2][grid] partials + 2 group totals + barrier words + flag, 256-byte aligned pieces
+    return (size_t)(2 * grid + 2) * sizeof(Partial) + 256;
+}
+
+extern "C" int b2ode_fused_solve(const b2ode_adaptive_desc *desc, int rhs_kind, const double *rhs_params, int n_rhs_params,
+                                 double time_sign, const void *y0, void *out, const double *t_out, int n_out, double t_start,
+                                 double first_step, void *state, void *workspace, size_t workspace_bytes, int rank, int nranks,
+                                 void *const *mailboxes, int64_t n_traj_global, void *cuda_stream) {
+    if (!desc || !y0 || !out || !t_out || !state || !workspace) return b2_fail(B2ODE_EINVAL, "null argument");
+    const int D = rhs_dim(rhs_kind);
+    if (D < 0) return b2_fail(B2ODE_EINVAL, "unknown built-in right-hand side %d", rhs_kind);
+    if (desc->nseg != 1 || desc->seg_len[0] % D != 0) return b2_fail(B2ODE_EINVAL, "state must be one (B, %d) tensor", D);
+    if (desc->dense_kind != 0) return b2_fail(B2ODE_EINVAL, "fused solve supports the quartic dense output only");
+    if (n_rhs_params < 0 || n_rhs_params > 8 || (n_rhs_params && !rhs_params)) return b2_fail(B2ODE_EINVAL, "bad rhs params");
+    const long long n_traj = desc->seg_len[0] / D;
+    if (n_traj < 1) return b2_fail(B2ODE_EINVAL, "empty batch");
+    if (workspace_bytes < b2ode_fused_workspace_bytes(n_traj)) return b2_fail(B2ODE_ENOMEM, "workspace too small");
+    const int grid = (int)((n_traj + kFThreads - 1) / kFThreads);
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    // workspace layout: [barrier 2 x u32 | pad to 64][flag u64 | pad to 128][gtot x2][partials 2 x grid]
+    unsigned char *w = (unsigned char *)workspace;
+    B2_CUDA(cudaMemsetAsync(w, 0, 256, st));
+    FusedParams p;
+    memset(&p, 0, sizeof(p));
+    p.st = (b2ode_state *)state;
+    p.bar = (unsigned *)w;
+    p.gflag = (unsigned long long *)(w + 64);
+    p.gtot = (Partial *)(w + 128);
+    p.part = (Partial *)(w + 256);
+    p.y0 = y0;
+    p.out = out;
+    p.n_traj = n_traj;
+    p.have_first_step = (first_step == first_step) ? 1 : 0;
+    p.t_start = t_start;
+    p.first_step = first_step;
+    p.time_sign = time_sign;
+    for (int i = 0; i < n_rhs_params; ++i) p.rhs[i] = rhs_params[i];
+    const int nk = desc->n_k;
+    for (int i = 0; i < B2ODE_MAXK; ++i) {
+        for (int j = 0; j < B2ODE_MAXK; ++j) p.beta[i][j] = desc->beta[i][j];
+        p.c_sol[i] = desc->c_sol[i];
+        p.c_error[i] = desc->c_error[i];
+        p.c_mid[i] = desc->c_mid[i];
+        p.c.alpha[i] = desc->alpha[i];
+    }
+    p.fsal = desc->fsal;
+    p.rtol0 = desc->rtol[0];
+    p.atol0 = desc->atol[0];
+    p.c.n_k = nk;
+    p.c.controller = desc->controller;
+    p.c.rtol[0] = desc->rtol[0];
+    p.c.atol[0] = desc->atol[0];
+    p.c.safety = desc->safety;
+    p.c.ifactor = desc->ifactor;
+    p.c.dfactor = desc->dfactor;
+    p.c.exponent = desc->exponent;
+    p.c.max_num_steps = desc->max_num_steps;
+    p.c.init_order = desc->init_order;
+    p.c.n_out = n_out;
+    p.c.t_out = t_out;
+    p.c.tstage = nullptr;
+    p.c.n_global[0] = (nranks > 1 ? n_traj_global : n_traj) * D;
+    p.comm.rank = rank;
+    p.comm.nranks = nranks > 1 ? nranks : 0;
+    if (nranks > 1) {
+        if (!mailboxes || nranks > B2ODE_MAXPEERS) return b2_fail(B2ODE_EINVAL, "bad mailboxes");
+        for (int r = 0; r < nranks; ++r) p.comm.box[r] = (Mailbox *)mailboxes[r];
+    }
+    if (desc->dtype == B2ODE_F64) return fused_dispatch_rhs<double>(p, rhs_kind, nk, grid, st);
+    if (desc->dtype == B2ODE_F32) return fused_dispatch_rhs<float>(p, rhs_kind, nk, grid, st);
+    return b2_fail(B2ODE_EINVAL, "dtype must be 0 or 1");
+}

@@ -48,6 +48,7 @@ def _is_numeric(x):
 def _check_inputs(func, y0, t):
     """tfdiffeq/misc.py:290-329: tensor -> 1-tuple wrap, reverse-time wrap, dtype checks."""
     tensor_input = False
+    base, sign = func, 1.0
     if isinstance(y0, torch.Tensor):
         tensor_input = True
         y0 = (y0,)
@@ -62,9 +63,16 @@ def _check_inputs(func, y0, t):
         t = -t
         _base_reverse_func = func
         func = lambda t, y: tuple(-f_ for f_ in _base_reverse_func(-t, y))   # noqa: E731
+        sign = -1.0
     for y0_ in y0:
         if not _is_numeric(y0_):
             raise TypeError('`y0` must be a floating point Tensor but is a {}'.format(y0_.dtype))
     if not _is_numeric(t):
         raise TypeError('`t` must be a floating point Tensor but is a {}'.format(t.dtype))
+    if tensor_input:
+        # lets a solver recognise a built-in right-hand side behind the wrappers (tfdiffeq_b200/rhs.py)
+        try:
+            func._b2ode_base, func._b2ode_sign = base, sign
+        except AttributeError:
+            pass
     return tensor_input, func, y0, t

@@ -142,6 +142,8 @@ class AdaptiveStepsizeODESolver(object):
         # extension: capture one attempt (the func calls included) into a CUDA graph and replay it.  Opt-in,
         # because python-side effects of func (e.g. an `nfe` counter on the module) happen once, at capture.
         self.cuda_graph = bool(unused_kwargs.pop("cuda_graph", False))
+        # extension: a built-in right-hand side (tfdiffeq_b200/rhs.py) runs in one persistent kernel unless disabled
+        self.fused_rhs = bool(unused_kwargs.pop("fused_rhs", True))
         _handle_unused_kwargs(self, unused_kwargs)
         del unused_kwargs
         self.func = func
@@ -199,7 +201,61 @@ class AdaptiveStepsizeODESolver(object):
         seg = _Segments(self.y0)
         dev, dtype = seg.device, seg.dtype
         with torch.cuda.device(dev), torch.no_grad():
+            fused = self._integrate_fused(t, seg, dev, dtype) if self.fused_rhs else None
+            if fused is not None:
+                return fused
             return self._integrate(t, seg, dev, dtype)
+
+    def _integrate_fused(self, t, seg, dev, dtype):
+        """Whole solve in one persistent kernel when func is a built-in right-hand side (rhs.py)."""
+        from .rhs import BuiltinRHS
+        base = getattr(self.func, "_b2ode_base", None)
+        tab = self.tableau
+        if not isinstance(base, BuiltinRHS) or seg.nseg != 1 or tab.c_mid is None or tab.n_k not in (2, 4, 7, 14):
+            return None
+        shape = seg.shapes[0]
+        if len(shape) < 1 or shape[-1] != base.dim or seg.lens[0] == 0:
+            return None
+        lib, check = _lib.lib, _lib.check
+        n_traj = seg.lens[0] // base.dim
+        t_host = t.detach().to("cpu", torch.float64).numpy()
+        t_dev = torch.from_numpy(t_host).to(dev)
+        n_out = int(t_host.shape[0])
+        y0 = self.y0[0].contiguous()
+        out = torch.empty((n_out,) + shape, dtype=dtype, device=dev)
+        state_dev = torch.zeros(256, dtype=torch.uint8, device=dev)
+        ws_bytes = int(lib.b2ode_fused_workspace_bytes(n_traj))
+        workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        desc = self._describe(seg)
+        prm = base.rhs_params()
+        prm_arr = (C.c_double * 8)(*(prm + [0.0] * (8 - len(prm))))
+        first = float("nan") if self.first_step is None else _tf_f64(self.first_step)
+        rank, world, boxes, n_glob = 0, 1, None, n_traj
+        if self.comm is not None:
+            rank, world, boxes = self.comm.rank, self.comm.world, self.comm._ptrs
+            n_glob = self.comm.global_count(n_traj)
+        stream = torch.cuda.current_stream(dev)
+        rc = lib.b2ode_fused_solve(C.byref(desc), base.kind, prm_arr, len(prm), float(self.func._b2ode_sign),
+                                   C.c_void_p(y0.data_ptr()), C.c_void_p(out.data_ptr()), C.c_void_p(t_dev.data_ptr()),
+                                   n_out, float(t_host[0]), first, C.c_void_p(state_dev.data_ptr()),
+                                   C.c_void_p(workspace.data_ptr()), ws_bytes, rank, world, boxes, n_glob,
+                                   C.c_void_p(stream.cuda_stream))
+        if rc == -3:          # batch larger than what can stay co-resident: use the generic path
+            return None
+        check(rc)
+        host = torch.empty(256, dtype=torch.uint8).pin_memory()
+        host.copy_(state_dev, non_blocking=True)
+        stream.synchronize()
+        final = _lib.State.from_buffer_copy(host.numpy().tobytes())
+        attempts = int(final.n_acc + final.n_rej)
+        nfe = 1 + (1 if self.first_step is None else 0) + (tab.n_k - 1) * attempts
+        self.stats = dict(n_accepted=int(final.n_acc), n_rejected=int(final.n_rej), nfe=nfe, attempts_enqueued=attempts,
+                          status=int(final.status), cuda_graph=False, fused_rhs=True)
+        last_stats.clear()
+        last_stats.update(self.stats)
+        if final.status:
+            self._raise(final, (out[0],), (y0,))
+        return (out,)
 
     def _integrate(self, t, seg, dev, dtype):
         lib, check = _lib.lib, _lib.check
@@ -336,7 +392,8 @@ class AdaptiveStepsizeODESolver(object):
                     known = _lib.State.from_buffer_copy(slots[slot])
             final = known
             self.stats = dict(n_accepted=int(final.n_acc), n_rejected=int(final.n_rej), nfe=nfe,
-                              attempts_enqueued=n_enq, status=int(final.status), cuda_graph=graph is not None)
+                              attempts_enqueued=n_enq, status=int(final.status), cuda_graph=graph is not None,
+                              fused_rhs=False)
             last_stats.clear()
             last_stats.update(self.stats)
             if final.status:
