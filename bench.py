@@ -9,6 +9,10 @@ workload : configs[1] = Lorenz attractor, batch 65 536 x dim 3, fp64, dopri5 ada
            1 000 output points t = arange(1000) * 0.01, synthetic seeded initial states (cfg 2).
 step     : ONE full odeint() solve of that workload (all accepted + rejected attempts, the dense output of
            all 1 000 points).  value = accepted_steps * state_elements / seconds, aggregated over ranks.
+paths    : --path fused_rhs (default): func = tfdiffeq_b200.rhs.Lorenz, the library's own right-hand side, so the
+           whole solve runs in one persistent kernel; --path external_func_cuda_graph / external_func_eager: func
+           is an arbitrary external PyTorch callable (the general path).  The non-primary paths are measured too
+           and reported under `other_paths`.
 N > 1    : weak scaling -- every rank integrates its own 65 536-trajectory shard; the shards form ONE ODE
            system with a shared step size (reference semantics), the per-attempt error-norm exchange runs
            inside the finalize kernel over NVLink peer memory.
@@ -218,112 +222,106 @@ def run_ours(args, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=dev)
         group = SharedStepGroup()
     peak, peak_src = peaks()
-    f = PROBLEMS["lorenz"](backend="torch", device=dev)
     # weak scaling: every rank owns a full 65 536-trajectory shard (different seed per rank)
     y0_host = torch.from_numpy(lorenz_y0(B, rank)).pin_memory()
     t_host = torch.arange(NPTS, dtype=torch.float64) * 0.01
     out_host = torch.empty((NPTS, B, DIM), dtype=torch.float64).pin_memory()
     y0_dev = y0_host.to(dev)
-    opts = {"cuda_graph": not args.eager}
-    if group is not None:
-        opts["shared_step_group"] = group
-    kw = dict(rtol=RTOL, atol=ATOL, method="dopri5", options=opts)
-    kw_eager = dict(kw, options={k: v for k, v in opts.items() if k != "cuda_graph"})
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)     # > 126 MB L2
+    base_opts = {"shared_step_group": group} if group is not None else {}
+
+    # the three ways the public API can run this workload
+    paths = {
+        # func = the library's own Lorenz module -> whole solve in one persistent kernel (b2ode_fused_solve)
+        "fused_rhs": (tfd.rhs.Lorenz(), dict(base_opts)),
+        # func = an arbitrary external PyTorch callable; one attempt captured in a CUDA graph and replayed
+        "external_func_cuda_graph": (PROBLEMS["lorenz"](backend="torch", device=dev), dict(base_opts, cuda_graph=True)),
+        # same, launched eagerly from python
+        "external_func_eager": (PROBLEMS["lorenz"](backend="torch", device=dev), dict(base_opts)),
+    }
+    primary = args.path
 
     def barrier():
         if world > 1:
             torch.distributed.barrier()
         torch.cuda.synchronize(dev)
 
-    def solve_resident():
-        return tfd.odeint(f, y0_dev, t_host, **kw)
+    def measure(name, steps, warmup, e2e):
+        f, opts = paths[name]
+        kw = dict(rtol=RTOL, atol=ATOL, method="dopri5", options=opts)
 
-    def solve_e2e():
-        y = y0_host.to(dev, non_blocking=True)                    # H2D inside the timed region
-        sol = tfd.odeint(f, y, t_host, **kw)
-        out_host.copy_(sol, non_blocking=True)                    # D2H of the result inside the timed region
+        def solve():
+            if e2e:
+                y = y0_host.to(dev, non_blocking=True)            # H2D of the inputs inside the timed region
+                sol = tfd.odeint(f, y, t_host, **kw)
+                out_host.copy_(sol, non_blocking=True)            # D2H of the whole solution inside the timed region
+                torch.cuda.synchronize(dev)
+            else:
+                tfd.odeint(f, y0_dev, t_host, **kw)
+        for _ in range(warmup):
+            solve()
         torch.cuda.synchronize(dev)
-        return sol
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        acc = rej = 0
+        l0 = int(_lib.lib.b2ode_launch_count())
+        barrier()
+        w0 = time.perf_counter()
+        for i in range(steps):
+            flush.fill_(i & 0xFF)                                 # L2 flush between timed iterations (untimed)
+            ev[i][0].record()
+            solve()
+            ev[i][1].record()
+            acc += tfd.last_stats["n_accepted"]
+            rej += tfd.last_stats["n_rejected"]
+        barrier()
+        wall = time.perf_counter() - w0
+        launches = int(_lib.lib.b2ode_launch_count()) - l0
+        if name == "external_func_cuda_graph":
+            # kernels inside the replayed graph are launched by the graph, not counted by the library's host-side
+            # counter: each replayed attempt runs the same 8 library kernels (6 stages, finalize, dense output)
+            launches += (acc + rej - steps) * 8
+        ms = sum(a.elapsed_time(b) for a, b in ev)
+        work = float(acc) * B * DIM
+        if world > 1:
+            import torch.distributed as dist
+            tt = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ww = torch.tensor([work, float(launches)], dtype=torch.float64, device=dev)
+            dist.all_reduce(ww, op=dist.ReduceOp.SUM)
+            ms, work, launches = float(tt[0]), float(ww[0]), int(ww[1])
+        return dict(value=work / (ms * 1e-3), ms_per_step=ms / steps, n_acc=acc / float(steps), n_rej=rej / float(steps),
+                    launches=launches, wall=wall)
 
-    for _ in range(max(args.warmup, 3)):
-        solve_resident()
-    torch.cuda.synchronize(dev)
-
-    # ---- timed region 1: inputs resident in HBM ------------------------------------------------------------
+    W = max(args.warmup, 3)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    launches0 = int(_lib.lib.b2ode_launch_count())
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    n_acc = n_rej = 0
-    barrier()
-    wall0 = time.perf_counter()
-    for i in range(args.steps):
-        flush.fill_(i & 0xFF)                                     # L2 flush between timed iterations (untimed)
-        ev[i][0].record()
-        solve_resident()
-        ev[i][1].record()
-        n_acc += tfd.last_stats["n_accepted"]
-        n_rej += tfd.last_stats["n_rejected"]
-    barrier()
-    wall1 = time.perf_counter()
-    launches = int(_lib.lib.b2ode_launch_count()) - launches0
-    if not args.eager:
-        # kernels inside the replayed graph are launched by the graph, not counted by the library's host-side
-        # counter: every attempt after the first replays the same 8 library kernels (6 stages, finalize, dense output)
-        launches = int(launches + (n_acc + n_rej - args.steps) * 8)
-    ms = sum(a.elapsed_time(b) for a, b in ev)
-
-    # ---- per-kernel timing pass (eager launches, CUDA events around every finalize launch, same workload) -----
-    _lib.check(_lib.lib.b2ode_timing_enable(1 << _lib.FAM_FINALIZE))
-    eager_ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-    flush.fill_(1)
-    eager_ev[0].record()
-    tfd.odeint(f, y0_dev, t_host, **kw_eager)
-    eager_ev[1].record()
-    torch.cuda.synchronize(dev)
-    eager_ms = eager_ev[0].elapsed_time(eager_ev[1])
-    eager_acc = tfd.last_stats["n_accepted"]
-    fin_ms, fin_cnt = C.c_double(), C.c_int()
-    _lib.check(_lib.lib.b2ode_timing_read(_lib.FAM_FINALIZE, C.byref(fin_ms), C.byref(fin_cnt)))
-    _lib.check(_lib.lib.b2ode_timing_enable(0))
-
-    # ---- timed region 2: end to end through the public API with host buffers -----------------------------------
-    solve_e2e()
-    ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    e2e_acc = 0
-    barrier()
-    for i in range(args.steps):
-        flush.fill_(i & 0xFF)
-        ev2[i][0].record()
-        solve_e2e()
-        ev2[i][1].record()
-        e2e_acc += tfd.last_stats["n_accepted"]
-    barrier()
-    ms2 = sum(a.elapsed_time(b) for a, b in ev2)
+    main_res = measure(primary, args.steps, W, e2e=False)
+    main_e2e = measure(primary, args.steps, 1, e2e=True)
     clocks = sampler.stop() if rank == 0 else None
+    others = {}
+    for name in paths:
+        if name != primary:
+            r = measure(name, max(1, min(args.steps, 2)), 1, e2e=False)
+            others[name] = {"value": r["value"], "unit": UNIT, "ms_per_step": r["ms_per_step"]}
 
-    # ---- aggregate over ranks: max time, summed work ---------------------------------------------------------
-    work = float(n_acc) * B * DIM
-    work2 = float(e2e_acc) * B * DIM
-    if world > 1:
-        import torch.distributed as dist
-        tt = torch.tensor([ms, ms2], dtype=torch.float64, device=dev)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ww = torch.tensor([work, work2, float(launches)], dtype=torch.float64, device=dev)
-        dist.all_reduce(ww, op=dist.ReduceOp.SUM)
-        ms, ms2 = float(tt[0]), float(tt[1])
-        work, work2, launches = float(ww[0]), float(ww[1]), int(ww[2])
-    value = work / (ms * 1e-3)
-    e2e_value = work2 / (ms2 * 1e-3)
+    # ---- per-kernel timing passes (CUDA events recorded by the library around its own launches) ----------------
+    n = B * DIM
+    kern = {}
+    if rank == 0 or world > 1:
+        _lib.check(_lib.lib.b2ode_timing_enable((1 << _lib.FAM_FUSED) | (1 << _lib.FAM_FINALIZE)))
+        for name in ("fused_rhs", "external_func_eager"):
+            f, opts = paths[name]
+            flush.fill_(3)
+            tfd.odeint(f, y0_dev, t_host, rtol=RTOL, atol=ATOL, method="dopri5", options=opts)
+            torch.cuda.synchronize(dev)
+            kern[name] = dict(tfd.last_stats)
+        fus_ms, fus_cnt, fin_ms, fin_cnt = C.c_double(), C.c_int(), C.c_double(), C.c_int()
+        _lib.check(_lib.lib.b2ode_timing_read(_lib.FAM_FUSED, C.byref(fus_ms), C.byref(fus_cnt)))
+        _lib.check(_lib.lib.b2ode_timing_read(_lib.FAM_FINALIZE, C.byref(fin_ms), C.byref(fin_cnt)))
+        _lib.check(_lib.lib.b2ode_timing_enable(0))
 
     if rank == 0:
-        n = B * DIM
-        fin_avg_ms = fin_ms.value / max(fin_cnt.value, 1)
-        fin_bytes = FINALIZE_ELEMS * n * 8
-        fin_gbs = fin_bytes / (fin_avg_ms * 1e-3) / 1e9 if fin_cnt.value else None
-        attempts = (n_acc + n_rej) / float(args.steps)
         headline = None
         cpu = None
         if world == 1:
@@ -337,33 +335,56 @@ def run_ours(args, rank, world, local_rank):
                 cpu = {"value": s["value"], "unit": UNIT, "cores": s["threads"], "kind": "port", "sample": s["sample"],
                        "seconds": s["seconds"], "probe": {"torch_all_threads": pt["value"], "numpy_1_thread": pn["value"],
                                                           "host_cores": os.cpu_count()}}
+        # roofline of the dominant kernel of the primary path
+        fin_avg_ms = fin_ms.value / max(fin_cnt.value, 1)
+        fin_bytes = FINALIZE_ELEMS * n * 8
+        fin_gbs = fin_bytes / (fin_avg_ms * 1e-3) / 1e9 if fin_cnt.value else None
+        finalize_roof = {"kernel": "k_rk_finalize<double,6> (error combine + norm + controller)", "achieved": fin_gbs,
+                         "frac": (fin_gbs / peak) if fin_gbs else None, "algorithmic_bytes_per_launch": fin_bytes,
+                         "avg_launch_ms": fin_avg_ms, "launches_timed": fin_cnt.value,
+                         "note": "8 x 1.5 MiB read streams per launch: L2-resident and launch-latency bound at this size "
+                                 "(eager pass; event pairs include the inter-launch gap); roofline_headline has the HBM-bound size"}
+        if primary == "fused_rhs" and fus_cnt.value:
+            ks = kern["fused_rhs"]
+            fus_avg = fus_ms.value / fus_cnt.value
+            # 352 B of HBM traffic per accepted fp64 element-step is what a func-external design must move;
+            # the persistent kernel keeps state and k's in registers and only writes the solution slab
+            alg = BYTES_PER_ELEM_STEP_FP64 * ks["n_accepted"] * n + 48 * NPTS * n
+            slab = NPTS * n * 8 + n * 8
+            roof = {"bound": "hbm", "kernel": "k_fused_adaptive<double, RhsLorenz<double>, 7> (one launch = one whole solve)",
+                    "achieved": alg / (fus_avg * 1e-3) / 1e9, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                    "frac": alg / (fus_avg * 1e-3) / 1e9 / peak, "traffic": None,
+                    "algorithmic_bytes_per_launch": int(alg), "avg_launch_ms": fus_avg, "launches_timed": fus_cnt.value,
+                    "bytes_actually_needed_per_launch": int(slab), "slab_write_GBps": slab / (fus_avg * 1e-3) / 1e9,
+                    "note": "achieved uses SURVEY 8(d)'s per-unit bytes (the traffic of a design with func outside the kernel): "
+                            "frac > 1 means the kernel avoids that traffic (state + k's in registers); its real HBM traffic is "
+                            "the solution slab (`bytes_actually_needed_per_launch`), and its time is set by %d grid-wide "
+                            "reductions (one per attempt), not by HBM" % (ks["n_accepted"] + ks["n_rejected"] + 2),
+                    "finalize_kernel_generic_path": finalize_roof}
+        else:
+            roof = dict({"bound": "hbm", "peak": peak, "peak_source": peak_src, "unit": "GB/s", "traffic": None}, **finalize_roof)
+        func_desc = {"fused_rhs": "tfdiffeq_b200.rhs.Lorenz (library right-hand side: whole solve in one persistent kernel)",
+                     "external_func_cuda_graph": "external PyTorch callable (tests/problems.py:Lorenz, 9 torch kernels per call), "
+                                                 "options={'cuda_graph': True}",
+                     "external_func_eager": "external PyTorch callable (tests/problems.py:Lorenz), eager launches"}[primary]
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "metric": METRIC, "value": main_res["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
+            "ms_per_step": main_res["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": "lorenz_b65536x3_f64_dopri5_1000pts", "per_gpu_batch": B, "dim": DIM, "rtol": RTOL,
-                       "atol": ATOL, "n_out": NPTS, "func": "external PyTorch callable (tests/problems.py:Lorenz), 9 torch kernels per call",
-                       "cuda_graph": not args.eager,
+                       "atol": ATOL, "n_out": NPTS, "path": primary, "func": func_desc,
                        "l2": "flushed between timed iterations (256 MiB write)",
                        "parallelism": "batch shards, shared step via in-kernel NVLink mailbox exchange" if world > 1 else "single GPU",
-                       "accepted_per_solve": n_acc / float(args.steps), "rejected_per_solve": n_rej / float(args.steps)},
-            "roofline": {"bound": "hbm", "kernel": "k_rk_finalize<double,6> (error combine + norm + controller)",
-                         "achieved": fin_gbs, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                         "frac": (fin_gbs / peak) if fin_gbs else None, "traffic": None,
-                         "algorithmic_bytes_per_launch": fin_bytes, "avg_launch_ms": fin_avg_ms, "launches_timed": fin_cnt.value,
-                         "note": "8 x 1.5 MiB read streams per launch: L2-resident and launch-latency bound at this "
-                                 "workload size (timed on an eager pass of the same solve; event pairs include the "
-                                 "inter-launch gap); see roofline_headline for the HBM-bound size",
-                         "step_algorithmic_GBps": BYTES_PER_ELEM_STEP_FP64 * value / 1e9},
+                       "accepted_per_solve": main_res["n_acc"], "rejected_per_solve": main_res["n_rej"]},
+            "roofline": roof,
             "roofline_headline": headline,
             "cpu_baseline": cpu,
-            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms2 / args.steps,
+            "e2e": {"value": main_e2e["value"], "unit": UNIT, "ms_per_step": main_e2e["ms_per_step"],
                     "h2d_bytes_per_step": int(B * DIM * 8 + NPTS * 8), "d2h_bytes_per_step": int(NPTS * B * DIM * 8)},
-            "gpu_launches": launches,
-            "eager_path": {"value": eager_acc * B * DIM * (world if world > 1 else 1) / (eager_ms * 1e-3), "unit": UNIT,
-                           "ms_per_step": eager_ms, "note": "same solve without options={'cuda_graph': True} (rank 0)"},
-            "attempts_per_solve": attempts,
-            "wall_s_timed_region": wall1 - wall0,
+            "gpu_launches": main_res["launches"],
+            "other_paths": others,
+            "attempts_per_solve": main_res["n_acc"] + main_res["n_rej"],
+            "wall_s_timed_region": main_res["wall"],
             "clocks": clocks,
         }
         print(json.dumps(line))
@@ -379,7 +400,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--eager", action="store_true", help="do not use options={'cuda_graph': True}")
+    ap.add_argument("--path", default="fused_rhs", choices=["fused_rhs", "external_func_cuda_graph", "external_func_eager"],
+                    help="which public-API path is the primary (timed) one; the others are reported under other_paths")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

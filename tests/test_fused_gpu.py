@@ -103,7 +103,7 @@ def test_fused_status_bits_and_fallbacks():
     with pytest.raises(AssertionError, match="non-finite values in state"):
         tfd().odeint(f, bad, t, method="dopri5", options=dict(first_step=0.01))
     # a state whose last axis is not the system dimension, a tuple state, tsit5 -> generic path, same API
-    out = tfd().odeint(f, (y0,), torch.tensor([0., 0.1]), method="dopri5")
+    out = tfd().odeint(lambda t, y: (f(t, y[0]),), (y0,), torch.tensor([0., 0.1]), method="dopri5")
     assert isinstance(out, tuple) and not tfd().last_stats["fused_rhs"]
     tfd().odeint(f, y0, torch.tensor([0., 0.001]), method="tsit5", rtol=1e-2, atol=1e-2)
     assert not tfd().last_stats["fused_rhs"]

@@ -845,7 +845,7 @@ extern "C" int b2ode_comm_set_global_len(b2ode_solver *s, const int64_t *global_
 static unsigned long long g_launches = 0;
 void b2_count_launch(void) { ++g_launches; }
 
-enum { B2_FAM_STAGE0 = 0, B2_FAM_STAGE = 1, B2_FAM_FINALIZE = 2, B2_FAM_EMIT = 3, B2_FAM_INIT = 4, B2_FAM_FIXED = 5, B2_NFAM = 6 };
+enum { B2_FAM_STAGE0 = 0, B2_FAM_STAGE = 1, B2_FAM_FINALIZE = 2, B2_FAM_EMIT = 3, B2_FAM_INIT = 4, B2_FAM_FIXED = 5, B2_FAM_FUSED = 6, B2_NFAM = 7 };
 constexpr int kMaxTimed = 2048;   // event pairs per family
 
 struct Timing {
@@ -878,8 +878,21 @@ static int launch(K kernel, int grid, cudaStream_t st, const P &p, int fam = -1)
 
 extern "C" unsigned long long b2ode_launch_count(void) { return g_launches; }
 
+// event pair around a launch made elsewhere (b2ode_fused.cu); returns the slot or -1
+int b2_timing_begin(int fam, cudaStream_t st) {
+    Timing *tm = g_timing;
+    if (!(tm && fam >= 0 && fam < B2_NFAM && ((tm->mask >> fam) & 1u) && tm->n[fam] < kMaxTimed)) return -1;
+    if (cudaEventRecord(tm->ev[fam][tm->n[fam]][0], st) != cudaSuccess) return -1;
+    return tm->n[fam];
+}
+void b2_timing_end(int fam, int slot, cudaStream_t st) {
+    if (slot < 0) return;
+    Timing *tm = g_timing;
+    if (cudaEventRecord(tm->ev[fam][slot][1], st) == cudaSuccess) tm->n[fam] = slot + 1;
+}
+
 // Enable CUDA-event timing of the kernel families in `family_mask` (bit f = family f: 0 stage0, 1 stage,
-// 2 finalize, 3 dense output, 4 initial step, 5 fixed grid); 0 disables.  Resets the counters.
+// 2 finalize, 3 dense output, 4 initial step, 5 fixed grid, 6 fused persistent solve); 0 disables.  Resets the counters.
 extern "C" int b2ode_timing_enable(unsigned family_mask) {
     if (!g_timing) {
         g_timing = new (std::nothrow) Timing();

@@ -18,6 +18,8 @@ static_assert(sizeof(b2ode_state) == 256, "b2ode_state must stay 256 bytes");
 // ------------------------------------------------------------------------------------------------
 int b2_fail(int code, const char *fmt, ...);      // defined in b2ode.cu; records the thread-local error string
 void b2_count_launch(void);                     // bench.py's gpu_launches counter (b2ode.cu)
+int b2_timing_begin(int fam, cudaStream_t st);  // optional CUDA-event timing of a kernel family (b2ode.cu)
+void b2_timing_end(int fam, int slot, cudaStream_t st);
 
 #define B2_CUDA(x)                                                                         \
     do {                                                                                   \

@@ -425,7 +425,9 @@ static int fused_launch(const FusedParams &p, int grid, cudaStream_t st) {
     if (!coop) return b2_fail(B2ODE_ESTATE, "device does not support cooperative launch");
     if (grid > per_sm * nsm)
         return b2_fail(B2ODE_ENOMEM, "batch needs %d co-resident blocks, device holds %d", grid, per_sm * nsm);
+    const int slot = b2_timing_begin(6 /* B2_FAM_FUSED */, st);
     B2_CUDA(cudaLaunchCooperativeKernel((const void *)k_fused_adaptive<T, RHS, S>, dim3(grid), dim3(kFThreads), args, 0, st));
+    b2_timing_end(6, slot, st);
     b2_count_launch();
     return 0;
 }
