@@ -12,8 +12,8 @@
 
 #include "b2ode_dev.cuh"
 
-constexpr int kFThreads = 128;
-constexpr int kFWarps = kFThreads / 32;
+// Block size is a template parameter: 512 threads (one block per SM, the fewest barrier arrivals and partials)
+// when the kernel fits in 128 registers per thread, 128 threads otherwise.
 
 // ------------------------------------------------------------------------------------------------
 // built-in right-hand sides: explicit mul/add in the order of the torch expressions in rhs.py
@@ -47,7 +47,7 @@ struct RhsLotkaVolterra {   // README.md:67-81 ; params {a, b, c, d}
 struct FusedParams {
     b2ode_state *st;
     Partial *part;          // [2][gridDim.x], double buffered by reduction parity
-    unsigned *bar;          // bar[0] = arrival counter, bar[1] = generation
+    unsigned *bar;          // monotonically increasing arrival counter of the grid barrier
     Partial *gtot;          // [2]: group totals published by block 0 when a shared-step group is attached
     unsigned long long *gflag;
     const void *y0;
@@ -66,27 +66,29 @@ struct FusedParams {
     CommParams comm;
 };
 
-__device__ __forceinline__ void grid_barrier(unsigned *bar) {
+__device__ __forceinline__ unsigned ld_acquire_gpu_u32(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Grid barrier on a monotonically increasing arrival counter (zeroed by the host before the launch): barrier
+// number e is passed once the counter reaches e * gridDim.x.  One atomic and one polled word per block.
+__device__ __forceinline__ void grid_barrier(unsigned *count, unsigned &epoch) {
     __syncthreads();
+    epoch += 1u;
     if (threadIdx.x == 0) {
-        volatile unsigned *gen = bar + 1;
-        const unsigned g = *gen;
+        const unsigned target = epoch * gridDim.x;
         __threadfence();
-        if (atomicAdd(bar, 1u) == gridDim.x - 1) {
-            bar[0] = 0;
-            __threadfence();
-            atomicAdd(bar + 1, 1u);
-        } else {
-            while (*gen == g) {
-            }
+        atomicAdd(count, 1u);
+        while (ld_acquire_gpu_u32(count) < target) {
         }
-        __threadfence();
     }
     __syncthreads();
 }
 
-template <unsigned MM>
-__device__ __forceinline__ Partial fblock_reduce(Partial x, Partial *sh /*[kFWarps]*/) {
+template <unsigned MM, int BT>
+__device__ __forceinline__ Partial fblock_reduce(Partial x, Partial *sh /*[BT/32]*/) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         Partial y;
@@ -100,20 +102,21 @@ __device__ __forceinline__ Partial fblock_reduce(Partial x, Partial *sh /*[kFWar
     __syncthreads();
     Partial r = sh[0];
 #pragma unroll
-    for (int i = 1; i < kFWarps; ++i) r = combine<MM>(r, sh[i]);
+    for (int i = 1; i < BT / 32; ++i) r = combine<MM>(r, sh[i]);
     return r;   // valid in EVERY thread
 }
 
 // All threads of the grid call this with their own contribution; all return the same (group-wide) totals.
-template <unsigned MM>
+template <unsigned MM, int BT>
 __device__ Partial grid_reduce(const FusedParams &p, Partial mine, unsigned &parity, Partial *sh, Partial *sh_tot) {
     Partial *part = p.part + (size_t)(parity & 1u) * gridDim.x;
-    Partial b = fblock_reduce<MM>(mine, sh);
+    Partial b = fblock_reduce<MM, BT>(mine, sh);
     if (threadIdx.x == 0) part[blockIdx.x] = b;
-    grid_barrier(p.bar);
+    grid_barrier(p.bar, parity);            // the barrier epoch is the reduction count
+    parity -= 1u;
     Partial acc = identity<MM>();
-    for (int i = threadIdx.x; i < (int)gridDim.x; i += kFThreads) acc = combine<MM>(acc, part[i]);
-    Partial tot = fblock_reduce<MM>(acc, sh);
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += BT) acc = combine<MM>(acc, part[i]);
+    Partial tot = fblock_reduce<MM, BT>(acc, sh);
     if (p.comm.nranks > 1) {
         // block 0 exchanges with the peer GPUs and publishes the group totals; the others wait for them
         const unsigned long long want = (unsigned long long)(parity + 1u);
@@ -148,13 +151,13 @@ __device__ Partial grid_reduce(const FusedParams &p, Partial mine, unsigned &par
 // ------------------------------------------------------------------------------------------------
 // the persistent solve
 // ------------------------------------------------------------------------------------------------
-template <typename T, typename RHS, int S>
-__global__ void __launch_bounds__(kFThreads) k_fused_adaptive(const __grid_constant__ FusedParams p) {
+template <typename T, typename RHS, int S, int BT>
+__global__ void __launch_bounds__(BT) k_fused_adaptive(const __grid_constant__ FusedParams p) {
     using A = Ar<T>;
     constexpr int D = RHS::D;
-    __shared__ Partial sh[kFWarps];
+    __shared__ Partial sh[BT / 32];
     __shared__ Partial sh_tot[1];
-    const long long i = (long long)blockIdx.x * kFThreads + threadIdx.x;
+    const long long i = (long long)blockIdx.x * BT + threadIdx.x;
     const bool live = i < p.n_traj;
     const long long N = p.n_traj * D;
     const T *y0g = (const T *)p.y0;
@@ -201,7 +204,7 @@ __global__ void __launch_bounds__(kFThreads) k_fused_adaptive(const __grid_const
                 mine.v[1] += q1 * q1;
             }
         }
-        Partial tot = grid_reduce<0u>(p, mine, parity, sh, sh_tot);
+        Partial tot = grid_reduce<0u, BT>(p, mine, parity, sh, sh_tot);
         T d1max;
         const T h0 = init_h0<T>(p.c, &tot, 1, &d1max);
         T y1[D], f1[D];
@@ -216,7 +219,7 @@ __global__ void __launch_bounds__(kFThreads) k_fused_adaptive(const __grid_const
                 mine.v[0] += q * q;
             }
         }
-        tot = grid_reduce<0u>(p, mine, parity, sh, sh_tot);
+        tot = grid_reduce<0u, BT>(p, mine, parity, sh, sh_tot);
         dt = (double)init_dt<T>(p.c, &tot, 1, h0, d1max);
     }
     int done = (p.c.n_out <= 1) ? 1 : 0;
@@ -300,7 +303,7 @@ __global__ void __launch_bounds__(kFThreads) k_fused_adaptive(const __grid_const
             mine.v[2] = m1.value();
             mine.v[3] = bad ? 1.0 : 0.0;
         }
-        const Partial tot = grid_reduce<0xEu>(p, mine, parity, sh, sh_tot);
+        const Partial tot = grid_reduce<0xEu, BT>(p, mine, parity, sh, sh_tot);
         const CtrlDecision dec = ctrl_decide<T>(p.c, &tot, 1, dt);
         const bool accept = dec.accept && true;
         if (dec.bad0) status |= B2ODE_ST_NONFINITE;
@@ -414,40 +417,42 @@ __global__ void __launch_bounds__(kFThreads) k_fused_adaptive(const __grid_const
 // ================================================================================================
 // host side
 // ================================================================================================
-template <typename T, typename RHS, int S>
-static int fused_launch(const FusedParams &p, int grid, cudaStream_t st) {
+template <typename T, typename RHS, int S, int BT>
+static int fused_launch(const FusedParams &p, long long n_traj, cudaStream_t st) {
     void *args[] = {(void *)&p};
     int dev = 0, coop = 0, nsm = 0, per_sm = 0;
     B2_CUDA(cudaGetDevice(&dev));
     B2_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
     B2_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
-    B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused_adaptive<T, RHS, S>, kFThreads, 0));
+    B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused_adaptive<T, RHS, S, BT>, BT, 0));
     if (!coop) return b2_fail(B2ODE_ESTATE, "device does not support cooperative launch");
+    const int grid = (int)((n_traj + BT - 1) / BT);
     if (grid > per_sm * nsm)
-        return b2_fail(B2ODE_ENOMEM, "batch needs %d co-resident blocks, device holds %d", grid, per_sm * nsm);
+        return b2_fail(B2ODE_ENOMEM, "batch needs %d co-resident blocks of %d threads, device holds %d", grid, BT, per_sm * nsm);
     const int slot = b2_timing_begin(6 /* B2_FAM_FUSED */, st);
-    B2_CUDA(cudaLaunchCooperativeKernel((const void *)k_fused_adaptive<T, RHS, S>, dim3(grid), dim3(kFThreads), args, 0, st));
+    B2_CUDA(cudaLaunchCooperativeKernel((const void *)k_fused_adaptive<T, RHS, S, BT>, dim3(grid), dim3(BT), args, 0, st));
     b2_timing_end(6, slot, st);
     b2_count_launch();
     return 0;
 }
 
 template <typename T, typename RHS>
-static int fused_dispatch_s(const FusedParams &p, int n_k, int grid, cudaStream_t st) {
+static int fused_dispatch_s(const FusedParams &p, int n_k, long long n_traj, cudaStream_t st) {
+    // 512-thread blocks (<= 128 registers per thread) for the tableaus whose k-set fits; 128 otherwise
     switch (n_k) {
-        case 2: return fused_launch<T, RHS, 2>(p, grid, st);
-        case 4: return fused_launch<T, RHS, 4>(p, grid, st);
-        case 7: return fused_launch<T, RHS, 7>(p, grid, st);
-        case 14: return fused_launch<T, RHS, 14>(p, grid, st);
+        case 2: return fused_launch<T, RHS, 2, 512>(p, n_traj, st);
+        case 4: return fused_launch<T, RHS, 4, 512>(p, n_traj, st);
+        case 7: return fused_launch<T, RHS, 7, 512>(p, n_traj, st);
+        case 14: return fused_launch<T, RHS, 14, 128>(p, n_traj, st);
     }
     return b2_fail(B2ODE_EINVAL, "fused solve supports tableaus with 2, 4, 7 or 14 k's (got %d)", n_k);
 }
 
 template <typename T>
-static int fused_dispatch_rhs(const FusedParams &p, int rhs_kind, int n_k, int grid, cudaStream_t st) {
+static int fused_dispatch_rhs(const FusedParams &p, int rhs_kind, int n_k, long long n_traj, cudaStream_t st) {
     switch (rhs_kind) {
-        case B2ODE_RHS_LORENZ: return fused_dispatch_s<T, RhsLorenz<T>>(p, n_k, grid, st);
-        case B2ODE_RHS_LOTKA_VOLTERRA: return fused_dispatch_s<T, RhsLotkaVolterra<T>>(p, n_k, grid, st);
+        case B2ODE_RHS_LORENZ: return fused_dispatch_s<T, RhsLorenz<T>>(p, n_k, n_traj, st);
+        case B2ODE_RHS_LOTKA_VOLTERRA: return fused_dispatch_s<T, RhsLotkaVolterra<T>>(p, n_k, n_traj, st);
     }
     return b2_fail(B2ODE_EINVAL, "unknown built-in right-hand side %d", rhs_kind);
 }
@@ -455,7 +460,7 @@ static int fused_dispatch_rhs(const FusedParams &p, int rhs_kind, int n_k, int g
 static int rhs_dim(int kind) { return kind == B2ODE_RHS_LORENZ ? 3 : kind == B2ODE_RHS_LOTKA_VOLTERRA ? 2 : -1; }
 
 extern "C" size_t b2ode_fused_workspace_bytes(int64_t n_traj) {
-    const long long grid = (n_traj + kFThreads - 1) / kFThreads;
+    const long long grid = (n_traj + 127) / 128;      // the smallest block size used is 128
     // [2][grid] partials + 2 group totals + barrier words + flag, 256-byte aligned pieces
     return (size_t)(2 * grid + 2) * sizeof(Partial) + 256;
 }
@@ -473,7 +478,6 @@ extern "C" int b2ode_fused_solve(const b2ode_adaptive_desc *desc, int rhs_kind, 
     const long long n_traj = desc->seg_len[0] / D;
     if (n_traj < 1) return b2_fail(B2ODE_EINVAL, "empty batch");
     if (workspace_bytes < b2ode_fused_workspace_bytes(n_traj)) return b2_fail(B2ODE_ENOMEM, "workspace too small");
-    const int grid = (int)((n_traj + kFThreads - 1) / kFThreads);
     cudaStream_t st = (cudaStream_t)cuda_stream;
     // workspace layout: [barrier 2 x u32 | pad to 64][flag u64 | pad to 128][gtot x2][partials 2 x grid]
     unsigned char *w = (unsigned char *)workspace;
@@ -524,7 +528,7 @@ extern "C" int b2ode_fused_solve(const b2ode_adaptive_desc *desc, int rhs_kind, 
         if (!mailboxes || nranks > B2ODE_MAXPEERS) return b2_fail(B2ODE_EINVAL, "bad mailboxes");
         for (int r = 0; r < nranks; ++r) p.comm.box[r] = (Mailbox *)mailboxes[r];
     }
-    if (desc->dtype == B2ODE_F64) return fused_dispatch_rhs<double>(p, rhs_kind, nk, grid, st);
-    if (desc->dtype == B2ODE_F32) return fused_dispatch_rhs<float>(p, rhs_kind, nk, grid, st);
+    if (desc->dtype == B2ODE_F64) return fused_dispatch_rhs<double>(p, rhs_kind, nk, n_traj, st);
+    if (desc->dtype == B2ODE_F32) return fused_dispatch_rhs<float>(p, rhs_kind, nk, n_traj, st);
     return b2_fail(B2ODE_EINVAL, "dtype must be 0 or 1");
 }
