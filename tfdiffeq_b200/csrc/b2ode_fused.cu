@@ -149,6 +149,106 @@ __device__ Partial grid_reduce(const FusedParams &p, Partial mine, unsigned &par
 }
 
 // ------------------------------------------------------------------------------------------------
+// per-attempt reduction: {sum err^2, max|y0|, max|y1|}.  For non-negative doubles the IEEE order is the order
+// of the bit patterns read as unsigned integers, and every NaN pattern sorts above +inf, so an integer max is a
+// NaN-propagating max for free; "y0 is non-finite" is simply max|y0| >= +inf (no fourth column).
+// ------------------------------------------------------------------------------------------------
+struct FRed {
+    double sum;
+    unsigned long long m0, m1;
+};
+
+__device__ __forceinline__ unsigned long long umax64(unsigned long long a, unsigned long long b) { return a > b ? a : b; }
+
+__device__ __forceinline__ FRed fred_combine(const FRed &a, const FRed &b) {
+    FRed r;
+    r.sum = a.sum + b.sum;
+    r.m0 = umax64(a.m0, b.m0);
+    r.m1 = umax64(a.m1, b.m1);
+    return r;
+}
+
+template <int BT>
+__device__ __forceinline__ FRed fred_block(FRed x, FRed *sh /*[BT/32]*/) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        FRed y;
+        y.sum = __shfl_xor_sync(0xffffffffu, x.sum, o);
+        y.m0 = __shfl_xor_sync(0xffffffffu, x.m0, o);
+        y.m1 = __shfl_xor_sync(0xffffffffu, x.m1, o);
+        x = fred_combine(x, y);
+    }
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();
+    if (l == 0) sh[w] = x;
+    __syncthreads();
+    FRed r = sh[0];
+#pragma unroll
+    for (int i = 1; i < BT / 32; ++i) r = fred_combine(r, sh[i]);
+    return r;   // valid in EVERY thread
+}
+
+// Grid-wide version; returns the totals as a Partial (columns as in the generic finalize kernel) in every thread.
+template <int BT>
+__device__ Partial fred_grid(const FusedParams &p, FRed mine, unsigned &parity, FRed *shf, Partial *sh, Partial *sh_tot) {
+    FRed *part = reinterpret_cast<FRed *>(p.part) + (size_t)(parity & 1u) * gridDim.x;
+    FRed b = fred_block<BT>(mine, shf);
+    if (threadIdx.x == 0) part[blockIdx.x] = b;
+    grid_barrier(p.bar, parity);
+    parity -= 1u;
+    FRed acc;
+    acc.sum = 0.0;
+    acc.m0 = acc.m1 = 0ull;
+    // gridDim.x <= 148 * blocks/SM: the first warps hold everything, the rest contribute the identity
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += BT) acc = fred_combine(acc, part[i]);
+    FRed t = fred_block<BT>(acc, shf);
+    Partial tot;
+    tot.v[0] = t.sum;
+    tot.v[1] = __longlong_as_double((long long)t.m0);
+    tot.v[2] = __longlong_as_double((long long)t.m1);
+    tot.v[3] = (t.m0 >= 0x7ff0000000000000ull) ? 1.0 : 0.0;     // inf or NaN somewhere in y0
+    if (p.comm.nranks > 1) {
+        const unsigned long long want = (unsigned long long)(parity + 1u);
+        if (blockIdx.x == 0) {
+            if (threadIdx.x == 0) sh_tot[0] = tot;
+            __syncthreads();
+            group_combine<0xEu>(p.comm, p.st, sh_tot, 1);
+            if (threadIdx.x == 0) {
+                p.gtot[parity & 1u] = sh_tot[0];
+                __threadfence();
+                atomicExch(p.gflag, want);
+            }
+            __syncthreads();
+            tot = sh_tot[0];
+        } else {
+            if (threadIdx.x == 0) {
+                volatile unsigned long long *f = p.gflag;
+                while (*f < want) {
+                }
+                __threadfence();
+                sh_tot[0] = p.gtot[parity & 1u];
+            }
+            __syncthreads();
+            tot = sh_tot[0];
+            __syncthreads();
+        }
+    }
+    parity += 1u;
+    return tot;
+}
+
+// what the controller (thread 0 of each block, identical everywhere) hands to the other threads of the block
+struct CtlOut {
+    double dt_next, t1_new;
+    int accept, cur, done;
+    unsigned status;
+    // bookkeeping only thread 0 touches (kept out of everybody's registers)
+    double m, t_prev, dt_last;
+    unsigned long long n_acc, n_rej, attempts;
+    long long nadv;
+};
+
+// ------------------------------------------------------------------------------------------------
 // the persistent solve
 // ------------------------------------------------------------------------------------------------
 template <typename T, typename RHS, int S, int BT>
@@ -227,11 +327,22 @@ __global__ void __launch_bounds__(BT) k_fused_adaptive(const __grid_constant__ F
         status |= B2ODE_ST_UNDERFLOW;
         done = 1;
     }
-    unsigned long long n_acc = 0, n_rej = 0, attempts = 0;
-    long long nadv = 0;
-    double t_prev = t_cur, dt_last = 0.0, msr = 0.0;
 
     // ---- attempts -------------------------------------------------------------------------------------
+    __shared__ FRed shf[BT / 32];
+    __shared__ CtlOut ctl;
+    if (threadIdx.x == 0) {
+        ctl.m = 0.0;
+        ctl.t_prev = t_cur;
+        ctl.dt_last = 0.0;
+        ctl.n_acc = ctl.n_rej = ctl.attempts = 0ull;
+        ctl.nadv = 0;
+        ctl.cur = cur;
+        ctl.status = status;
+        ctl.dt_next = dt;
+        ctl.t1_new = t_cur;
+    }
+    __syncthreads();
     while (!done) {
         const T t0c = (T)t_cur, dtc = (T)dt;                               // rk_common.py:45-46
         T k[S][D];
@@ -241,114 +352,159 @@ __global__ void __launch_bounds__(BT) k_fused_adaptive(const __grid_constant__ F
 #pragma unroll
         for (int s = 0; s < S - 1; ++s) {
             const T ti = A::add(t0c, A::mul((T)p.c.alpha[s], dtc));
+            T acc[D];
+            bool first = true;
 #pragma unroll
-            for (int d = 0; d < D; ++d) {
-                T acc = T(0);
-                bool first = true;
+            for (int j = 0; j <= s; ++j) {
+                const double bj = p.beta[s][j];
+                if (bj != 0.0) {                                           // uniform: the tableau's structural zeros
+                    const T c = A::mul(dtc, (T)bj);                        // (scale * x), misc.py:121
 #pragma unroll
-                for (int j = 0; j <= s; ++j) {
-                    const double bj = p.beta[s][j];
-                    if (bj != 0.0) {
-                        const T term = A::mul(A::mul(dtc, (T)bj), k[j][d]);
-                        acc = first ? term : A::add(acc, term);
-                        first = false;
+                    for (int d = 0; d < D; ++d) {
+                        const T term = A::mul(c, k[j][d]);
+                        acc[d] = first ? term : A::add(acc[d], term);
                     }
+                    first = false;
                 }
-                yi[d] = A::add(y[d], acc);
             }
+#pragma unroll
+            for (int d = 0; d < D; ++d) yi[d] = first ? y[d] : A::add(y[d], acc[d]);
             rhs(ti, yi, k[s + 1]);
         }
         if (!p.fsal) {                                                     // rk_common.py:54-56
+            T acc[D];
+            bool first = true;
 #pragma unroll
-            for (int d = 0; d < D; ++d) {
-                T acc = T(0);
-                bool first = true;
+            for (int j = 0; j < S; ++j) {
+                const double cj = p.c_sol[j];
+                if (cj != 0.0) {
+                    const T c = A::mul(dtc, (T)cj);
 #pragma unroll
-                for (int j = 0; j < S; ++j) {
-                    const double cj = p.c_sol[j];
-                    if (cj != 0.0) {
-                        const T term = A::mul(A::mul(dtc, (T)cj), k[j][d]);
-                        acc = first ? term : A::add(acc, term);
-                        first = false;
+                    for (int d = 0; d < D; ++d) {
+                        const T term = A::mul(c, k[j][d]);
+                        acc[d] = first ? term : A::add(acc[d], term);
                     }
+                    first = false;
                 }
-                yi[d] = A::add(y[d], acc);
             }
+#pragma unroll
+            for (int d = 0; d < D; ++d) yi[d] = first ? y[d] : A::add(y[d], acc[d]);
         }
         // error estimate + this thread's share of the reduction (rk_common.py:60, misc.py:256-263)
-        Partial mine = identity<0xEu>();
-        if (live) {
-            AbsMax<T> m0, m1;
-            bool bad = false;
+        FRed mine;
+        mine.sum = 0.0;
+        mine.m0 = mine.m1 = 0ull;
+        {
+            T err[D];
+            bool first = true;
 #pragma unroll
-            for (int d = 0; d < D; ++d) {
-                T err = T(0);
-                bool first = true;
+            for (int j = 0; j < S; ++j) {
+                const double cj = p.c_error[j];
+                if (cj != 0.0) {
+                    const T c = A::mul(dtc, (T)cj);
 #pragma unroll
-                for (int j = 0; j < S; ++j) {
-                    const double cj = p.c_error[j];
-                    if (cj != 0.0) {
-                        const T term = A::mul(A::mul(dtc, (T)cj), k[j][d]);
-                        err = first ? term : A::add(err, term);
-                        first = false;
+                    for (int d = 0; d < D; ++d) {
+                        const T term = A::mul(c, k[j][d]);
+                        err[d] = first ? term : A::add(err[d], term);
                     }
+                    first = false;
                 }
-                const double ed = (double)err;
-                mine.v[0] += ed * ed;
-                m0.see(y[d]);
-                m1.see(yi[d]);
-                bad |= !isfinite((double)y[d]);
             }
-            mine.v[1] = m0.value();
-            mine.v[2] = m1.value();
-            mine.v[3] = bad ? 1.0 : 0.0;
+            if (live) {
+#pragma unroll
+                for (int d = 0; d < D; ++d) {
+                    const double ed = first ? 0.0 : (double)err[d];
+                    mine.sum += ed * ed;
+                    mine.m0 = umax64(mine.m0, (unsigned long long)__double_as_longlong(fabs((double)y[d])));
+                    mine.m1 = umax64(mine.m1, (unsigned long long)__double_as_longlong(fabs((double)yi[d])));
+                }
+            }
         }
-        const Partial tot = grid_reduce<0xEu, BT>(p, mine, parity, sh, sh_tot);
-        const CtrlDecision dec = ctrl_decide<T>(p.c, &tot, 1, dt);
-        const bool accept = dec.accept && true;
-        if (dec.bad0) status |= B2ODE_ST_NONFINITE;
-        const double t1_new = accept ? t_cur + dt : t_cur;
+        const Partial tot = fred_grid<BT>(p, mine, parity, shf, sh, sh_tot);
+        // controller: once per block (thread 0), identical in every block; broadcast through shared memory
+        if (threadIdx.x == 0) {
+            const CtrlDecision dec = ctrl_decide<T>(p.c, &tot, 1, dt);
+            unsigned st_bits = status;
+            if (dec.bad0) st_bits |= B2ODE_ST_NONFINITE;
+            const double t1n = dec.accept ? t_cur + dt : t_cur;
+            int c2 = cur;
+            if (dec.accept && !dec.bad0) {
+                while (c2 < p.c.n_out && p.c.t_out[c2] <= t1n) ++c2;        // advance(): `while next_t > t1`
+            }
+            const long long nadv2 = (c2 > cur) ? 0 : ctl.nadv + 1;
+            int dn = (c2 >= p.c.n_out) ? 1 : 0;
+            if (!dn) {
+                if (nadv2 >= p.c.max_num_steps) st_bits |= B2ODE_ST_MAXSTEPS;
+                if (!(t1n + dec.dt_next > t1n)) st_bits |= B2ODE_ST_UNDERFLOW;
+            }
+            if (st_bits) dn = 1;
+            ctl.dt_next = dec.dt_next;
+            ctl.t1_new = t1n;
+            ctl.m = dec.m;
+            ctl.accept = dec.accept ? 1 : 0;
+            ctl.cur = c2;
+            ctl.done = dn;
+            ctl.status = st_bits;
+            ctl.nadv = nadv2;
+            ctl.dt_last = dt;
+            ctl.attempts += 1;
+            if (dec.accept) {
+                ctl.n_acc += 1;
+                ctl.t_prev = t_cur;
+            } else {
+                ctl.n_rej += 1;
+            }
+        }
+        __syncthreads();
+        const bool accept = ctl.accept != 0;
+        const double t1_new = ctl.t1_new;
         const int j0 = cur;
-        if (accept && !dec.bad0) {
-            while (cur < p.c.n_out && p.c.t_out[cur] <= t1_new) ++cur;      // advance(): `while next_t > t1`
-        }
+        cur = ctl.cur;
         if (accept && cur > j0 && live) {
             // dense output for every output time inside the step (dopri5.py:39-45, interp.py:22-67)
             const T t0s = t0c, t1s = (T)t1_new;
             const T den = A::sub(t1s, t0s);
             const T m2dt = A::mul(T(-2), dtc), p2dt = A::mul(T(2), dtc), p5dt = A::mul(T(5), dtc);
             const T m3dt = A::mul(T(-3), dtc), m4dt = A::mul(T(-4), dtc);
-            T ca[D], cb[D], cc[D], cd[D];
-#pragma unroll
-            for (int d = 0; d < D; ++d) {
-                T acc = T(0);
+            T ymid[D];
+            {
+                T acc[D];
                 bool first = true;
 #pragma unroll
                 for (int j = 0; j < S; ++j) {
                     const double cj = p.c_mid[j];
                     if (cj != 0.0) {
-                        const T term = A::mul(A::mul(dtc, (T)cj), k[j][d]);
-                        acc = first ? term : A::add(acc, term);
+                        const T c = A::mul(dtc, (T)cj);
+#pragma unroll
+                        for (int d = 0; d < D; ++d) {
+                            const T term = A::mul(c, k[j][d]);
+                            acc[d] = first ? term : A::add(acc[d], term);
+                        }
                         first = false;
                     }
                 }
-                const T ymid = A::add(y[d], acc);
+#pragma unroll
+                for (int d = 0; d < D; ++d) ymid[d] = first ? y[d] : A::add(y[d], acc[d]);
+            }
+            T ca[D], cb[D], cc[D], cd[D];
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
                 const T f0e = k[0][d], f1e = k[S - 1][d], y0e = y[d], y1e = yi[d];
                 T a = A::mul(m2dt, f0e);
                 a = A::add(a, A::mul(p2dt, f1e));
                 a = A::add(a, A::mul(T(-8), y0e));
                 a = A::add(a, A::mul(T(-8), y1e));
-                a = A::add(a, A::mul(T(16), ymid));
+                a = A::add(a, A::mul(T(16), ymid[d]));
                 T b = A::mul(p5dt, f0e);
                 b = A::add(b, A::mul(m3dt, f1e));
                 b = A::add(b, A::mul(T(18), y0e));
                 b = A::add(b, A::mul(T(14), y1e));
-                b = A::add(b, A::mul(T(-32), ymid));
+                b = A::add(b, A::mul(T(-32), ymid[d]));
                 T cq = A::mul(m4dt, f0e);
                 cq = A::add(cq, A::mul(dtc, f1e));
                 cq = A::add(cq, A::mul(T(-11), y0e));
                 cq = A::add(cq, A::mul(T(-5), y1e));
-                cq = A::add(cq, A::mul(T(16), ymid));
+                cq = A::add(cq, A::mul(T(16), ymid[d]));
                 ca[d] = a;
                 cb[d] = b;
                 cc[d] = cq;
@@ -370,42 +526,31 @@ __global__ void __launch_bounds__(BT) k_fused_adaptive(const __grid_constant__ F
             }
         }
         // state update (dopri5.py:113-120)
-        dt_last = dt;
-        msr = dec.m;
-        attempts += 1;
         if (accept) {
-            n_acc += 1;
-            t_prev = t_cur;
             t_cur = t1_new;
 #pragma unroll
             for (int d = 0; d < D; ++d) {
                 y[d] = yi[d];
                 f0[d] = k[S - 1][d];
             }
-        } else {
-            n_rej += 1;
         }
-        dt = dec.dt_next;
-        nadv = (cur > j0) ? 0 : nadv + 1;
-        done = (cur >= p.c.n_out) ? 1 : 0;
-        if (!done) {
-            if (nadv >= p.c.max_num_steps) status |= B2ODE_ST_MAXSTEPS;
-            if (!(t_cur + dt > t_cur)) status |= B2ODE_ST_UNDERFLOW;
-        }
-        if (status) done = 1;
+        dt = ctl.dt_next;
+        status = ctl.status;
+        done = ctl.done;
+        __syncthreads();     // ctl is rewritten by thread 0 in the next attempt
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         b2ode_state z;
         memset(&z, 0, sizeof(z));
-        z.t0 = t_prev;
+        z.t0 = ctl.t_prev;
         z.t1 = t_cur;
         z.dt = dt;
-        z.dt_last = dt_last;
-        z.msr_max = msr;
-        z.n_acc = n_acc;
-        z.n_rej = n_rej;
-        z.attempt = attempts;
-        z.n_steps_adv = nadv;
+        z.dt_last = ctl.dt_last;
+        z.msr_max = ctl.m;
+        z.n_acc = ctl.n_acc;
+        z.n_rej = ctl.n_rej;
+        z.attempt = ctl.attempts;
+        z.n_steps_adv = ctl.nadv;
         z.done = 1;
         z.status = status;
         z.cursor = cur;
