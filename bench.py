@@ -219,6 +219,7 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         import torch.distributed as dist
         from tfdiffeq_b200.comm import SharedStepGroup
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
         group = SharedStepGroup()
     peak, peak_src = peaks()

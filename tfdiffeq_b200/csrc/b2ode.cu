@@ -43,7 +43,7 @@ struct StageParams {
 };
 
 template <typename T, int NK>
-__global__ void __launch_bounds__(kThreads) k_rk_stage(const __grid_constant__ StageParams<NK> p) {
+__global__ void __launch_bounds__(kThreads, B2_MINB_STAGE) k_rk_stage(const __grid_constant__ StageParams<NK> p) {
     const int s = find_seg(p.g, blockIdx.x);
     const int bl = blockIdx.x - p.g.blk_begin[s], nb = p.g.blk_begin[s + 1] - p.g.blk_begin[s];
     const T dt = (T)p.st->dt;
@@ -207,7 +207,7 @@ __device__ void control_step(b2ode_state *st, const CtrlParams &c, const Partial
 }
 
 template <typename T, int NK>
-__global__ void __launch_bounds__(kThreads) k_rk_finalize(const __grid_constant__ FinalizeParams<NK> p) {
+__global__ void __launch_bounds__(kThreads, B2_MINB_FINALIZE) k_rk_finalize(const __grid_constant__ FinalizeParams<NK> p) {
     const int s = find_seg(p.g, blockIdx.x);
     const int bl = blockIdx.x - p.g.blk_begin[s], nb = p.g.blk_begin[s + 1] - p.g.blk_begin[s];
     const T dt = (T)p.st->dt;

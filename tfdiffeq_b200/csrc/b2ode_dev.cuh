@@ -30,6 +30,17 @@ void b2_timing_end(int fam, int slot, cudaStream_t st);
 // ------------------------------------------------------------------------------------------------
 // device helpers
 // ------------------------------------------------------------------------------------------------
+// tuning knobs (compile-time; defaults are what profiles/ measured best)
+#ifndef B2_MINB_FINALIZE
+#define B2_MINB_FINALIZE 1      // min resident blocks per SM requested for the finalize kernel
+#endif
+#ifndef B2_MINB_STAGE
+#define B2_MINB_STAGE 1
+#endif
+#ifndef B2_UNROLL
+#define B2_UNROLL 1             // packs per thread per loop trip in the streaming loops
+#endif
+constexpr int kUnroll = B2_UNROLL;
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
 
@@ -108,6 +119,7 @@ __device__ __forceinline__ void seg_for_each(long long n, bool vec_ok, int bl, i
     const long long first = (long long)bl * kThreads + threadIdx.x;
     if (vec_ok) {
         const long long nv = n / VW;
+#pragma unroll kUnroll
         for (long long i = first; i < nv; i += stride) body(IC<VW>{}, i);
         const long long tail = nv * VW + threadIdx.x;
         if (bl == 0 && tail < n) body(IC<1>{}, tail);
@@ -202,7 +214,11 @@ struct MailSlot {
 struct Mailbox {
     MailSlot slot[2][B2ODE_MAXPEERS];
     unsigned long long local_seq;   // exchanges completed by the owning rank; persists across solves
-    unsigned long long pad[7];
+    unsigned long long ll_seq;      // same, for the low-latency protocol of the persistent fused kernel
+    unsigned long long pad[6];
+    // low-latency slots (the protocol of NCCL's "LL": every 8-byte word = {32 data bits, 32-bit sequence flag},
+    // so a word is valid as soon as its flag matches -- no fence, no separate flag store): 3 doubles = 6 words
+    unsigned long long ll[2][B2ODE_MAXPEERS][8];
 };
 
 struct CommParams {

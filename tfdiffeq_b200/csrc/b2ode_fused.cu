@@ -189,8 +189,17 @@ __device__ __forceinline__ FRed fred_block(FRed x, FRed *sh /*[BT/32]*/) {
 }
 
 // Grid-wide version; returns the totals as a Partial (columns as in the generic finalize kernel) in every thread.
+__device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
 template <int BT>
-__device__ Partial fred_grid(const FusedParams &p, FRed mine, unsigned &parity, FRed *shf, Partial *sh, Partial *sh_tot) {
+__device__ Partial fred_grid(const FusedParams &p, FRed mine, unsigned &parity, unsigned ll_base, FRed *shf) {
     FRed *part = reinterpret_cast<FRed *>(p.part) + (size_t)(parity & 1u) * gridDim.x;
     FRed b = fred_block<BT>(mine, shf);
     if (threadIdx.x == 0) part[blockIdx.x] = b;
@@ -208,30 +217,51 @@ __device__ Partial fred_grid(const FusedParams &p, FRed mine, unsigned &parity, 
     tot.v[2] = __longlong_as_double((long long)t.m1);
     tot.v[3] = (t.m0 >= 0x7ff0000000000000ull) ? 1.0 : 0.0;     // inf or NaN somewhere in y0
     if (p.comm.nranks > 1) {
-        const unsigned long long want = (unsigned long long)(parity + 1u);
-        if (blockIdx.x == 0) {
-            if (threadIdx.x == 0) sh_tot[0] = tot;
-            __syncthreads();
-            group_combine<0xEu>(p.comm, p.st, sh_tot, 1);
-            if (threadIdx.x == 0) {
-                p.gtot[parity & 1u] = sh_tot[0];
-                __threadfence();
-                atomicExch(p.gflag, want);
-            }
-            __syncthreads();
-            tot = sh_tot[0];
-        } else {
-            if (threadIdx.x == 0) {
-                volatile unsigned long long *f = p.gflag;
-                while (*f < want) {
+        // Cross-GPU combine, low-latency protocol: block 0 pushes this rank's 3 totals to every peer as six
+        // {32 data bits | 32-bit sequence} words over NVLink; EVERY block polls its own rank's mailbox directly
+        // (no second hop through a local flag) and combines the ranks in rank order.
+        const unsigned seq = ll_base + parity + 1u;
+        const int par = (int)(seq & 1u);
+        __shared__ unsigned long long peer_bits[B2ODE_MAXPEERS][3];
+        if (threadIdx.x < p.comm.nranks) {
+            const int q = threadIdx.x;
+            if (blockIdx.x == 0) {
+                unsigned long long *dst = p.comm.box[q]->ll[par][p.comm.rank];
+                const unsigned long long bits[3] = {(unsigned long long)__double_as_longlong(t.sum), t.m0, t.m1};
+#pragma unroll
+                for (int w = 0; w < 3; ++w) {
+                    st_relaxed_sys_u64(dst + 2 * w, ((unsigned long long)seq << 32) | (bits[w] & 0xffffffffull));
+                    st_relaxed_sys_u64(dst + 2 * w + 1, ((unsigned long long)seq << 32) | (bits[w] >> 32));
                 }
-                __threadfence();
-                sh_tot[0] = p.gtot[parity & 1u];
             }
-            __syncthreads();
-            tot = sh_tot[0];
-            __syncthreads();
+            const unsigned long long *src = p.comm.box[p.comm.rank]->ll[par][q];
+#pragma unroll
+            for (int w = 0; w < 3; ++w) {
+                unsigned long long lo, hi;
+                do {
+                    lo = ld_relaxed_sys_u64(src + 2 * w);
+                } while ((unsigned)(lo >> 32) != seq);
+                do {
+                    hi = ld_relaxed_sys_u64(src + 2 * w + 1);
+                } while ((unsigned)(hi >> 32) != seq);
+                peer_bits[q][w] = (lo & 0xffffffffull) | (hi << 32);
+            }
         }
+        __syncthreads();
+        FRed g;
+        g.sum = __longlong_as_double((long long)peer_bits[0][0]);
+        g.m0 = peer_bits[0][1];
+        g.m1 = peer_bits[0][2];
+        for (int q = 1; q < p.comm.nranks; ++q) {
+            g.sum += __longlong_as_double((long long)peer_bits[q][0]);
+            g.m0 = umax64(g.m0, peer_bits[q][1]);
+            g.m1 = umax64(g.m1, peer_bits[q][2]);
+        }
+        tot.v[0] = g.sum;
+        tot.v[1] = __longlong_as_double((long long)g.m0);
+        tot.v[2] = __longlong_as_double((long long)g.m1);
+        tot.v[3] = (g.m0 >= 0x7ff0000000000000ull) ? 1.0 : 0.0;
+        __syncthreads();
     }
     parity += 1u;
     return tot;
@@ -264,6 +294,9 @@ __global__ void __launch_bounds__(BT) k_fused_adaptive(const __grid_constant__ F
     T *out = (T *)p.out;
     const T tsign = (T)p.time_sign;
     unsigned parity = 0;
+    // sequence base of the low-latency exchange (persists in this rank's mailbox across solves); the two grid
+    // reductions of the initial-step heuristic use the generic mailbox protocol, the attempts use this one
+    const unsigned ll_base = (p.comm.nranks > 1) ? (unsigned)p.comm.box[p.comm.rank]->ll_seq : 0u;
 
     T y[D], f0[D];
 #pragma unroll
@@ -420,7 +453,7 @@ __global__ void __launch_bounds__(BT) k_fused_adaptive(const __grid_constant__ F
                 }
             }
         }
-        const Partial tot = fred_grid<BT>(p, mine, parity, shf, sh, sh_tot);
+        const Partial tot = fred_grid<BT>(p, mine, parity, ll_base, shf);
         // controller: once per block (thread 0), identical in every block; broadcast through shared memory
         if (threadIdx.x == 0) {
             const CtrlDecision dec = ctrl_decide<T>(p.c, &tot, 1, dt);
@@ -556,6 +589,7 @@ __global__ void __launch_bounds__(BT) k_fused_adaptive(const __grid_constant__ F
         z.cursor = cur;
         z.xseq = p.st->xseq;
         *p.st = z;
+        if (p.comm.nranks > 1) p.comm.box[p.comm.rank]->ll_seq = (unsigned long long)(ll_base + parity);
     }
 }
 
