@@ -367,13 +367,22 @@ class AdaptiveStepsizeODESolver(object):
                         graph.replay()
                     elif self.cuda_graph and n_enq >= 1:
                         # attempt 1 ran eagerly (warm-up); capture attempt 2 and replay it from now on
+                        # (capture_begin/capture_end directly: torch.cuda.graph() would also run gc.collect() and
+                        # empty the allocator cache on entry, tens of milliseconds per solve)
                         graph = torch.cuda.CUDAGraph()
+                        cap = torch.cuda.Stream(dev)
+                        cap.wait_stream(stream)
                         try:
-                            with torch.cuda.graph(graph):
-                                check(lib.b2ode_set_stream(handle, C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
-                                graph_ks = run_attempt()
+                            with torch.cuda.stream(cap):
+                                check(lib.b2ode_set_stream(handle, C.c_void_p(cap.cuda_stream)))
+                                graph.capture_begin()
+                                try:
+                                    graph_ks = run_attempt()
+                                finally:
+                                    graph.capture_end()
                         finally:
                             check(lib.b2ode_set_stream(handle, C.c_void_p(stream.cuda_stream)))
+                        stream.wait_stream(cap)
                         graph.replay()
                     else:
                         prev_last = run_attempt()[-1]
