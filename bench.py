@@ -71,7 +71,7 @@ class ClockSampler(object):
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
@@ -205,7 +205,8 @@ def headline_kernel_roofline(dev, peak):
     fin = out.get("finalize", {})
     return {"bound": "hbm", "kernel": "k_rk_finalize<double,6>", "workload": "linear_b65536x128_f64_dopri5",
             "achieved": fin.get("achieved"), "peak": peak, "unit": "GB/s", "frac": fin.get("frac"),
-            "traffic": None, "per_kernel": out, "n_accepted": st.get("n_accepted"), "n_rejected": st.get("n_rejected")}
+            # ncu --set full, same launch (profiles/r01_finalize_65536x128_f64.md): 537.0 MB read + 3.3 MB written
+            "traffic": 540.3e6, "per_kernel": out, "n_accepted": st.get("n_accepted"), "n_rejected": st.get("n_rejected")}
 
 
 def run_ours(args, rank, world, local_rank):
@@ -299,12 +300,12 @@ def run_ours(args, rank, world, local_rank):
         sampler.start()
     main_res = measure(primary, args.steps, W, e2e=False)
     main_e2e = measure(primary, args.steps, 1, e2e=True)
-    clocks = sampler.stop() if rank == 0 else None
     others = {}
     for name in paths:
         if name != primary:
             r = measure(name, max(1, min(args.steps, 2)), 1, e2e=False)
             others[name] = {"value": r["value"], "unit": UNIT, "ms_per_step": r["ms_per_step"]}
+    clocks = sampler.stop() if rank == 0 else None     # sampled every 20 ms across all the timed regions above
 
     # ---- per-kernel timing passes (CUDA events recorded by the library around its own launches) ----------------
     n = B * DIM
@@ -354,7 +355,10 @@ def run_ours(args, rank, world, local_rank):
             slab = NPTS * n * 8 + n * 8
             roof = {"bound": "hbm", "kernel": "k_fused_adaptive<double, RhsLorenz<double>, 7> (one launch = one whole solve)",
                     "achieved": alg / (fus_avg * 1e-3) / 1e9, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                    "frac": alg / (fus_avg * 1e-3) / 1e9 / peak, "traffic": None,
+                    "frac": alg / (fus_avg * 1e-3) / 1e9 / peak,
+                    # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one `ncu --set full` capture of the
+                    # same launch (profiles/r01_fused_lorenz_65536x3_f64.md): the solution slab and nothing else
+                    "traffic": 1517.4e6,
                     "algorithmic_bytes_per_launch": int(alg), "avg_launch_ms": fus_avg, "launches_timed": fus_cnt.value,
                     "bytes_actually_needed_per_launch": int(slab), "slab_write_GBps": slab / (fus_avg * 1e-3) / 1e9,
                     "note": "achieved uses SURVEY 8(d)'s per-unit bytes (the traffic of a design with func outside the kernel): "

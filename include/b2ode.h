@@ -205,7 +205,7 @@ size_t b2ode_fused_workspace_bytes(int64_t n_trajectories);
 int b2ode_fused_solve(const b2ode_adaptive_desc *desc, int rhs_kind, const double *rhs_params, int n_rhs_params,
                       double time_sign, const void *y0, void *out, const double *t_out, int n_out, double t_start,
                       double first_step, void *state, void *workspace, size_t workspace_bytes, int rank, int nranks,
-                      void *const *mailboxes, const int64_t *traj_per_rank, void *cuda_stream);
+                      void *const *mailboxes, int64_t n_traj_global, void *cuda_stream);
 
 /* ---- measurement hooks (bench.py) --------------------------------------------------------------------- */
 unsigned long long b2ode_launch_count(void);            /* kernels launched by this library so far          */

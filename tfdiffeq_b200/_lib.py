@@ -80,7 +80,7 @@ _SIGNATURES = {
     "b2ode_fused_workspace_bytes": (C.c_size_t, [C.c_int64]),
     "b2ode_fused_solve": (C.c_int, [C.POINTER(AdaptiveDesc), C.c_int, C.POINTER(C.c_double), C.c_int, C.c_double,
                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_void_p,
-                                    C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int64),
+                                    C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_int64,
                                     C.c_void_p]),
     "b2ode_launch_count": (C.c_ulonglong, []),
     "b2ode_timing_enable": (C.c_int, [C.c_uint]),

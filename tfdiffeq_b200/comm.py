@@ -100,14 +100,13 @@ class SharedStepGroup(object):
         check(lib.b2ode_comm_attach(handle, self.rank, self.world, self._ptrs))
         check(lib.b2ode_comm_set_global_len(handle, glob))
 
-    def all_counts(self, n):
-        """Every rank's value of a per-rank count (e.g. trajectories), in rank order."""
+    def global_count(self, n):
+        """Sum of a per-rank count over the group (e.g. trajectories, for the mean in the error norm)."""
         v = torch.tensor([int(n)], dtype=torch.int64)
         if dist.get_backend(self.group) == "nccl":
             v = v.to(self.device)
-        out = [torch.empty_like(v) for _ in range(self.world)]
-        dist.all_gather(out, v, group=self.group)
-        return [int(o.item()) for o in out]
+        dist.all_reduce(v, group=self.group)
+        return int(v.item())
 
     def close(self):
         lib = _lib.lib

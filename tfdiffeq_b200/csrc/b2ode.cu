@@ -691,8 +691,7 @@ static void build_geom(SegGeom *g, int dtype, int nseg, const int64_t *seg_len, 
 extern "C" int b2ode_version(void) { return B2ODE_ABI_VERSION; }
 extern "C" const char *b2ode_last_error(void) { return g_err; }
 extern "C" size_t b2ode_state_bytes(void) { return sizeof(b2ode_state); }
-extern "C" size_t b2ode_fused_ll_bytes(void);    // b2ode_fused.cu: flag array of the persistent kernel's all-gather
-extern "C" size_t b2ode_mailbox_bytes(void) { return sizeof(Mailbox) + b2ode_fused_ll_bytes(); }
+extern "C" size_t b2ode_mailbox_bytes(void) { return sizeof(Mailbox); }
 
 extern "C" size_t b2ode_workspace_bytes(const b2ode_adaptive_desc *desc) {
     if (!desc || desc->nseg < 1 || desc->nseg > B2ODE_MAXSEG) return 0;
@@ -936,8 +935,8 @@ extern "C" int b2ode_mailbox_create(void **dev_ptr, unsigned char handle_out[64]
     if (!dev_ptr || !handle_out) return b2_fail(B2ODE_EINVAL, "null argument");
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle is 64 bytes");
     void *p = nullptr;
-    B2_CUDA(cudaMalloc(&p, b2ode_mailbox_bytes()));
-    B2_CUDA(cudaMemset(p, 0, b2ode_mailbox_bytes()));
+    B2_CUDA(cudaMalloc(&p, sizeof(Mailbox)));
+    B2_CUDA(cudaMemset(p, 0, sizeof(Mailbox)));
     B2_CUDA(cudaDeviceSynchronize());
     cudaIpcMemHandle_t h;
     B2_CUDA(cudaIpcGetMemHandle(&h, p));

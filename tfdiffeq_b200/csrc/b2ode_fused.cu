@@ -44,18 +44,12 @@ struct RhsLotkaVolterra {   // README.md:67-81 ; params {a, b, c, d}
 // ------------------------------------------------------------------------------------------------
 // grid-wide reduction: block tree -> partial per block -> grid barrier -> every block re-reduces all partials
 // ------------------------------------------------------------------------------------------------
-constexpr int kMaxBlk = 640;     // most blocks a rank can have (148 SMs x 4 blocks of 128 threads, rounded up)
-constexpr int kLLWords = 8;      // 64-byte line per (rank, block) item; 6 words used
-
 struct FusedParams {
     b2ode_state *st;
-    // flag arrays of the barrier-free all-gather reduction, one per rank, laid out [2][pstride][kMaxBlk][8]:
-    // ll[q] is rank q's array as mapped in THIS process (peer memory over NVLink for q != rank);
-    // with no group attached ll[0] lives in the caller's workspace.
-    unsigned long long *ll[B2ODE_MAXPEERS];
-    unsigned long long *seq_store;   // persistent sequence base (own mailbox), or null
-    int grid_of[B2ODE_MAXPEERS];     // blocks launched by each rank
-    int rank, nranks, pstride;
+    Partial *part;          // [2][gridDim.x], double buffered by reduction parity
+    unsigned *bar;          // monotonically increasing arrival counter of the grid barrier
+    Partial *gtot;          // [2]: group totals published by block 0 when a shared-step group is attached
+    unsigned long long *gflag;
     const void *y0;
     void *out;
     long long n_traj;       // trajectories on this rank
@@ -69,8 +63,132 @@ struct FusedParams {
     int fsal;
     double rtol0, atol0;
     CtrlParams c;
+    CommParams comm;
 };
 
+__device__ __forceinline__ unsigned ld_acquire_gpu_u32(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Grid barrier on a monotonically increasing arrival counter (zeroed by the host before the launch): barrier
+// number e is passed once the counter reaches e * gridDim.x.  One atomic and one polled word per block.
+__device__ __forceinline__ void grid_barrier(unsigned *count, unsigned &epoch) {
+    __syncthreads();
+    epoch += 1u;
+    if (threadIdx.x == 0) {
+        const unsigned target = epoch * gridDim.x;
+        __threadfence();
+        atomicAdd(count, 1u);
+        while (ld_acquire_gpu_u32(count) < target) {
+        }
+    }
+    __syncthreads();
+}
+
+template <unsigned MM, int BT>
+__device__ __forceinline__ Partial fblock_reduce(Partial x, Partial *sh /*[BT/32]*/) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        Partial y;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) y.v[c] = __shfl_xor_sync(0xffffffffu, x.v[c], o);
+        x = combine<MM>(x, y);
+    }
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();
+    if (l == 0) sh[w] = x;
+    __syncthreads();
+    Partial r = sh[0];
+#pragma unroll
+    for (int i = 1; i < BT / 32; ++i) r = combine<MM>(r, sh[i]);
+    return r;   // valid in EVERY thread
+}
+
+// All threads of the grid call this with their own contribution; all return the same (group-wide) totals.
+template <unsigned MM, int BT>
+__device__ Partial grid_reduce(const FusedParams &p, Partial mine, unsigned &parity, Partial *sh, Partial *sh_tot) {
+    Partial *part = p.part + (size_t)(parity & 1u) * gridDim.x;
+    Partial b = fblock_reduce<MM, BT>(mine, sh);
+    if (threadIdx.x == 0) part[blockIdx.x] = b;
+    grid_barrier(p.bar, parity);            // the barrier epoch is the reduction count
+    parity -= 1u;
+    Partial acc = identity<MM>();
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += BT) acc = combine<MM>(acc, part[i]);
+    Partial tot = fblock_reduce<MM, BT>(acc, sh);
+    if (p.comm.nranks > 1) {
+        // block 0 exchanges with the peer GPUs and publishes the group totals; the others wait for them
+        const unsigned long long want = (unsigned long long)(parity + 1u);
+        if (blockIdx.x == 0) {
+            if (threadIdx.x == 0) sh_tot[0] = tot;
+            __syncthreads();
+            group_combine<MM>(p.comm, p.st, sh_tot, 1);
+            if (threadIdx.x == 0) {
+                p.gtot[parity & 1u] = sh_tot[0];
+                __threadfence();
+                atomicExch(p.gflag, want);
+            }
+            __syncthreads();
+            tot = sh_tot[0];
+        } else {
+            if (threadIdx.x == 0) {
+                volatile unsigned long long *f = p.gflag;
+                while (*f < want) {
+                }
+                __threadfence();
+                sh_tot[0] = p.gtot[parity & 1u];
+            }
+            __syncthreads();
+            tot = sh_tot[0];
+            __syncthreads();
+        }
+    }
+    parity += 1u;
+    return tot;
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-attempt reduction: {sum err^2, max|y0|, max|y1|}.  For non-negative doubles the IEEE order is the order
+// of the bit patterns read as unsigned integers, and every NaN pattern sorts above +inf, so an integer max is a
+// NaN-propagating max for free; "y0 is non-finite" is simply max|y0| >= +inf (no fourth column).
+// ------------------------------------------------------------------------------------------------
+struct FRed {
+    double sum;
+    unsigned long long m0, m1;
+};
+
+__device__ __forceinline__ unsigned long long umax64(unsigned long long a, unsigned long long b) { return a > b ? a : b; }
+
+__device__ __forceinline__ FRed fred_combine(const FRed &a, const FRed &b) {
+    FRed r;
+    r.sum = a.sum + b.sum;
+    r.m0 = umax64(a.m0, b.m0);
+    r.m1 = umax64(a.m1, b.m1);
+    return r;
+}
+
+template <int BT>
+__device__ __forceinline__ FRed fred_block(FRed x, FRed *sh /*[BT/32]*/) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        FRed y;
+        y.sum = __shfl_xor_sync(0xffffffffu, x.sum, o);
+        y.m0 = __shfl_xor_sync(0xffffffffu, x.m0, o);
+        y.m1 = __shfl_xor_sync(0xffffffffu, x.m1, o);
+        x = fred_combine(x, y);
+    }
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();
+    if (l == 0) sh[w] = x;
+    __syncthreads();
+    FRed r = sh[0];
+#pragma unroll
+    for (int i = 1; i < BT / 32; ++i) r = fred_combine(r, sh[i]);
+    return r;   // valid in EVERY thread
+}
+
+// Grid-wide version; returns the totals as a Partial (columns as in the generic finalize kernel) in every thread.
 __device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long *p, unsigned long long v) {
     asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
@@ -80,114 +198,72 @@ __device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned 
     return v;
 }
 
-// ------------------------------------------------------------------------------------------------
-// Barrier-free, deterministic all-gather reduction over every block of every rank.
-//
-// Three 64-bit lanes per contribution; lane c is an fp64 SUM if bit c of SUMMASK is set, otherwise an unsigned
-// integer MAX of the bit patterns.  (For non-negative doubles the IEEE order is the order of the bit patterns
-// read as unsigned integers, and every NaN pattern sorts above +inf: an integer max is a NaN-propagating max
-// of absolute values for free, and "y0 is non-finite" is simply max|y0| >= +inf.)
-//
-// Each block publishes its block total as six {32 data bits | 32-bit sequence number} words -- the word is
-// valid the moment its flag matches, so there is no fence, no atomic and no separate flag (the idea of NCCL's
-// LL protocol) -- into the flag array of EVERY rank (its own included; peers over NVLink), then polls its own
-// rank's array until the words of all (rank, block) items carry the current sequence number, and combines them
-// in a fixed order.  That one step is at the same time the grid barrier, the grid-wide reduction and the
-// cross-GPU exchange: its latency is one store-to-visible hop.  Slots are double buffered by sequence parity: a
-// block can publish sequence s+2 only after it has gathered s+1, which needs everybody's s+1 publication, which
-// everybody makes only after gathering s -- so nobody is still reading the slot being overwritten.
-// ------------------------------------------------------------------------------------------------
-struct F3 {
-    unsigned long long b[3];
-};
-
-__device__ __forceinline__ unsigned long long umax64(unsigned long long a, unsigned long long b) { return a > b ? a : b; }
-__device__ __forceinline__ unsigned long long dbits(double x) { return (unsigned long long)__double_as_longlong(x); }
-__device__ __forceinline__ double bitsd(unsigned long long x) { return __longlong_as_double((long long)x); }
-
-template <unsigned SUMMASK>
-__device__ __forceinline__ F3 f3_combine(const F3 &x, const F3 &y) {
-    F3 r;
-#pragma unroll
-    for (int c = 0; c < 3; ++c) r.b[c] = ((SUMMASK >> c) & 1u) ? dbits(bitsd(x.b[c]) + bitsd(y.b[c])) : umax64(x.b[c], y.b[c]);
-    return r;
-}
-
-// fixed-order block reduction (xor butterfly inside a warp, then warps in order); result valid in EVERY thread
-template <unsigned SUMMASK, int BT>
-__device__ __forceinline__ F3 f3_block(F3 x, F3 *sh /*[BT/32]*/) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        F3 y;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) y.b[c] = __shfl_xor_sync(0xffffffffu, x.b[c], o);
-        x = f3_combine<SUMMASK>(x, y);
-    }
-    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-    __syncthreads();
-    if (l == 0) sh[w] = x;
-    __syncthreads();
-    F3 r = sh[0];
-#pragma unroll
-    for (int i = 1; i < BT / 32; ++i) r = f3_combine<SUMMASK>(r, sh[i]);
-    return r;
-}
-
-__device__ __forceinline__ size_t ll_index(const FusedParams &p, int par, int src_rank, int blk) {
-    return (((size_t)par * p.pstride + src_rank) * kMaxBlk + blk) * kLLWords;
-}
-
-template <unsigned SUMMASK, int BT>
-__device__ F3 f3_allgather(const FusedParams &p, F3 mine, unsigned &count, unsigned base, F3 *sh) {
-    count += 1u;
-    const unsigned seq = base + count;
-    const int par = (int)(seq & 1u);
-    const int nr = p.nranks > 1 ? p.nranks : 1;
-    const F3 b = f3_block<SUMMASK, BT>(mine, sh);
-    // publish: thread 6*q + w sends word w of this block's total to rank q
-    if (threadIdx.x < 6 * nr) {
-        const int q = threadIdx.x / 6, w = threadIdx.x - 6 * q;
-        const unsigned long long v = b.b[w >> 1];
-        const unsigned long long half = (w & 1) ? (v >> 32) : (v & 0xffffffffull);
-        st_relaxed_sys_u64(p.ll[q] + ll_index(p, par, p.rank, blockIdx.x) + w, ((unsigned long long)seq << 32) | half);
-    }
-    // gather: item = (rank r, block k), rank-major; thread t takes items t, t+BT, ... in increasing order
-    int total = 0;
-    for (int r = 0; r < nr; ++r) total += p.grid_of[r];
-    F3 acc;
-    acc.b[0] = acc.b[1] = acc.b[2] = 0ull;      // identity of both operations
-    const unsigned long long *mybox = p.ll[p.nranks > 1 ? p.rank : 0];
-    for (int item = threadIdx.x; item < total; item += BT) {
-        int r = 0, k = item;
-        while (k >= p.grid_of[r]) {
-            k -= p.grid_of[r];
-            ++r;
-        }
-        const unsigned long long *src = mybox + ll_index(p, par, r, k);
-        unsigned long long w[6];
-        bool ok;
-        do {
-            ok = true;
-#pragma unroll
-            for (int j = 0; j < 6; ++j) {
-                w[j] = ld_relaxed_sys_u64(src + j);
-                ok = ok && ((unsigned)(w[j] >> 32) == seq);
-            }
-        } while (!ok);
-        F3 x;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) x.b[c] = (w[2 * c] & 0xffffffffull) | (w[2 * c + 1] << 32);
-        acc = f3_combine<SUMMASK>(acc, x);
-    }
-    return f3_block<SUMMASK, BT>(acc, sh);
-}
-
-__device__ __forceinline__ Partial f3_to_partial(const F3 &t) {
+template <int BT>
+__device__ Partial fred_grid(const FusedParams &p, FRed mine, unsigned &parity, unsigned ll_base, FRed *shf) {
+    FRed *part = reinterpret_cast<FRed *>(p.part) + (size_t)(parity & 1u) * gridDim.x;
+    FRed b = fred_block<BT>(mine, shf);
+    if (threadIdx.x == 0) part[blockIdx.x] = b;
+    grid_barrier(p.bar, parity);
+    parity -= 1u;
+    FRed acc;
+    acc.sum = 0.0;
+    acc.m0 = acc.m1 = 0ull;
+    // gridDim.x <= 148 * blocks/SM: the first warps hold everything, the rest contribute the identity
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += BT) acc = fred_combine(acc, part[i]);
+    FRed t = fred_block<BT>(acc, shf);
     Partial tot;
-    tot.v[0] = bitsd(t.b[0]);
-    tot.v[1] = bitsd(t.b[1]);
-    tot.v[2] = bitsd(t.b[2]);
-    tot.v[3] = (t.b[1] >= 0x7ff0000000000000ull) ? 1.0 : 0.0;     // inf or NaN somewhere in y0
+    tot.v[0] = t.sum;
+    tot.v[1] = __longlong_as_double((long long)t.m0);
+    tot.v[2] = __longlong_as_double((long long)t.m1);
+    tot.v[3] = (t.m0 >= 0x7ff0000000000000ull) ? 1.0 : 0.0;     // inf or NaN somewhere in y0
+    if (p.comm.nranks > 1) {
+        // Cross-GPU combine, low-latency protocol: block 0 pushes this rank's 3 totals to every peer as six
+        // {32 data bits | 32-bit sequence} words over NVLink; EVERY block polls its own rank's mailbox directly
+        // (no second hop through a local flag) and combines the ranks in rank order.
+        const unsigned seq = ll_base + parity + 1u;
+        const int par = (int)(seq & 1u);
+        __shared__ unsigned long long peer_bits[B2ODE_MAXPEERS][3];
+        if (threadIdx.x < p.comm.nranks) {
+            const int q = threadIdx.x;
+            if (blockIdx.x == 0) {
+                unsigned long long *dst = p.comm.box[q]->ll[par][p.comm.rank];
+                const unsigned long long bits[3] = {(unsigned long long)__double_as_longlong(t.sum), t.m0, t.m1};
+#pragma unroll
+                for (int w = 0; w < 3; ++w) {
+                    st_relaxed_sys_u64(dst + 2 * w, ((unsigned long long)seq << 32) | (bits[w] & 0xffffffffull));
+                    st_relaxed_sys_u64(dst + 2 * w + 1, ((unsigned long long)seq << 32) | (bits[w] >> 32));
+                }
+            }
+            const unsigned long long *src = p.comm.box[p.comm.rank]->ll[par][q];
+#pragma unroll
+            for (int w = 0; w < 3; ++w) {
+                unsigned long long lo, hi;
+                do {
+                    lo = ld_relaxed_sys_u64(src + 2 * w);
+                } while ((unsigned)(lo >> 32) != seq);
+                do {
+                    hi = ld_relaxed_sys_u64(src + 2 * w + 1);
+                } while ((unsigned)(hi >> 32) != seq);
+                peer_bits[q][w] = (lo & 0xffffffffull) | (hi << 32);
+            }
+        }
+        __syncthreads();
+        FRed g;
+        g.sum = __longlong_as_double((long long)peer_bits[0][0]);
+        g.m0 = peer_bits[0][1];
+        g.m1 = peer_bits[0][2];
+        for (int q = 1; q < p.comm.nranks; ++q) {
+            g.sum += __longlong_as_double((long long)peer_bits[q][0]);
+            g.m0 = umax64(g.m0, peer_bits[q][1]);
+            g.m1 = umax64(g.m1, peer_bits[q][2]);
+        }
+        tot.v[0] = g.sum;
+        tot.v[1] = __longlong_as_double((long long)g.m0);
+        tot.v[2] = __longlong_as_double((long long)g.m1);
+        tot.v[3] = (g.m0 >= 0x7ff0000000000000ull) ? 1.0 : 0.0;
+        __syncthreads();
+    }
+    parity += 1u;
     return tot;
 }
 
@@ -209,7 +285,8 @@ template <typename T, typename RHS, int S, int BT>
 __global__ void __launch_bounds__(BT) k_fused_adaptive(const __grid_constant__ FusedParams p) {
     using A = Ar<T>;
     constexpr int D = RHS::D;
-    __shared__ F3 sh[BT / 32];
+    __shared__ Partial sh[BT / 32];
+    __shared__ Partial sh_tot[1];
     const long long i = (long long)blockIdx.x * BT + threadIdx.x;
     const bool live = i < p.n_traj;
     const long long N = p.n_traj * D;
@@ -219,7 +296,7 @@ __global__ void __launch_bounds__(BT) k_fused_adaptive(const __grid_constant__ F
     unsigned parity = 0;
     // sequence base of the low-latency exchange (persists in this rank's mailbox across solves); the two grid
     // reductions of the initial-step heuristic use the generic mailbox protocol, the attempts use this one
-    const unsigned ll_base = p.seq_store ? (unsigned)*p.seq_store : 0u;
+    const unsigned ll_base = (p.comm.nranks > 1) ? (unsigned)p.comm.box[p.comm.rank]->ll_seq : 0u;
 
     T y[D], f0[D];
 #pragma unroll
@@ -250,38 +327,32 @@ __global__ void __launch_bounds__(BT) k_fused_adaptive(const __grid_constant__ F
     } else {
         const T rtol = (T)p.rtol0, atol = (T)p.atol0;
         T scale[D];
-        double s0 = 0.0, s1 = 0.0;
+        Partial mine = identity<0u>();
 #pragma unroll
         for (int d = 0; d < D; ++d) {
             scale[d] = A::add(atol, A::mul(A::abs(y[d]), rtol));
             if (live) {
                 const double q0 = (double)A::div(y[d], scale[d]), q1 = (double)A::div(f0[d], scale[d]);
-                s0 += q0 * q0;
-                s1 += q1 * q1;
+                mine.v[0] += q0 * q0;
+                mine.v[1] += q1 * q1;
             }
         }
-        F3 mine;
-        mine.b[0] = dbits(s0);
-        mine.b[1] = dbits(s1);
-        mine.b[2] = 0ull;
-        Partial tot = f3_to_partial(f3_allgather<0x3u, BT>(p, mine, parity, ll_base, sh));
+        Partial tot = grid_reduce<0u, BT>(p, mine, parity, sh, sh_tot);
         T d1max;
         const T h0 = init_h0<T>(p.c, &tot, 1, &d1max);
         T y1[D], f1[D];
 #pragma unroll
         for (int d = 0; d < D; ++d) y1[d] = A::add(y[d], A::mul(h0, f0[d]));
         rhs(A::add((T)t_cur, h0), y1, f1);
-        double s2 = 0.0;
+        mine = identity<0u>();
         if (live) {
 #pragma unroll
             for (int d = 0; d < D; ++d) {
                 const double q = (double)A::div(A::sub(f1[d], f0[d]), scale[d]);
-                s2 += q * q;
+                mine.v[0] += q * q;
             }
         }
-        mine.b[0] = dbits(s2);
-        mine.b[1] = mine.b[2] = 0ull;
-        tot = f3_to_partial(f3_allgather<0x3u, BT>(p, mine, parity, ll_base, sh));
+        tot = grid_reduce<0u, BT>(p, mine, parity, sh, sh_tot);
         dt = (double)init_dt<T>(p.c, &tot, 1, h0, d1max);
     }
     int done = (p.c.n_out <= 1) ? 1 : 0;
@@ -291,6 +362,7 @@ __global__ void __launch_bounds__(BT) k_fused_adaptive(const __grid_constant__ F
     }
 
     // ---- attempts -------------------------------------------------------------------------------------
+    __shared__ FRed shf[BT / 32];
     __shared__ CtlOut ctl;
     if (threadIdx.x == 0) {
         ctl.m = 0.0;
@@ -352,8 +424,9 @@ __global__ void __launch_bounds__(BT) k_fused_adaptive(const __grid_constant__ F
             for (int d = 0; d < D; ++d) yi[d] = first ? y[d] : A::add(y[d], acc[d]);
         }
         // error estimate + this thread's share of the reduction (rk_common.py:60, misc.py:256-263)
-        double esum = 0.0;
-        unsigned long long em0 = 0ull, em1 = 0ull;
+        FRed mine;
+        mine.sum = 0.0;
+        mine.m0 = mine.m1 = 0ull;
         {
             T err[D];
             bool first = true;
@@ -374,17 +447,13 @@ __global__ void __launch_bounds__(BT) k_fused_adaptive(const __grid_constant__ F
 #pragma unroll
                 for (int d = 0; d < D; ++d) {
                     const double ed = first ? 0.0 : (double)err[d];
-                    esum += ed * ed;
-                    em0 = umax64(em0, dbits(fabs((double)y[d])));
-                    em1 = umax64(em1, dbits(fabs((double)yi[d])));
+                    mine.sum += ed * ed;
+                    mine.m0 = umax64(mine.m0, (unsigned long long)__double_as_longlong(fabs((double)y[d])));
+                    mine.m1 = umax64(mine.m1, (unsigned long long)__double_as_longlong(fabs((double)yi[d])));
                 }
             }
         }
-        F3 mine;
-        mine.b[0] = dbits(esum);
-        mine.b[1] = em0;
-        mine.b[2] = em1;
-        const Partial tot = f3_to_partial(f3_allgather<0x1u, BT>(p, mine, parity, ll_base, sh));
+        const Partial tot = fred_grid<BT>(p, mine, parity, ll_base, shf);
         // controller: once per block (thread 0), identical in every block; broadcast through shared memory
         if (threadIdx.x == 0) {
             const CtrlDecision dec = ctrl_decide<T>(p.c, &tot, 1, dt);
@@ -518,9 +587,9 @@ __global__ void __launch_bounds__(BT) k_fused_adaptive(const __grid_constant__ F
         z.done = 1;
         z.status = status;
         z.cursor = cur;
-        z.xseq = (unsigned long long)(ll_base + parity);
+        z.xseq = p.st->xseq;
         *p.st = z;
-        if (p.seq_store) *p.seq_store = (unsigned long long)(ll_base + parity);
+        if (p.comm.nranks > 1) p.comm.box[p.comm.rank]->ll_seq = (unsigned long long)(ll_base + parity);
     }
 }
 
@@ -528,24 +597,17 @@ __global__ void __launch_bounds__(BT) k_fused_adaptive(const __grid_constant__ F
 // host side
 // ================================================================================================
 template <typename T, typename RHS, int S, int BT>
-static int fused_launch(FusedParams p, const long long *traj_of, cudaStream_t st) {
+static int fused_launch(const FusedParams &p, long long n_traj, cudaStream_t st) {
+    void *args[] = {(void *)&p};
     int dev = 0, coop = 0, nsm = 0, per_sm = 0;
     B2_CUDA(cudaGetDevice(&dev));
     B2_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
     B2_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
     B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused_adaptive<T, RHS, S, BT>, BT, 0));
     if (!coop) return b2_fail(B2ODE_ESTATE, "device does not support cooperative launch");
-    const int nr = p.nranks > 1 ? p.nranks : 1;
-    for (int r = 0; r < nr; ++r) {
-        const long long g = (traj_of[r] + BT - 1) / BT;
-        // every rank must be able to keep its blocks co-resident (they spin on each other's flags)
-        if (g > (long long)per_sm * nsm || g > kMaxBlk)
-            return b2_fail(B2ODE_ENOMEM, "rank %d needs %lld co-resident blocks of %d threads, device holds %d", r, g, BT,
-                           per_sm * nsm < kMaxBlk ? per_sm * nsm : kMaxBlk);
-        p.grid_of[r] = (int)g;
-    }
-    const int grid = p.grid_of[p.nranks > 1 ? p.rank : 0];
-    void *args[] = {(void *)&p};
+    const int grid = (int)((n_traj + BT - 1) / BT);
+    if (grid > per_sm * nsm)
+        return b2_fail(B2ODE_ENOMEM, "batch needs %d co-resident blocks of %d threads, device holds %d", grid, BT, per_sm * nsm);
     const int slot = b2_timing_begin(6 /* B2_FAM_FUSED */, st);
     B2_CUDA(cudaLaunchCooperativeKernel((const void *)k_fused_adaptive<T, RHS, S, BT>, dim3(grid), dim3(BT), args, 0, st));
     b2_timing_end(6, slot, st);
@@ -554,42 +616,38 @@ static int fused_launch(FusedParams p, const long long *traj_of, cudaStream_t st
 }
 
 template <typename T, typename RHS>
-static int fused_dispatch_s(const FusedParams &p, int n_k, const long long *traj_of, cudaStream_t st) {
+static int fused_dispatch_s(const FusedParams &p, int n_k, long long n_traj, cudaStream_t st) {
     // 512-thread blocks (<= 128 registers per thread) for the tableaus whose k-set fits; 128 otherwise
     switch (n_k) {
-        case 2: return fused_launch<T, RHS, 2, 512>(p, traj_of, st);
-        case 4: return fused_launch<T, RHS, 4, 512>(p, traj_of, st);
-        case 7: return fused_launch<T, RHS, 7, 512>(p, traj_of, st);
-        case 14: return fused_launch<T, RHS, 14, 128>(p, traj_of, st);
+        case 2: return fused_launch<T, RHS, 2, 512>(p, n_traj, st);
+        case 4: return fused_launch<T, RHS, 4, 512>(p, n_traj, st);
+        case 7: return fused_launch<T, RHS, 7, 512>(p, n_traj, st);
+        case 14: return fused_launch<T, RHS, 14, 128>(p, n_traj, st);
     }
     return b2_fail(B2ODE_EINVAL, "fused solve supports tableaus with 2, 4, 7 or 14 k's (got %d)", n_k);
 }
 
 template <typename T>
-static int fused_dispatch_rhs(const FusedParams &p, int rhs_kind, int n_k, const long long *traj_of, cudaStream_t st) {
+static int fused_dispatch_rhs(const FusedParams &p, int rhs_kind, int n_k, long long n_traj, cudaStream_t st) {
     switch (rhs_kind) {
-        case B2ODE_RHS_LORENZ: return fused_dispatch_s<T, RhsLorenz<T>>(p, n_k, traj_of, st);
-        case B2ODE_RHS_LOTKA_VOLTERRA: return fused_dispatch_s<T, RhsLotkaVolterra<T>>(p, n_k, traj_of, st);
+        case B2ODE_RHS_LORENZ: return fused_dispatch_s<T, RhsLorenz<T>>(p, n_k, n_traj, st);
+        case B2ODE_RHS_LOTKA_VOLTERRA: return fused_dispatch_s<T, RhsLotkaVolterra<T>>(p, n_k, n_traj, st);
     }
     return b2_fail(B2ODE_EINVAL, "unknown built-in right-hand side %d", rhs_kind);
 }
 
 static int rhs_dim(int kind) { return kind == B2ODE_RHS_LORENZ ? 3 : kind == B2ODE_RHS_LOTKA_VOLTERRA ? 2 : -1; }
 
-// bytes of one rank's flag array: [2][pstride][kMaxBlk][8] words
-static size_t ll_bytes(int pstride) { return (size_t)2 * pstride * kMaxBlk * kLLWords * sizeof(unsigned long long); }
-
-extern "C" size_t b2ode_fused_ll_bytes(void) { return ll_bytes(B2ODE_MAXPEERS); }
-
 extern "C" size_t b2ode_fused_workspace_bytes(int64_t n_traj) {
-    (void)n_traj;
-    return ll_bytes(1) + 256;      // the single-GPU flag array (zeroed per solve)
+    const long long grid = (n_traj + 127) / 128;      // the smallest block size used is 128
+    // [2][grid] partials + 2 group totals + barrier words + flag, 256-byte aligned pieces
+    return (size_t)(2 * grid + 2) * sizeof(Partial) + 256;
 }
 
 extern "C" int b2ode_fused_solve(const b2ode_adaptive_desc *desc, int rhs_kind, const double *rhs_params, int n_rhs_params,
                                  double time_sign, const void *y0, void *out, const double *t_out, int n_out, double t_start,
                                  double first_step, void *state, void *workspace, size_t workspace_bytes, int rank, int nranks,
-                                 void *const *mailboxes, const int64_t *traj_per_rank, void *cuda_stream) {
+                                 void *const *mailboxes, int64_t n_traj_global, void *cuda_stream) {
     if (!desc || !y0 || !out || !t_out || !state || !workspace) return b2_fail(B2ODE_EINVAL, "null argument");
     const int D = rhs_dim(rhs_kind);
     if (D < 0) return b2_fail(B2ODE_EINVAL, "unknown built-in right-hand side %d", rhs_kind);
@@ -598,37 +656,18 @@ extern "C" int b2ode_fused_solve(const b2ode_adaptive_desc *desc, int rhs_kind, 
     if (n_rhs_params < 0 || n_rhs_params > 8 || (n_rhs_params && !rhs_params)) return b2_fail(B2ODE_EINVAL, "bad rhs params");
     const long long n_traj = desc->seg_len[0] / D;
     if (n_traj < 1) return b2_fail(B2ODE_EINVAL, "empty batch");
+    if (workspace_bytes < b2ode_fused_workspace_bytes(n_traj)) return b2_fail(B2ODE_ENOMEM, "workspace too small");
     cudaStream_t st = (cudaStream_t)cuda_stream;
+    // workspace layout: [barrier 2 x u32 | pad to 64][flag u64 | pad to 128][gtot x2][partials 2 x grid]
+    unsigned char *w = (unsigned char *)workspace;
+    B2_CUDA(cudaMemsetAsync(w, 0, 256, st));
     FusedParams p;
     memset(&p, 0, sizeof(p));
     p.st = (b2ode_state *)state;
-    long long traj_of[B2ODE_MAXPEERS];
-    long long n_glob = n_traj;
-    if (nranks > 1) {
-        if (!mailboxes || !traj_per_rank || nranks > B2ODE_MAXPEERS || rank < 0 || rank >= nranks)
-            return b2_fail(B2ODE_EINVAL, "bad shared-step group arguments");
-        if (traj_per_rank[rank] != n_traj) return b2_fail(B2ODE_EINVAL, "traj_per_rank[rank] does not match the local batch");
-        n_glob = 0;
-        for (int r = 0; r < nranks; ++r) {
-            if (!mailboxes[r] || traj_per_rank[r] < 1) return b2_fail(B2ODE_EINVAL, "bad mailbox / batch of rank %d", r);
-            traj_of[r] = traj_per_rank[r];
-            n_glob += traj_per_rank[r];
-            p.ll[r] = (unsigned long long *)((unsigned char *)mailboxes[r] + sizeof(Mailbox));   // flag array follows the Mailbox
-        }
-        p.seq_store = &((Mailbox *)mailboxes[rank])->ll_seq;
-        p.rank = rank;
-        p.nranks = nranks;
-        p.pstride = B2ODE_MAXPEERS;
-    } else {
-        if (workspace_bytes < b2ode_fused_workspace_bytes(n_traj)) return b2_fail(B2ODE_ENOMEM, "workspace too small");
-        B2_CUDA(cudaMemsetAsync(workspace, 0, b2ode_fused_workspace_bytes(n_traj), st));
-        traj_of[0] = n_traj;
-        p.ll[0] = (unsigned long long *)((unsigned char *)workspace + 256);
-        p.seq_store = nullptr;
-        p.rank = 0;
-        p.nranks = 0;
-        p.pstride = 1;
-    }
+    p.bar = (unsigned *)w;
+    p.gflag = (unsigned long long *)(w + 64);
+    p.gtot = (Partial *)(w + 128);
+    p.part = (Partial *)(w + 256);
     p.y0 = y0;
     p.out = out;
     p.n_traj = n_traj;
@@ -661,8 +700,14 @@ extern "C" int b2ode_fused_solve(const b2ode_adaptive_desc *desc, int rhs_kind, 
     p.c.n_out = n_out;
     p.c.t_out = t_out;
     p.c.tstage = nullptr;
-    p.c.n_global[0] = n_glob * D;
-    if (desc->dtype == B2ODE_F64) return fused_dispatch_rhs<double>(p, rhs_kind, nk, traj_of, st);
-    if (desc->dtype == B2ODE_F32) return fused_dispatch_rhs<float>(p, rhs_kind, nk, traj_of, st);
+    p.c.n_global[0] = (nranks > 1 ? n_traj_global : n_traj) * D;
+    p.comm.rank = rank;
+    p.comm.nranks = nranks > 1 ? nranks : 0;
+    if (nranks > 1) {
+        if (!mailboxes || nranks > B2ODE_MAXPEERS) return b2_fail(B2ODE_EINVAL, "bad mailboxes");
+        for (int r = 0; r < nranks; ++r) p.comm.box[r] = (Mailbox *)mailboxes[r];
+    }
+    if (desc->dtype == B2ODE_F64) return fused_dispatch_rhs<double>(p, rhs_kind, nk, n_traj, st);
+    if (desc->dtype == B2ODE_F32) return fused_dispatch_rhs<float>(p, rhs_kind, nk, n_traj, st);
     return b2_fail(B2ODE_EINVAL, "dtype must be 0 or 1");
 }

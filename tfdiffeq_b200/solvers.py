@@ -230,15 +230,15 @@ class AdaptiveStepsizeODESolver(object):
         prm = base.rhs_params()
         prm_arr = (C.c_double * 8)(*(prm + [0.0] * (8 - len(prm))))
         first = float("nan") if self.first_step is None else _tf_f64(self.first_step)
-        rank, world, boxes, per_rank = 0, 1, None, None
+        rank, world, boxes, n_glob = 0, 1, None, n_traj
         if self.comm is not None:
             rank, world, boxes = self.comm.rank, self.comm.world, self.comm._ptrs
-            per_rank = _lib.LenArray(*self.comm.all_counts(n_traj))     # every rank's batch (grid sizes of the peers)
+            n_glob = self.comm.global_count(n_traj)
         stream = torch.cuda.current_stream(dev)
         rc = lib.b2ode_fused_solve(C.byref(desc), base.kind, prm_arr, len(prm), float(self.func._b2ode_sign),
                                    C.c_void_p(y0.data_ptr()), C.c_void_p(out.data_ptr()), C.c_void_p(t_dev.data_ptr()),
                                    n_out, float(t_host[0]), first, C.c_void_p(state_dev.data_ptr()),
-                                   C.c_void_p(workspace.data_ptr()), ws_bytes, rank, world, boxes, per_rank,
+                                   C.c_void_p(workspace.data_ptr()), ws_bytes, rank, world, boxes, n_glob,
                                    C.c_void_p(stream.cuda_stream))
         if rc == -3:          # batch larger than what can stay co-resident: use the generic path
             return None
