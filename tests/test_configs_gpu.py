@@ -90,23 +90,28 @@ def test_config4_conv_odefunc_forward_vs_oracle_and_adjoint_gradient():
     assert max_rel_err(got.cpu().numpy(), ref.numpy()) <= 1e-6
     # adjoint backward (reference ODEBlock(adjoint=True) raises, dense_odenet.py:116: the func is used directly)
     x = x0.to(DEV).requires_grad_(True)
-    tight = dict(rtol=1e-9, atol=1e-9, method="dopri5")
+    tight = dict(rtol=1e-10, atol=1e-10, method="dopri5")
     out = tfd().odeint_adjoint(m, x, t, **tight)
     loss = (out[-1] ** 2).mean()
     loss.backward()
-    g = m.c2.weight.grad[1, 2, 0, 1].item()
     assert all(p.grad is not None and bool(torch.isfinite(p.grad).all()) for p in m.parameters())
     assert x.grad is not None and bool(torch.isfinite(x.grad).all())
+    # directional derivative along a random direction of the 3x3 conv weights (one entry alone is below the
+    # noise floor of a finite difference of two 1e-10-accurate solves)
+    w = m.c2.weight
+    v = torch.randn_like(w)
+    v /= v.norm()
+    g_dir = float((w.grad * v).sum())
 
     def fwd():
         with torch.no_grad():
             return float((tfd().odeint(m, x0.to(DEV), t, **tight)[-1] ** 2).mean())
-    w = m.c2.weight
-    old = w.data[1, 2, 0, 1].item()
-    w.data[1, 2, 0, 1] = old + 1e-5
+    w0 = w.data.clone()
+    eps = 1e-4
+    w.data = w0 + eps * v
     lp = fwd()
-    w.data[1, 2, 0, 1] = old - 1e-5
+    w.data = w0 - eps * v
     lm = fwd()
-    w.data[1, 2, 0, 1] = old
-    fd = (lp - lm) / 2e-5
-    assert abs(fd - g) <= 1e-5 * max(1.0, abs(fd)), (fd, g)
+    w.data = w0
+    fd = (lp - lm) / (2 * eps)
+    assert abs(fd - g_dir) <= 1e-4 * max(abs(fd), 1e-3), (fd, g_dir)

@@ -358,3 +358,53 @@ def test_cuda_graph_with_tuple_state_and_reverse_time():
     b = tfd().odeint(f, y0, t, method="dopri5", options=dict(cuda_graph=True))
     for x, y in zip(a, b):
         assert torch.equal(x, y)
+
+
+# --------------------------------------------------------------------------------------------------
+# option surface
+# --------------------------------------------------------------------------------------------------
+def test_option_surface_and_input_forms():
+    f = lambda t, y: -y                                            # noqa: E731
+    y0 = torch.linspace(0.5, 1.5, 10, dtype=torch.float64, device=DEV)
+    t_cpu = torch.linspace(0., 1., 5)
+    base = tfd().odeint(f, y0, t_cpu, method="dopri5")
+    # t on the GPU, in float64, or as a python list: same result
+    assert torch.equal(base, tfd().odeint(f, y0, t_cpu.to(DEV), method="dopri5"))
+    assert torch.equal(base, tfd().odeint(f, y0, t_cpu.tolist(), method="dopri5"))
+    # Dopri5's `tableau=` option (dopri5.py:53,67) and per-component tolerances as lists
+    from tfdiffeq_b200 import tableaus
+    assert torch.equal(base, tfd().odeint(f, y0, t_cpu, method="dopri5", options=dict(tableau=tableaus.DOPRI5)))
+    assert torch.equal(base, tfd().odeint(f, y0, t_cpu, method="dopri5", rtol=[1e-7], atol=[1e-9]))
+    # the caller's options dict is not modified
+    opts = dict(first_step=0.05, cuda_graph=False)
+    tfd().odeint(f, y0, t_cpu, method="dopri5", options=opts)
+    assert opts == dict(first_step=0.05, cuda_graph=False)
+    # grid_constructor (solvers.py:41-56): a finer uniform grid, outputs by linear interpolation
+    gc = lambda func, y, t: torch.linspace(float(t[0]), float(t[-1]), 41, dtype=t.dtype)   # noqa: E731
+    a = tfd().odeint(f, y0, t_cpu, method="rk4", options=dict(grid_constructor=gc))
+    exact = y0.cpu().numpy()[None, :] * np.exp(-np.linspace(0., 1., 5))[:, None]
+    assert np.max(np.abs(a.cpu().numpy() - exact)) < 1e-7
+    # integer states are rejected (the engine integrates float32 / float64)
+    with pytest.raises(TypeError):
+        tfd().odeint(f, torch.ones(3, dtype=torch.int64, device=DEV), t_cpu, method="dopri5")
+    with pytest.raises(AssertionError):
+        tfd().odeint(f, y0, torch.tensor([0., 2., 1.]), method="dopri5")
+    # func returning a tensor of the wrong size is an error, not silent corruption
+    with pytest.raises((ValueError, RuntimeError)):
+        tfd().odeint(lambda t, y: y[:3], y0, t_cpu, method="dopri5")
+
+
+def test_nfe_counter_on_the_module_matches_the_reference_pattern():
+    """The reference's models count function evaluations on the module (dense_odenet.py:38,78); on the eager
+    path every evaluation is a real python call, so the count equals last_stats['nfe']."""
+    class F(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.nfe = 0
+
+        def forward(self, t, y):
+            self.nfe += 1
+            return -y
+    m = F()
+    tfd().odeint(m, torch.ones(4, dtype=torch.float64, device=DEV), torch.tensor([0., 1.]), method="dopri5")
+    assert m.nfe == tfd().last_stats["nfe"]
