@@ -193,6 +193,8 @@ int b2ode_comm_set_global_len(b2ode_solver *s, const int64_t *global_len);
 
 #define B2ODE_RHS_LORENZ 0          /* (B,3): s(y-x), x(r-z)-y, xy-bz ; params {sigma, beta, rho}   examples/lorenz_attractor.py:20-37 */
 #define B2ODE_RHS_LOTKA_VOLTERRA 1  /* (B,2): ax-bxz, -cz+dxz        ; params {a, b, c, d}          README.md:67-81                   */
+#define B2ODE_RHS_CUBIC_MLP 2       /* (B,2): W2 tanh(W1 y^3 + b1) + b2; params {H <= 128, cube}; rhs_data = packed
+                                       [W1 (2 x H) | b1 (H) | W2 (H x 2) | b2 (2)] in the state dtype   examples/ode_demo.py:115-129 */
 
 /* Replaces the WHOLE of AdaptiveStepsizeODESolver.integrate (tfdiffeq/solvers.py:27-35) for a func the library
  * knows: every trajectory stays in one thread's registers (state + all k's) for the entire solve, one grid-wide
@@ -203,9 +205,19 @@ int b2ode_comm_set_global_len(b2ode_solver *s, const int64_t *global_len);
  * generic path).  time_sign = -1 integrates the reversed system of tfdiffeq/misc.py:318-321. */
 size_t b2ode_fused_workspace_bytes(int64_t n_trajectories);
 int b2ode_fused_solve(const b2ode_adaptive_desc *desc, int rhs_kind, const double *rhs_params, int n_rhs_params,
-                      double time_sign, const void *y0, void *out, const double *t_out, int n_out, double t_start,
+                      const void *rhs_data, double time_sign, const void *y0, void *out, const double *t_out, int n_out, double t_start,
                       double first_step, void *state, void *workspace, size_t workspace_bytes, int rank, int nranks,
                       void *const *mailboxes, int64_t n_traj_global, void *cuda_stream);
+
+/* Fixed-grid methods (0 euler, 1 midpoint, 2 heun, 3 rk4 3/8 rule) with a built-in right-hand side: replaces the
+ * whole of FixedGridODESolver.integrate (tfdiffeq/solvers.py:82-104); no reductions, one launch.  The host
+ * supplies, in the state dtype, the stage times of every grid cell ([n_steps][4]), dt per cell, and for the
+ * outputs: j0[i]..j0[i+1] = outputs inside cell i, ends[i] = the cell ends exactly on its last output (then y1 is
+ * stored, otherwise the linear interpolation of solvers.py:106-115 with s1[i] = t1 - t0 and s2[j] = t_j - t0). */
+int b2ode_fused_fixed_solve(int dtype, int method, int rhs_kind, const double *rhs_params, int n_rhs_params,
+                            const void *rhs_data, double time_sign, const void *y0, void *out, int64_t n_traj,
+                            int n_steps, int n_out, const void *times, const void *dts, const int32_t *j0,
+                            const unsigned char *ends, const void *s1, const void *s2, int sm_count, void *cuda_stream);
 
 /* ---- measurement hooks (bench.py) --------------------------------------------------------------------- */
 unsigned long long b2ode_launch_count(void);            /* kernels launched by this library so far          */

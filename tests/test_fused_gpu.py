@@ -111,3 +111,69 @@ def test_fused_status_bits_and_fallbacks():
     big = torch.ones(300000, 3, dtype=torch.float64, device=DEV)
     tfd().odeint(f, big, torch.tensor([0., 0.01]), method="dopri5")
     assert not tfd().last_stats["fused_rhs"]
+
+
+# --------------------------------------------------------------------------------------------------
+# fixed-grid methods with a built-in right-hand side: one launch, no reductions
+# --------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("method", ["euler", "midpoint", "heun", "rk4"])
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_fused_fixed_grid_is_bit_identical_to_generic_path(method, dtype):
+    """Same IEEE operations in the same order, and no reduction anywhere: the two paths must agree exactly."""
+    rng = np.random.default_rng(4)
+    y0 = torch.tensor(np.array([1., 1., 1.]) + 0.1 * rng.standard_normal((1000, 3)), dtype=dtype, device=DEV)
+    t = torch.linspace(0., 0.5, 51)
+    f = tfd().rhs.Lorenz()
+    a = tfd().odeint(f, y0, t, method=method)
+    assert tfd().last_stats["fused_rhs"]
+    nfe_a = tfd().last_stats["nfe"]
+    b = tfd().odeint(f, y0, t, method=method, options=dict(fused_rhs=False))
+    assert not tfd().last_stats["fused_rhs"] and tfd().last_stats["nfe"] == nfe_a
+    assert torch.equal(a, b)
+    # reverse time and a finer internal grid with interpolated outputs
+    tr = torch.tensor([0.5, 0.37, 0.2, 0.0])
+    a = tfd().odeint(f, y0, tr, method=method, options=dict(step_size=0.03))
+    b = tfd().odeint(f, y0, tr, method=method, options=dict(step_size=0.03, fused_rhs=False))
+    assert torch.equal(a, b)
+
+
+def test_cubic_mlp_builtin_fixed_and_adaptive_vs_generic():
+    g = torch.Generator().manual_seed(0)
+    for dtype, tol in ((torch.float64, 1e-9), (torch.float32, 1e-3)):
+        m = tfd().rhs.CubicMLP(hidden=50, dtype=dtype, generator=g).to(DEV)
+        rng = np.random.default_rng(9)
+        y0 = torch.tensor(np.array([2., 0.]) + 0.1 * rng.standard_normal((777, 2)), dtype=dtype, device=DEV)
+        t = torch.linspace(0., 2., 81)
+        a = tfd().odeint(m, y0, t, method="rk4")
+        assert tfd().last_stats["fused_rhs"]
+        b = tfd().odeint(m, y0, t, method="rk4", options=dict(fused_rhs=False))
+        # torch evaluates the two matrix products with cuBLAS (its own FMA order): agreement to rounding
+        assert float((a - b).abs().max()) <= tol * max(1.0, float(b.abs().max()))
+        kw = dict(rtol=1e-6, atol=1e-8) if dtype == torch.float64 else dict(rtol=1e-3, atol=1e-4)
+        a = tfd().odeint(m, y0, t[:21], method="dopri5", **kw)
+        sa = dict(tfd().last_stats)
+        b = tfd().odeint(m, y0, t[:21], method="dopri5", options=dict(fused_rhs=False), **kw)
+        sb = dict(tfd().last_stats)
+        assert sa["fused_rhs"] and not sb["fused_rhs"]
+        assert abs(sa["n_accepted"] - sb["n_accepted"]) <= 1 and abs(sa["n_rejected"] - sb["n_rejected"]) <= 1
+        assert float((a - b).abs().max()) <= max(tol, 1e-6) * max(1.0, float(b.abs().max()))
+
+
+def test_config3_full_size_fused_mlp_rk4():
+    """BASELINE config 3 at full size through the built-in module: 131 072 x 2 fp32, rk4, 2 000 grid cells, ONE
+    kernel launch; a random subset is checked against the oracle (fixed grids have no coupling between
+    trajectories)."""
+    g = torch.Generator().manual_seed(1)
+    m = tfd().rhs.CubicMLP(hidden=50, dtype=torch.float32, generator=g).to(DEV)
+    rng = np.random.default_rng(3)
+    y0 = (np.array([2., 0.]) + 0.1 * rng.standard_normal((131072, 2))).astype(np.float32)
+    t = np.linspace(0., 25., 2001).astype(np.float32)
+    sol = tfd().odeint(m, torch.tensor(y0, device=DEV), torch.tensor(t), method="rk4")
+    s = dict(tfd().last_stats)
+    assert s["fused_rhs"] and s["nfe"] == 8000 and sol.shape == (2001, 131072, 2)
+    W1, b1, W2, b2 = (p.detach().cpu().numpy() for p in (m.W1, m.b1, m.W2, m.b2))
+    f_np = lambda tt, y: np.tanh((y ** 3) @ W1 + b1) @ W2 + b2               # noqa: E731
+    idx = rng.choice(131072, size=32, replace=False)
+    ref = np_ref.odeint(f_np, y0[idx], t, method="rk4")
+    got = sol[:, torch.tensor(idx, device=DEV)].cpu().numpy()
+    assert max_rel_err(got, ref) <= 1e-3

@@ -13,7 +13,7 @@ F32, F64 = 0, 1
 ST_UNDERFLOW, ST_NONFINITE, ST_MAXSTEPS = 1, 2, 4
 CTRL_REFERENCE, CTRL_TSIT5 = 0, 1
 FAM_STAGE0, FAM_STAGE, FAM_FINALIZE, FAM_EMIT, FAM_INIT, FAM_FIXED, FAM_FUSED = range(7)
-RHS_LORENZ, RHS_LOTKA_VOLTERRA = 0, 1
+RHS_LORENZ, RHS_LOTKA_VOLTERRA, RHS_CUBIC_MLP = 0, 1, 2
 OP_EULER, OP_HALF_STEP, OP_HEUN_FINAL, OP_RK4_S2, OP_RK4_S3, OP_RK4_S4, OP_RK4_FINAL, OP_LERP = range(8)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -78,7 +78,10 @@ _SIGNATURES = {
     "b2ode_mailbox_close": (C.c_int, [C.c_void_p]),
     "b2ode_mailbox_destroy": (C.c_int, [C.c_void_p]),
     "b2ode_fused_workspace_bytes": (C.c_size_t, [C.c_int64]),
-    "b2ode_fused_solve": (C.c_int, [C.POINTER(AdaptiveDesc), C.c_int, C.POINTER(C.c_double), C.c_int, C.c_double,
+    "b2ode_fused_fixed_solve": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.c_int, C.c_void_p, C.c_double,
+                                          C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "b2ode_fused_solve": (C.c_int, [C.POINTER(AdaptiveDesc), C.c_int, C.POINTER(C.c_double), C.c_int, C.c_void_p, C.c_double,
                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_void_p,
                                     C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_int64,
                                     C.c_void_p]),

@@ -21,7 +21,8 @@
 template <typename T>
 struct RhsLorenz {   // examples/lorenz_attractor.py:20-37 ; params {sigma, beta, rho}
     static constexpr int D = 3;
-    static __device__ __forceinline__ void eval(const double *prm, T /*t*/, const T (&y)[3], T (&dy)[3]) {
+    static constexpr int kSmem = 1;      // no staged weights
+    static __device__ __forceinline__ void eval(const double *prm, const T * /*sw*/, T /*t*/, const T (&y)[3], T (&dy)[3]) {
         using A = Ar<T>;
         const T sigma = (T)prm[0], beta = (T)prm[1], rho = (T)prm[2];
         dy[0] = A::mul(sigma, A::sub(y[1], y[0]));                          // sigma * (y - x)
@@ -33,12 +34,44 @@ struct RhsLorenz {   // examples/lorenz_attractor.py:20-37 ; params {sigma, beta
 template <typename T>
 struct RhsLotkaVolterra {   // README.md:67-81 ; params {a, b, c, d}
     static constexpr int D = 2;
-    static __device__ __forceinline__ void eval(const double *prm, T /*t*/, const T (&y)[2], T (&dy)[2]) {
+    static constexpr int kSmem = 1;
+    static __device__ __forceinline__ void eval(const double *prm, const T * /*sw*/, T /*t*/, const T (&y)[2], T (&dy)[2]) {
         using A = Ar<T>;
         const T a = (T)prm[0], b = (T)prm[1], c = (T)prm[2], d = (T)prm[3];
         dy[0] = A::sub(A::mul(a, y[0]), A::mul(A::mul(b, y[0]), y[1]));     // a*x - b*x*z
         dy[1] = A::add(A::mul(-c, y[1]), A::mul(A::mul(d, y[0]), y[1]));    // -c*z + d*x*z
     }
+};
+
+// examples/ode_demo.py:115-129 (BASELINE config 3): W2 . tanh(W1 . y**3 + b1) + b2, 2 -> H -> 2, H <= 128.
+// params {H, cube}; weights staged in shared memory, packed [W1 (2 x H) | b1 (H) | W2 (H x 2) | b2 (2)].
+// torch evaluates the two products with cuBLAS (its own FMA order), so this right-hand side agrees with the
+// module's forward to rounding, not bit for bit.
+template <typename T>
+struct RhsCubicMLP {
+    static constexpr int D = 2;
+    static constexpr int kMaxH = 128;
+    static constexpr int kSmem = 2 * kMaxH + kMaxH + 2 * kMaxH + 2;
+    static __device__ __forceinline__ T act(T a) { return (T)tanh((double)a); }
+    static __device__ __forceinline__ void eval(const double *prm, const T *sw, T /*t*/, const T (&y)[2], T (&dy)[2]) {
+        using A = Ar<T>;
+        const int H = (int)prm[0];
+        const bool cube = prm[1] != 0.0;
+        const T u0 = cube ? A::mul(A::mul(y[0], y[0]), y[0]) : y[0];
+        const T u1 = cube ? A::mul(A::mul(y[1], y[1]), y[1]) : y[1];
+        const T *W1 = sw, *b1 = sw + 2 * H, *W2 = sw + 3 * H, *b2 = sw + 5 * H;
+        T o0 = T(0), o1 = T(0);
+        for (int h = 0; h < H; ++h) {
+            const T a = A::add(A::add(A::mul(u0, W1[h]), A::mul(u1, W1[H + h])), b1[h]);
+            const T z = act_dispatch(a);
+            o0 = A::add(o0, A::mul(z, W2[2 * h]));
+            o1 = A::add(o1, A::mul(z, W2[2 * h + 1]));
+        }
+        dy[0] = A::add(o0, b2[0]);
+        dy[1] = A::add(o1, b2[1]);
+    }
+    static __device__ __forceinline__ float act_dispatch(float a) { return tanhf(a); }
+    static __device__ __forceinline__ double act_dispatch(double a) { return tanh(a); }
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -57,6 +90,7 @@ struct FusedParams {
     double t_start, first_step;
     double time_sign;       // -1 when integrating the reversed system (misc.py:318-321)
     double rhs[8];
+    const void *rhs_data;   // device buffer of staged weights (RhsCubicMLP), else null
     // tableau (runtime values; structural zeros are skipped exactly like the generic path does)
     double beta[B2ODE_MAXK][B2ODE_MAXK];
     double c_sol[B2ODE_MAXK], c_error[B2ODE_MAXK], c_mid[B2ODE_MAXK];
@@ -305,14 +339,20 @@ __global__ void __launch_bounds__(BT) k_fused_adaptive(const __grid_constant__ F
 #pragma unroll
         for (int d = 0; d < D; ++d) out[i * D + d] = y[d];                 // solution[0] = y0 (solvers.py:29)
     }
+    __shared__ T sw[RHS::kSmem];
+    if (RHS::kSmem > 1) {
+        const int nw = (int)p.rhs[0] * 5 + 2;
+        for (int q = threadIdx.x; q < nw && q < RHS::kSmem; q += BT) sw[q] = ((const T *)p.rhs_data)[q];
+        __syncthreads();
+    }
     auto rhs = [&](T t, const T(&yy)[D], T(&dy)[D]) {
         // reverse-time wrapper of misc.py:318-321: f'(t, y) = -f(-t, y)
         if (tsign < T(0)) {
-            RHS::eval(p.rhs, -t, yy, dy);
+            RHS::eval(p.rhs, sw, -t, yy, dy);
 #pragma unroll
             for (int d = 0; d < D; ++d) dy[d] = -dy[d];
         } else {
-            RHS::eval(p.rhs, t, yy, dy);
+            RHS::eval(p.rhs, sw, t, yy, dy);
         }
     };
     double t_cur = p.t_start;
@@ -632,11 +672,22 @@ static int fused_dispatch_rhs(const FusedParams &p, int rhs_kind, int n_k, long 
     switch (rhs_kind) {
         case B2ODE_RHS_LORENZ: return fused_dispatch_s<T, RhsLorenz<T>>(p, n_k, n_traj, st);
         case B2ODE_RHS_LOTKA_VOLTERRA: return fused_dispatch_s<T, RhsLotkaVolterra<T>>(p, n_k, n_traj, st);
+        case B2ODE_RHS_CUBIC_MLP: return fused_dispatch_s<T, RhsCubicMLP<T>>(p, n_k, n_traj, st);
     }
     return b2_fail(B2ODE_EINVAL, "unknown built-in right-hand side %d", rhs_kind);
 }
 
-static int rhs_dim(int kind) { return kind == B2ODE_RHS_LORENZ ? 3 : kind == B2ODE_RHS_LOTKA_VOLTERRA ? 2 : -1; }
+static int rhs_dim(int kind) {
+    return kind == B2ODE_RHS_LORENZ ? 3 : (kind == B2ODE_RHS_LOTKA_VOLTERRA || kind == B2ODE_RHS_CUBIC_MLP) ? 2 : -1;
+}
+
+static int rhs_check(int kind, const double *prm, int n_prm, const void *rhs_data) {
+    if (kind == B2ODE_RHS_CUBIC_MLP) {
+        if (n_prm < 2 || !rhs_data) return b2_fail(B2ODE_EINVAL, "cubic-MLP right-hand side needs {H, cube} and its weights");
+        if (prm[0] < 1 || prm[0] > 128) return b2_fail(B2ODE_EINVAL, "cubic-MLP hidden width must be in [1, 128]");
+    }
+    return 0;
+}
 
 extern "C" size_t b2ode_fused_workspace_bytes(int64_t n_traj) {
     const long long grid = (n_traj + 127) / 128;      // the smallest block size used is 128
@@ -645,7 +696,7 @@ extern "C" size_t b2ode_fused_workspace_bytes(int64_t n_traj) {
 }
 
 extern "C" int b2ode_fused_solve(const b2ode_adaptive_desc *desc, int rhs_kind, const double *rhs_params, int n_rhs_params,
-                                 double time_sign, const void *y0, void *out, const double *t_out, int n_out, double t_start,
+                                 const void *rhs_data, double time_sign, const void *y0, void *out, const double *t_out, int n_out, double t_start,
                                  double first_step, void *state, void *workspace, size_t workspace_bytes, int rank, int nranks,
                                  void *const *mailboxes, int64_t n_traj_global, void *cuda_stream) {
     if (!desc || !y0 || !out || !t_out || !state || !workspace) return b2_fail(B2ODE_EINVAL, "null argument");
@@ -676,6 +727,11 @@ extern "C" int b2ode_fused_solve(const b2ode_adaptive_desc *desc, int rhs_kind, 
     p.first_step = first_step;
     p.time_sign = time_sign;
     for (int i = 0; i < n_rhs_params; ++i) p.rhs[i] = rhs_params[i];
+    p.rhs_data = rhs_data;
+    {
+        const int rc_ = rhs_check(rhs_kind, rhs_params, n_rhs_params, rhs_data);
+        if (rc_) return rc_;
+    }
     const int nk = desc->n_k;
     for (int i = 0; i < B2ODE_MAXK; ++i) {
         for (int j = 0; j < B2ODE_MAXK; ++j) p.beta[i][j] = desc->beta[i][j];
@@ -709,5 +765,158 @@ extern "C" int b2ode_fused_solve(const b2ode_adaptive_desc *desc, int rhs_kind, 
     }
     if (desc->dtype == B2ODE_F64) return fused_dispatch_rhs<double>(p, rhs_kind, nk, n_traj, st);
     if (desc->dtype == B2ODE_F32) return fused_dispatch_rhs<float>(p, rhs_kind, nk, n_traj, st);
+    return b2_fail(B2ODE_EINVAL, "dtype must be 0 or 1");
+}
+
+// ================================================================================================
+// fixed-grid methods with a built-in right-hand side: no step-size control, hence no reductions at all --
+// every thread integrates its trajectory through the whole grid and writes its outputs
+// (tfdiffeq/solvers.py:82-115, fixed_grid.py, rk_common.py:73-81; same operation order as k_fixed<T, OP>)
+// ================================================================================================
+struct FusedFixedParams {
+    const void *y0;
+    void *out;
+    long long n_traj;
+    int n_steps, n_out, method;     // method: 0 euler, 1 midpoint, 2 heun, 3 rk4 (3/8 rule)
+    const void *times;              // [n_steps][4] stage times, state dtype
+    const void *dts;                // [n_steps]
+    const int *j0;                  // [n_steps + 1]: outputs inside cell i are [j0[i], j0[i+1])
+    const unsigned char *ends;      // [n_steps]: the cell ends exactly on its last output
+    const void *s1;                 // [n_steps]  t1 - t0
+    const void *s2;                 // [n_out]    t_out[j] - t0 of its cell
+    double time_sign;
+    double rhs[8];
+    const void *rhs_data;
+};
+
+template <typename T, typename RHS>
+__global__ void __launch_bounds__(256) k_fused_fixed(const __grid_constant__ FusedFixedParams p) {
+    using A = Ar<T>;
+    constexpr int D = RHS::D;
+    __shared__ T sw[RHS::kSmem];
+    if (RHS::kSmem > 1) {
+        const int nw = (int)p.rhs[0] * 5 + 2;
+        for (int q = threadIdx.x; q < nw && q < RHS::kSmem; q += 256) sw[q] = ((const T *)p.rhs_data)[q];
+        __syncthreads();
+    }
+    const T tsign = (T)p.time_sign;
+    auto rhs = [&](T t, const T(&yy)[D], T(&dy)[D]) {
+        if (tsign < T(0)) {
+            RHS::eval(p.rhs, sw, -t, yy, dy);
+#pragma unroll
+            for (int d = 0; d < D; ++d) dy[d] = -dy[d];
+        } else {
+            RHS::eval(p.rhs, sw, t, yy, dy);
+        }
+    };
+    const long long N = p.n_traj * D;
+    const T *times = (const T *)p.times, *dts = (const T *)p.dts, *s1 = (const T *)p.s1, *s2 = (const T *)p.s2;
+    T *out = (T *)p.out;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < p.n_traj; i += (long long)gridDim.x * 256) {
+        T y[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            y[d] = ((const T *)p.y0)[i * D + d];
+            out[i * D + d] = y[d];
+        }
+        for (int s = 0; s < p.n_steps; ++s) {
+            const T dt = dts[s];
+            const T *tm = times + 4 * s;
+            T y1[D], k1[D], k2[D], k3[D], k4[D], ys[D];
+            rhs(tm[0], y, k1);
+            if (p.method == 0) {
+#pragma unroll
+                for (int d = 0; d < D; ++d) y1[d] = A::add(y[d], A::mul(dt, k1[d]));                       // B2ODE_OP_EULER
+            } else if (p.method == 1) {
+#pragma unroll
+                for (int d = 0; d < D; ++d) ys[d] = A::add(y[d], A::div(A::mul(k1[d], dt), T(2)));         // HALF_STEP
+                rhs(tm[1], ys, k2);
+#pragma unroll
+                for (int d = 0; d < D; ++d) y1[d] = A::add(y[d], A::mul(dt, k2[d]));
+            } else if (p.method == 2) {
+#pragma unroll
+                for (int d = 0; d < D; ++d) ys[d] = A::add(y[d], A::mul(dt, k1[d]));
+                rhs(tm[1], ys, k2);
+#pragma unroll
+                for (int d = 0; d < D; ++d) y1[d] = A::add(y[d], A::mul(A::div(dt, T(2)), A::add(k1[d], k2[d])));   // HEUN_FINAL
+            } else {
+#pragma unroll
+                for (int d = 0; d < D; ++d) ys[d] = A::add(y[d], A::div(A::mul(dt, k1[d]), T(3)));         // RK4_S2
+                rhs(tm[1], ys, k2);
+#pragma unroll
+                for (int d = 0; d < D; ++d) ys[d] = A::add(y[d], A::mul(dt, A::add(A::div(k1[d], T(-3)), k2[d])));   // RK4_S3
+                rhs(tm[2], ys, k3);
+#pragma unroll
+                for (int d = 0; d < D; ++d) ys[d] = A::add(y[d], A::mul(dt, A::add(A::sub(k1[d], k2[d]), k3[d])));   // RK4_S4
+                rhs(tm[3], ys, k4);
+#pragma unroll
+                for (int d = 0; d < D; ++d)
+                    y1[d] = A::add(y[d], A::mul(A::add(A::add(A::add(k1[d], A::mul(T(3), k2[d])), A::mul(T(3), k3[d])), k4[d]),
+                                                A::div(dt, T(8))));                                          // RK4_FINAL
+            }
+            const int ja = p.j0[s], jb = p.j0[s + 1];
+            for (int j = ja; j < jb; ++j) {
+                T *row = out + (long long)j * N + i * D;
+                if (j == jb - 1 && p.ends[s]) {
+#pragma unroll
+                    for (int d = 0; d < D; ++d) row[d] = y1[d];
+                } else {
+#pragma unroll
+                    for (int d = 0; d < D; ++d) row[d] = A::add(y[d], A::mul(A::div(A::sub(y1[d], y[d]), s1[s]), s2[j]));   // LERP
+                }
+            }
+#pragma unroll
+            for (int d = 0; d < D; ++d) y[d] = y1[d];
+        }
+    }
+}
+
+template <typename T>
+static int fused_fixed_dispatch(const FusedFixedParams &p, int rhs_kind, int sm_count, cudaStream_t st) {
+    const long long blocks_needed = (p.n_traj + 255) / 256;
+    const long long cap = (long long)(sm_count > 0 ? sm_count : 148) * 8;
+    const int grid = (int)(blocks_needed < cap ? blocks_needed : cap);
+    switch (rhs_kind) {
+        case B2ODE_RHS_LORENZ: k_fused_fixed<T, RhsLorenz<T>><<<grid, 256, 0, st>>>(p); break;
+        case B2ODE_RHS_LOTKA_VOLTERRA: k_fused_fixed<T, RhsLotkaVolterra<T>><<<grid, 256, 0, st>>>(p); break;
+        case B2ODE_RHS_CUBIC_MLP: k_fused_fixed<T, RhsCubicMLP<T>><<<grid, 256, 0, st>>>(p); break;
+        default: return b2_fail(B2ODE_EINVAL, "unknown built-in right-hand side %d", rhs_kind);
+    }
+    B2_CUDA(cudaGetLastError());
+    b2_count_launch();
+    return 0;
+}
+
+extern "C" int b2ode_fused_fixed_solve(int dtype, int method, int rhs_kind, const double *rhs_params, int n_rhs_params,
+                                       const void *rhs_data, double time_sign, const void *y0, void *out, int64_t n_traj,
+                                       int n_steps, int n_out, const void *times, const void *dts, const int32_t *j0,
+                                       const unsigned char *ends, const void *s1, const void *s2, int sm_count,
+                                       void *cuda_stream) {
+    if (!y0 || !out || n_traj < 1 || n_out < 1 || n_steps < 0) return b2_fail(B2ODE_EINVAL, "bad arguments");
+    if (n_steps > 0 && (!times || !dts || !j0 || !ends || !s1 || !s2)) return b2_fail(B2ODE_EINVAL, "null grid array");
+    if (method < 0 || method > 3) return b2_fail(B2ODE_EINVAL, "method must be 0..3");
+    if (rhs_dim(rhs_kind) < 0) return b2_fail(B2ODE_EINVAL, "unknown built-in right-hand side %d", rhs_kind);
+    if (n_rhs_params < 0 || n_rhs_params > 8 || (n_rhs_params && !rhs_params)) return b2_fail(B2ODE_EINVAL, "bad rhs params");
+    const int rc = rhs_check(rhs_kind, rhs_params, n_rhs_params, rhs_data);
+    if (rc) return rc;
+    FusedFixedParams p;
+    memset(&p, 0, sizeof(p));
+    p.y0 = y0;
+    p.out = out;
+    p.n_traj = n_traj;
+    p.n_steps = n_steps;
+    p.n_out = n_out;
+    p.method = method;
+    p.times = times;
+    p.dts = dts;
+    p.j0 = j0;
+    p.ends = ends;
+    p.s1 = s1;
+    p.s2 = s2;
+    p.time_sign = time_sign;
+    for (int i = 0; i < n_rhs_params; ++i) p.rhs[i] = rhs_params[i];
+    p.rhs_data = rhs_data;
+    if (dtype == B2ODE_F64) return fused_fixed_dispatch<double>(p, rhs_kind, sm_count, (cudaStream_t)cuda_stream);
+    if (dtype == B2ODE_F32) return fused_fixed_dispatch<float>(p, rhs_kind, sm_count, (cudaStream_t)cuda_stream);
     return b2_fail(B2ODE_EINVAL, "dtype must be 0 or 1");
 }

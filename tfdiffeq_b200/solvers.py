@@ -229,13 +229,16 @@ class AdaptiveStepsizeODESolver(object):
         desc = self._describe(seg)
         prm = base.rhs_params()
         prm_arr = (C.c_double * 8)(*(prm + [0.0] * (8 - len(prm))))
+        weights = base.rhs_data(dtype, dev)
         first = float("nan") if self.first_step is None else _tf_f64(self.first_step)
         rank, world, boxes, n_glob = 0, 1, None, n_traj
         if self.comm is not None:
             rank, world, boxes = self.comm.rank, self.comm.world, self.comm._ptrs
             n_glob = self.comm.global_count(n_traj)
         stream = torch.cuda.current_stream(dev)
-        rc = lib.b2ode_fused_solve(C.byref(desc), base.kind, prm_arr, len(prm), float(self.func._b2ode_sign),
+        rc = lib.b2ode_fused_solve(C.byref(desc), base.kind, prm_arr, len(prm),
+                                   C.c_void_p(weights.data_ptr()) if weights is not None else None,
+                                   float(self.func._b2ode_sign),
                                    C.c_void_p(y0.data_ptr()), C.c_void_p(out.data_ptr()), C.c_void_p(t_dev.data_ptr()),
                                    n_out, float(t_host[0]), first, C.c_void_p(state_dev.data_ptr()),
                                    C.c_void_p(workspace.data_ptr()), ws_bytes, rank, world, boxes, n_glob,
@@ -472,6 +475,9 @@ class FixedGridODESolver(object):
     def __init__(self, func, y0, step_size=None, grid_constructor=None, eps=0.0, **unused_kwargs):
         unused_kwargs.pop('rtol', None)
         unused_kwargs.pop('atol', None)
+        unused_kwargs.pop('shared_step_group', None)     # a fixed grid needs no exchange between shards
+        unused_kwargs.pop('cuda_graph', None)
+        self.fused_rhs = bool(unused_kwargs.pop("fused_rhs", True))
         _handle_unused_kwargs(self, unused_kwargs)
         del unused_kwargs
         self.func = func
@@ -541,6 +547,46 @@ class FixedGridODESolver(object):
             te = t0s + eps                                                     # fixed_grid.py:42
             times = np.stack([te, te + dts / npdt(3), te + dts * npdt(2) / npdt(3), te + dts], 1)  # rk_common.py:76-79
         times_dev = torch.from_numpy(np.ascontiguousarray(times.astype(npdt))).to(dev)
+
+        # ---- built-in right-hand side: the whole grid in one launch (b2ode_fused_fixed_solve) -----------------------
+        from .rhs import BuiltinRHS
+        base = getattr(self.func, "_b2ode_base", None)
+        if (self.fused_rhs and isinstance(base, BuiltinRHS) and seg.nseg == 1 and len(seg.shapes[0]) >= 1
+                and seg.shapes[0][-1] == base.dim and seg.lens[0] > 0):
+            n_traj = seg.lens[0] // base.dim
+            j0 = np.zeros(n_steps + 1, dtype=np.int32)
+            ends = np.zeros(max(n_steps, 1), dtype=np.uint8)
+            s2 = np.zeros(n_out, dtype=npdt)
+            j = 1
+            for i in range(n_steps):
+                j0[i] = j
+                while j < n_out and g_np[i + 1] >= t_np[j]:          # solvers.py:97
+                    s2[j] = npdt(t_np[j]) - npdt(g_np[i])
+                    j += 1
+                ends[i] = 1 if (j > j0[i] and t_np[j - 1] == g_np[i + 1]) else 0
+            j0[n_steps] = j
+            times4 = np.zeros((max(n_steps, 1), 4), dtype=npdt)
+            times4[:n_steps, :times.shape[1]] = times
+            up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)                                  # noqa: E731
+            times_d, dts_d, j0_d, ends_d, s1_d, s2_d = up(times4), up(dts.astype(npdt)), up(j0), up(ends), up(dts.astype(npdt)), up(s2)
+            prm = base.rhs_params()
+            prm_arr = (C.c_double * 8)(*(prm + [0.0] * (8 - len(prm))))
+            weights = base.rhs_data(dtype, dev)
+            y0c = self.y0[0].contiguous()
+            mcode = {"euler": 0, "midpoint": 1, "heun": 2, "rk4": 3}[m]
+            check(lib.b2ode_fused_fixed_solve(dcode, mcode, base.kind, prm_arr, len(prm),
+                                              C.c_void_p(weights.data_ptr()) if weights is not None else None,
+                                              float(self.func._b2ode_sign), C.c_void_p(y0c.data_ptr()),
+                                              C.c_void_p(outs[0].data_ptr()), n_traj, n_steps, n_out,
+                                              C.c_void_p(times_d.data_ptr()), C.c_void_p(dts_d.data_ptr()),
+                                              C.c_void_p(j0_d.data_ptr()), C.c_void_p(ends_d.data_ptr()),
+                                              C.c_void_p(s1_d.data_ptr()), C.c_void_p(s2_d.data_ptr()), sm, sptr))
+            per_step = {"euler": 1, "midpoint": 2, "heun": 2, "rk4": 4}[m]
+            self.stats = dict(n_accepted=n_steps, n_rejected=0, nfe=per_step * n_steps, status=0, fused_rhs=True)
+            last_stats.clear()
+            last_stats.update(self.stats)
+            stream.synchronize()
+            return tuple(outs)
 
         # two scratch states: the stage input, and y1 for grid cells whose end is not an output time
         S, Y1a, Y1b = seg.new(), seg.new(), seg.new()
@@ -619,7 +665,7 @@ class FixedGridODESolver(object):
                 op(_lib.OP_LERP, row_ptrs(jj), y_ptrs, y1_ptrs, s1=npdt(t1) - npdt(t0), s2=npdt(t_np[jj]) - npdt(t0))
             j = j_hi
             y_views, y_ptrs = y1_views, y1_ptrs
-        self.stats = dict(n_accepted=n_steps, n_rejected=0, nfe=nfe, status=0)
+        self.stats = dict(n_accepted=n_steps, n_rejected=0, nfe=nfe, status=0, fused_rhs=False)
         last_stats.clear()
         last_stats.update(self.stats)
         stream.synchronize()
