@@ -131,10 +131,10 @@ def test_fused_fixed_grid_is_bit_identical_to_generic_path(method, dtype):
     assert not tfd().last_stats["fused_rhs"] and tfd().last_stats["nfe"] == nfe_a
     assert torch.equal(a, b)
     # reverse time and a finer internal grid with interpolated outputs
-    tr = torch.tensor([0.5, 0.37, 0.2, 0.0])
-    a = tfd().odeint(f, y0, tr, method=method, options=dict(step_size=0.03))
-    b = tfd().odeint(f, y0, tr, method=method, options=dict(step_size=0.03, fused_rhs=False))
-    assert torch.equal(a, b)
+    tr = torch.tensor([0.1, 0.07, 0.03, 0.0])
+    a = tfd().odeint(f, y0, tr, method=method, options=dict(step_size=0.013))
+    b = tfd().odeint(f, y0, tr, method=method, options=dict(step_size=0.013, fused_rhs=False))
+    assert bool(torch.isfinite(b).all()) and torch.equal(a, b)
 
 
 def test_cubic_mlp_builtin_fixed_and_adaptive_vs_generic():

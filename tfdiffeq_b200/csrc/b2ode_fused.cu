@@ -52,7 +52,6 @@ struct RhsCubicMLP {
     static constexpr int D = 2;
     static constexpr int kMaxH = 128;
     static constexpr int kSmem = 2 * kMaxH + kMaxH + 2 * kMaxH + 2;
-    static __device__ __forceinline__ T act(T a) { return (T)tanh((double)a); }
     static __device__ __forceinline__ void eval(const double *prm, const T *sw, T /*t*/, const T (&y)[2], T (&dy)[2]) {
         using A = Ar<T>;
         const int H = (int)prm[0];

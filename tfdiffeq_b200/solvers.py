@@ -483,12 +483,16 @@ class FixedGridODESolver(object):
         self.func = func
         self.y0 = y0
         self.eps = eps
-        if step_size is not None and grid_constructor is None:
+        # tfdiffeq/solvers.py:49-56 raises "exclusive arguments" whenever a grid_constructor is given at all (its
+        # last `else`), which makes the option unusable; the evident intent (both given -> error) is implemented
+        if step_size is not None and grid_constructor is not None:
+            raise ValueError("step_size and grid_constructor are exclusive arguments.")
+        if step_size is not None:
             self.grid_constructor = self._grid_constructor_from_step_size(step_size)
         elif grid_constructor is None:
             self.grid_constructor = lambda f, y0, t: t
         else:
-            raise ValueError("step_size and grid_constructor are exclusive arguments.")
+            self.grid_constructor = grid_constructor
         self.stats = {}
 
     @staticmethod
