@@ -219,6 +219,17 @@ int b2ode_fused_fixed_solve(int dtype, int method, int rhs_kind, const double *r
                             int n_steps, int n_out, const void *times, const void *dts, const int32_t *j0,
                             const unsigned char *ends, const void *s1, const void *s2, int sm_count, void *cuda_stream);
 
+/* ---- GEMM-backed func on tensor cores ---------------------------------------------------- */
+
+/* One dense layer of an ODENet-style func (tfdiffeq/models/dense_odenet.py:85-92) on tcgen05 / TMEM:
+ *     out[M, N] = act( A[M, K] . W[N, K]^T + bias[N] ),   fp32 storage, TF32 tensor-core math,
+ * act: 0 none, 1 relu, 2 tanh, 3 softplus.  With nk == 0, A = x.  With nk > 0 the Runge-Kutta stage combine
+ * (tfdiffeq/rk_common.py:51) is the A-operand producer: A = x + sum_j (dt * coef[j]) * k[j] with dt read from
+ * `state` (x = y0 of the step); if `ystage` is non-null the stage input is also stored there (the last stage
+ * needs it: it is y1).  W is torch's nn.Linear.weight layout.  N must be a multiple of 16. */
+int b2ode_dense_layer(const void *x, const void *const *k, const double *coef, int nk, const void *state, void *ystage,
+                      const void *W, const void *bias, void *out, int64_t M, int K, int N, int act, void *cuda_stream);
+
 /* ---- measurement hooks (bench.py) --------------------------------------------------------------------- */
 unsigned long long b2ode_launch_count(void);            /* kernels launched by this library so far          */
 int b2ode_timing_enable(unsigned family_mask);          /* CUDA-event timing per kernel family; 0 = off     */

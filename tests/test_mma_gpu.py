@@ -1,0 +1,108 @@
+"""GPU: the tcgen05 / TMEM dense layer (b2ode_dense_layer) against an fp64 product of the
+TF32-rounded operands (what the tensor core is specified to compute), with and without the fused
+Runge-Kutta stage combine as the A-operand producer."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device("cuda:0")
+
+
+def lib():
+    from tfdiffeq_b200 import _lib
+    return _lib
+
+
+def tf32_round(x):
+    """cvt.rna.tf32.f32: round the fp32 mantissa to 10 bits, nearest, ties away from zero."""
+    i = x.contiguous().view(torch.int32)
+    r = ((i.to(torch.int64) + 0x1000) & 0xFFFFE000).to(torch.int32)
+    return r.view(torch.float32)
+
+
+def run_layer(x, W, bias, act, ks=None, coefs=None, dt=None, want_ystage=False):
+    L = lib()
+    M, K = x.shape
+    N = W.shape[0]
+    out = torch.empty(M, N, dtype=torch.float32, device=DEV)
+    ystage = torch.empty_like(x) if want_ystage else None
+    state = None
+    karr, carr, nk = None, None, 0
+    if ks:
+        nk = len(ks)
+        karr = (C.c_void_p * nk)(*[k.data_ptr() for k in ks])
+        carr = (C.c_double * nk)(*coefs)
+        st = L.State()
+        st.dt = dt
+        state = torch.frombuffer(bytearray(bytes(st)), dtype=torch.uint8).to(DEV)
+    L.check(L.lib.b2ode_dense_layer(C.c_void_p(x.data_ptr()), karr, carr, nk,
+                                    C.c_void_p(state.data_ptr()) if state is not None else None,
+                                    C.c_void_p(ystage.data_ptr()) if ystage is not None else None,
+                                    C.c_void_p(W.data_ptr()), C.c_void_p(bias.data_ptr()) if bias is not None else None,
+                                    C.c_void_p(out.data_ptr()), M, K, N, act,
+                                    C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    torch.cuda.synchronize()
+    return out, ystage
+
+
+def reference(a, W, bias, act):
+    r = tf32_round(a).double() @ tf32_round(W).double().t()
+    if bias is not None:
+        r = r + bias.double()
+    if act == 1:
+        r = torch.relu(r)
+    elif act == 2:
+        r = torch.tanh(r)
+    elif act == 3:
+        r = torch.nn.functional.softplus(r)
+    return r
+
+
+@pytest.mark.parametrize("M,K,N", [(128, 64, 64), (128, 32, 16), (1000, 64, 256), (300, 100, 48), (257, 36, 16),
+                                   (512, 256, 512), (4096, 784, 256), (65, 7, 32)])
+@pytest.mark.parametrize("act", [0, 1, 2])
+def test_dense_layer_matches_tf32_reference(M, K, N, act):
+    g = torch.Generator(device="cpu").manual_seed(M * 7 + K * 3 + N)
+    x = torch.randn(M, K, generator=g).to(DEV)
+    W = (torch.randn(N, K, generator=g) / K ** 0.5).to(DEV)
+    b = torch.randn(N, generator=g).to(DEV)
+    out, _ = run_layer(x, W, b, act)
+    ref = reference(x, W, b, act)
+    err = float((out.double() - ref).abs().max())
+    scale = max(1.0, float(ref.abs().max()))
+    assert err <= 2e-5 * scale, (M, K, N, act, err)
+
+
+def test_dense_layer_with_fused_stage_combine():
+    """A = y0 + sum_j (dt*beta_j) k_j built in the kernel (same fp32 operation order as k_rk_stage), then the GEMM."""
+    g = torch.Generator(device="cpu").manual_seed(5)
+    M, K, N = 777, 64, 128
+    y0 = torch.randn(M, K, generator=g).to(DEV)
+    ks = [torch.randn(M, K, generator=g).to(DEV) for _ in range(4)]
+    coefs = [19372 / 6561, -25360 / 2187, 64448 / 6561, -212 / 729]
+    dt = 0.0371
+    W = (torch.randn(N, K, generator=g) / 8).to(DEV)
+    b = torch.randn(N, generator=g).to(DEV)
+    out, ystage = run_layer(y0, W, b, 1, ks=ks, coefs=coefs, dt=dt, want_ystage=True)
+    dt32 = torch.tensor(dt, dtype=torch.float32)
+    acc = None
+    for c, k in zip(coefs, ks):
+        term = (dt32 * torch.tensor(c, dtype=torch.float32)).item() * k          # (dt*beta) in fp32, then * k
+        acc = term if acc is None else acc + term
+    a = y0 + acc
+    assert torch.equal(ystage, a)                                                # bit-identical stage input
+    ref = reference(a, W, b, 1)
+    assert float((out.double() - ref).abs().max()) <= 2e-5 * max(1.0, float(ref.abs().max()))
+
+
+def test_dense_layer_argument_checks():
+    L = lib()
+    x = torch.zeros(4, 8, device=DEV)
+    W = torch.zeros(10, 8, device=DEV)
+    out = torch.zeros(4, 10, device=DEV)
+    rc = L.lib.b2ode_dense_layer(C.c_void_p(x.data_ptr()), None, None, 0, None, None, C.c_void_p(W.data_ptr()), None,
+                                 C.c_void_p(out.data_ptr()), 4, 8, 10, 0, None)
+    assert rc == -1 and b"multiple of 16" in L.lib.b2ode_last_error()

@@ -1,0 +1,309 @@
+// b2ode_mma.cu -- the GEMM-shaped part of the path: a dense layer of an ODENet-style func on tcgen05.
+//
+// SURVEY.md 8(f)-3 / north_star: "tensor cores used only when func is the ODENet linear block (a genuine dense
+// GEMM)".  The reference's ODEFunc is fc1 -> relu -> fc2 -> relu -> fc3 (tfdiffeq/models/dense_odenet.py:85-92).
+// One kernel computes   out[M, N] = act( A[M, K] . W[N, K]^T + bias[N] )   with fp32 storage and TF32 tensor-core
+// math (TensorFlow's own default for fp32 matmuls on Ampere and later), where A is either a plain activation
+// matrix or -- for the first layer -- the Runge-Kutta stage input produced on the fly,
+//     A = y0 + sum_j (dt * beta_j) * k_j          (tfdiffeq/rk_common.py:51, dt read from the device state),
+// i.e. the stage combine is the A-operand producer and the stage input never round-trips HBM for the GEMM.
+//
+// Blackwell mapping: one CTA (128 threads) per 128-row tile; operands are written by the threads themselves into
+// the canonical K-major SWIZZLE_128B shared-memory layout (they are computed, not copied, so there is nothing
+// for TMA to fetch); tcgen05.mma.kind::tf32 (M = 128, N <= 256, K = 8 per instruction) is issued by one
+// thread with the accumulator in TMEM; tcgen05.commit -> mbarrier tells the CTA when shared memory may be
+// refilled / the accumulator read; the epilogue reads TMEM with tcgen05.ld (one accumulator row per thread), adds
+// the bias, applies the activation and stores fp32 rows.
+
+#include "b2ode_dev.cuh"
+
+#include <stdint.h>
+
+constexpr int kMmaThreads = 128;
+constexpr int kTileM = 128;
+constexpr int kKChunk = 64;              // K elements staged per round: 2 swizzle blocks of 32 tf32 (128 bytes)
+constexpr int kMaxNK = 8;
+
+struct DenseParams {
+    const float *x;                      // A (nk == 0) or y0 (nk > 0), row-major [M, K]
+    const float *k[kMaxNK];              // stage derivatives, row-major [M, K]
+    double coef[kMaxNK];                 // beta_j of the stage row (zeros already dropped)
+    int nk;
+    const b2ode_state *st;               // dt lives here when nk > 0
+    float *ystage;                       // optional: also materialise the stage input (needed for the last stage)
+    const float *W;                      // [N, K] row-major (torch nn.Linear.weight): K-major "B" operand
+    const float *bias;                   // [N] or null
+    float *out;                          // [M, N]
+    int M, K, N;
+    int act;                             // 0 none, 1 relu, 2 tanh, 3 softplus
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+
+// byte offset of (row, 16-byte chunk c in 0..7) inside one [rows x 128 B] K-major SWIZZLE_128B block:
+// 8-row atoms of 1024 B, the chunk index XOR-ed with the row inside the atom (Swizzle<3,4,3>)
+__device__ __forceinline__ uint32_t sw128_offset(int row, int chunk) {
+    return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((chunk ^ (row & 7)) << 4));
+}
+
+// shared-memory matrix descriptor, K-major, SWIZZLE_128B, dense 8-row atoms (SBO = 1024 B), sm_100 version bit
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);            // start address  [0,14)
+    d |= (uint64_t)1 << 16;                               // leading byte offset (unused for swizzled K-major) [16,30)
+    d |= (uint64_t)(1024 >> 4) << 32;                     // stride byte offset [32,46)
+    d |= (uint64_t)1 << 46;                               // descriptor version (Blackwell)  [46,48)
+    d |= (uint64_t)2 << 61;                               // SWIZZLE_128B  [61,64)
+    return d;
+}
+
+__device__ __forceinline__ uint32_t make_idesc_tf32(int N) {
+    uint32_t d = 0;
+    d |= 1u << 4;                                         // D format F32
+    d |= 2u << 7;                                         // A format TF32
+    d |= 2u << 10;                                        // B format TF32
+    d |= (uint32_t)(N >> 3) << 17;                        // N
+    d |= (uint32_t)(kTileM >> 4) << 24;                   // M = 128
+    return d;                                             // A, B K-major; no negate; dense
+}
+
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+    if (act == 1) return v > 0.f ? v : 0.f;
+    if (act == 2) return tanhf(v);
+    if (act == 3) return (v > 20.f) ? v : log1pf(expf(v));
+    return v;
+}
+
+__global__ void __launch_bounds__(kMmaThreads, 1) k_dense_layer_tf32(const __grid_constant__ DenseParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    // 1024-byte alignment for the swizzle atoms
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t *sA = smem;                                   // 2 blocks x [128 rows x 128 B]          = 32 KB
+    uint8_t *sB = smem + 2 * kTileM * 128;                // 2 blocks x [256 rows x 128 B] (max)    = 64 KB
+    __shared__ __align__(8) uint64_t mbar;
+    __shared__ uint32_t tmem_slot;
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int m0 = blockIdx.x * kTileM;
+    const int NT_max = p.N < 256 ? p.N : 256;
+    uint32_t ncols = 32;
+    while ((int)ncols < NT_max) ncols <<= 1;
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(ncols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)));
+        asm volatile("fence.mbarrier_init.release.cluster;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const uint32_t tmem_base = tmem_slot;
+    uint32_t phase = 0;
+
+    float cf[kMaxNK];
+    if (p.nk > 0) {
+        const float dt = (float)p.st->dt;
+#pragma unroll
+        for (int j = 0; j < kMaxNK; ++j) cf[j] = (j < p.nk) ? __fmul_rn(dt, (float)p.coef[j]) : 0.f;
+    }
+
+    for (int n0 = 0; n0 < p.N; n0 += 256) {
+        const int NT = (p.N - n0) < 256 ? (p.N - n0) : 256;
+        const uint32_t idesc = make_idesc_tf32(NT);
+        for (int kc = 0; kc < p.K; kc += kKChunk) {
+            // ---- produce the A chunk: 128 rows x 64 columns, as float4 (16-byte) pieces ------------------------
+            for (int f = tid; f < kTileM * (kKChunk / 4); f += kMmaThreads) {
+                const int row = f / (kKChunk / 4), c4 = f % (kKChunk / 4);
+                const int gm = m0 + row, gk = kc + c4 * 4;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (gm < p.M && gk < p.K) {
+                    const size_t off = (size_t)gm * p.K + gk;
+                    if (gk + 3 < p.K && ((p.K & 3) == 0)) {
+                        v = *reinterpret_cast<const float4 *>(p.x + off);
+                        if (p.nk > 0) {
+                            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                            for (int j = 0; j < kMaxNK; ++j) {
+                                if (j < p.nk) {
+                                    const float4 kv = *reinterpret_cast<const float4 *>(p.k[j] + off);
+                                    const float tx = __fmul_rn(cf[j], kv.x), ty = __fmul_rn(cf[j], kv.y);
+                                    const float tz = __fmul_rn(cf[j], kv.z), tw = __fmul_rn(cf[j], kv.w);
+                                    acc.x = j ? __fadd_rn(acc.x, tx) : tx;
+                                    acc.y = j ? __fadd_rn(acc.y, ty) : ty;
+                                    acc.z = j ? __fadd_rn(acc.z, tz) : tz;
+                                    acc.w = j ? __fadd_rn(acc.w, tw) : tw;
+                                }
+                            }
+                            v.x = __fadd_rn(v.x, acc.x);
+                            v.y = __fadd_rn(v.y, acc.y);
+                            v.z = __fadd_rn(v.z, acc.z);
+                            v.w = __fadd_rn(v.w, acc.w);
+                            if (p.ystage && n0 == 0) *reinterpret_cast<float4 *>(p.ystage + off) = v;
+                        }
+                    } else {
+                        float e[4] = {0.f, 0.f, 0.f, 0.f};
+                        for (int q = 0; q < 4 && gk + q < p.K; ++q) {
+                            float a = p.x[off + q];
+                            if (p.nk > 0) {
+                                float acc = 0.f;
+                                for (int j = 0; j < p.nk; ++j) {
+                                    const float t = __fmul_rn(cf[j], p.k[j][off + q]);
+                                    acc = j ? __fadd_rn(acc, t) : t;
+                                }
+                                a = __fadd_rn(a, acc);
+                                if (p.ystage && n0 == 0) p.ystage[off + q] = a;
+                            }
+                            e[q] = a;
+                        }
+                        v = make_float4(e[0], e[1], e[2], e[3]);
+                    }
+                }
+                uint4 t = make_uint4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+                const int kb = c4 >> 3, chunk = c4 & 7;
+                *reinterpret_cast<uint4 *>(sA + kb * (kTileM * 128) + sw128_offset(row, chunk)) = t;
+            }
+            // ---- produce the B chunk: NT rows (output features) x 64 columns of W[N, K] --------------------------
+            for (int f = tid; f < NT * (kKChunk / 4); f += kMmaThreads) {
+                const int row = f / (kKChunk / 4), c4 = f % (kKChunk / 4);
+                const int gn = n0 + row, gk = kc + c4 * 4;
+                float e[4] = {0.f, 0.f, 0.f, 0.f};
+                if (gk < p.K) {
+                    const size_t off = (size_t)gn * p.K + gk;
+                    if (gk + 3 < p.K && ((p.K & 3) == 0)) {
+                        const float4 w = *reinterpret_cast<const float4 *>(p.W + off);
+                        e[0] = w.x; e[1] = w.y; e[2] = w.z; e[3] = w.w;
+                    } else {
+                        for (int q = 0; q < 4 && gk + q < p.K; ++q) e[q] = p.W[off + q];
+                    }
+                }
+                uint4 t = make_uint4(to_tf32(e[0]), to_tf32(e[1]), to_tf32(e[2]), to_tf32(e[3]));
+                const int kb = c4 >> 3, chunk = c4 & 7;
+                *reinterpret_cast<uint4 *>(sB + kb * (256 * 128) + sw128_offset(row, chunk)) = t;
+            }
+            // make the generic-proxy writes visible to the tensor core (async proxy), then hand over
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;");
+            __syncthreads();
+            if (tid == 0) {
+                asm volatile("tcgen05.fence::after_thread_sync;");
+#pragma unroll
+                for (int kb = 0; kb < 2; ++kb) {
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {
+                        const uint64_t da = make_desc(smem_u32(sA + kb * (kTileM * 128)) + ks * 32);
+                        const uint64_t db = make_desc(smem_u32(sB + kb * (256 * 128)) + ks * 32);
+                        const uint32_t accum = (kc > 0 || kb > 0 || ks > 0) ? 1u : 0u;
+                        asm volatile(
+                            "{\n\t.reg .pred p;\n\t"
+                            "setp.ne.b32 p, %4, 0;\n\t"
+                            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                            ::"r"(tmem_base), "l"(da), "l"(db), "r"(idesc), "r"(accum)
+                            : "memory");
+                    }
+                }
+                // arrives on the mbarrier once every MMA issued so far has finished reading shared memory / writing TMEM
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mbar))
+                             : "memory");
+            }
+            mbar_wait(smem_u32(&mbar), phase);
+            phase ^= 1u;
+        }
+        // ---- epilogue: one accumulator row per thread (TMEM lane = row), 32 columns at a time -----------------------
+        asm volatile("tcgen05.fence::after_thread_sync;");
+        const int gm = m0 + tid;
+        for (int c0 = 0; c0 < NT; c0 += 32) {
+            uint32_t r[32];
+            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                  "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+                  "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+                  "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (gm < p.M) {
+                float *dst = p.out + (size_t)gm * p.N + n0 + c0;
+#pragma unroll
+                for (int q = 0; q < 32; ++q) {
+                    if (c0 + q < NT) {
+                        float v = __uint_as_float(r[q]);
+                        if (p.bias) v += p.bias[n0 + c0 + q];
+                        dst[q] = apply_act(v, p.act);
+                    }
+                }
+            }
+        }
+        // the accumulator columns are reused by the next N tile
+        asm volatile("tcgen05.fence::before_thread_sync;");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;");
+    }
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols));
+}
+
+// ================================================================================================
+// host side
+// ================================================================================================
+extern "C" int b2ode_dense_layer(const void *x, const void *const *k, const double *coef, int nk, const void *state,
+                                 void *ystage, const void *W, const void *bias, void *out, int64_t M, int K, int N, int act,
+                                 void *cuda_stream) {
+    if (!x || !W || !out || M < 1 || K < 1 || N < 1) return b2_fail(B2ODE_EINVAL, "bad dense-layer arguments");
+    if (N % 16 != 0) return b2_fail(B2ODE_EINVAL, "dense layer: N must be a multiple of 16 (got %d)", N);
+    if (nk < 0 || nk > kMaxNK || (nk > 0 && (!k || !coef || !state))) return b2_fail(B2ODE_EINVAL, "bad stage-combine arguments");
+    if (act < 0 || act > 3) return b2_fail(B2ODE_EINVAL, "unknown activation %d", act);
+    if (M > (int64_t)2147483647 - kTileM) return b2_fail(B2ODE_EINVAL, "M too large");
+    DenseParams p;
+    memset(&p, 0, sizeof(p));
+    p.x = (const float *)x;
+    for (int j = 0; j < nk; ++j) {
+        if (!k[j]) return b2_fail(B2ODE_EINVAL, "k[%d] is null", j);
+        p.k[j] = (const float *)k[j];
+        p.coef[j] = coef[j];
+    }
+    p.nk = nk;
+    p.st = (const b2ode_state *)state;
+    p.ystage = (float *)ystage;
+    p.W = (const float *)W;
+    p.bias = (const float *)bias;
+    p.out = (float *)out;
+    p.M = (int)M;
+    p.K = K;
+    p.N = N;
+    p.act = act;
+    const size_t smem = 2 * kTileM * 128 + 2 * 256 * 128 + 1024;      // A + B + alignment slack = 99 328 B
+    static bool configured = false;
+    if (!configured) {
+        B2_CUDA(cudaFuncSetAttribute(k_dense_layer_tf32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    const int grid = (int)((M + kTileM - 1) / kTileM);
+    k_dense_layer_tf32<<<grid, kMmaThreads, smem, (cudaStream_t)cuda_stream>>>(p);
+    B2_CUDA(cudaGetLastError());
+    b2_count_launch();
+    return 0;
+}
