@@ -227,6 +227,9 @@ int b2ode_fused_fixed_solve(int dtype, int method, int rhs_kind, const double *r
  * (tfdiffeq/rk_common.py:51) is the A-operand producer: A = x + sum_j (dt * coef[j]) * k[j] with dt read from
  * `state` (x = y0 of the step); if `ystage` is non-null the stage input is also stored there (the last stage
  * needs it: it is y1).  W is torch's nn.Linear.weight layout.  N must be a multiple of 16. */
+/* Registers k_i with the solver without launching the stage kernel (the combine then happens inside
+ * b2ode_dense_layer as the A-operand producer). */
+int b2ode_set_k(b2ode_solver *s, int i, const void *const *k_new);
 int b2ode_dense_layer(const void *x, const void *const *k, const double *coef, int nk, const void *state, void *ystage,
                       const void *W, const void *bias, void *out, int64_t M, int K, int N, int act, void *cuda_stream);
 

@@ -1069,6 +1069,18 @@ static int dispatch_stage(b2ode_solver *s, int row) {
     return b2_fail(B2ODE_EINVAL, "unsupported number of stage terms %d", s->st_nk[row]);
 }
 
+// Register k_i (the output of the func call that followed stage i-1) WITHOUT launching the stage kernel: used when
+// the stage combine runs as the A-operand producer of a tensor-core dense layer (b2ode_dense_layer) instead.
+extern "C" int b2ode_set_k(b2ode_solver *s, int i, const void *const *k_new) {
+    B2_REQUIRE_BOUND(s);
+    if (i < 1 || i > s->d.n_k - 1 || !k_new) return b2_fail(B2ODE_EINVAL, "bad b2ode_set_k arguments");
+    for (int sg = 0; sg < s->d.nseg; ++sg) {
+        if (!k_new[sg] && s->d.seg_len[sg] > 0) return b2_fail(B2ODE_EINVAL, "k_new[%d] is null", sg);
+        s->k[i][sg] = k_new[sg];
+    }
+    return 0;
+}
+
 extern "C" int b2ode_rk_stage(b2ode_solver *s, int i, const void *const *k_new) {
     B2_REQUIRE_BOUND(s);
     const int nk = s->d.n_k;

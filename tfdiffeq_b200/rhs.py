@@ -86,3 +86,77 @@ class CubicMLP(BuiltinRHS):
     def forward(self, t, y):
         u = y ** 3 if self.cube else y
         return torch.tanh(u @ self.W1 + self.b1) @ self.W2 + self.b2
+
+
+_ACT = {None: 0, "none": 0, "relu": 1, "tanh": 2, "softplus": 3}
+
+
+def dense_layer(x, weight, bias, act="none", stage=None):
+    """``act(x @ weight.T + bias)`` on the tcgen05 tensor cores (fp32 storage, TF32 math): ``b2ode_dense_layer``.
+
+    ``stage = (k_tensors, coefs, state_ptr, ystage_or_None)`` makes the Runge-Kutta stage combine the A-operand
+    producer: A = x + sum_j (dt * coefs[j]) * k_tensors[j], dt read from the device state."""
+    import ctypes as C
+    M, K = x.shape
+    N = weight.shape[0]
+    out = torch.empty((M, N), dtype=torch.float32, device=x.device)
+    karr = carr = state = ys = None
+    nk = 0
+    if stage is not None:
+        ks, coefs, state, ys = stage
+        nk = len(ks)
+        karr = (C.c_void_p * nk)(*[k.data_ptr() for k in ks])
+        carr = (C.c_double * nk)(*coefs)
+    _lib.check(_lib.lib.b2ode_dense_layer(
+        C.c_void_p(x.data_ptr()), karr, carr, nk, C.c_void_p(state) if state else None,
+        C.c_void_p(ys.data_ptr()) if ys is not None else None, C.c_void_p(weight.data_ptr()),
+        C.c_void_p(bias.data_ptr()) if bias is not None else None, C.c_void_p(out.data_ptr()), M, K, N, _ACT[act],
+        C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)))
+    return out
+
+
+class DenseMLP(nn.Module):
+    """The reference's ``ODEFunc`` (tfdiffeq/models/dense_odenet.py:11-92, time-independent form): fc1 -> act ->
+    fc2 -> act -> fc3 on a ``(batch, dim)`` state, counting ``nfe`` like the reference does (:78).
+
+    Under ``torch.no_grad()`` on a CUDA fp32 state -- which is how ``odeint`` evaluates ``func`` -- the three
+    layers run on the tcgen05 tensor cores (TF32 math, TensorFlow's default for fp32 matmuls on Ampere+), and the
+    adaptive solvers feed the first layer straight from the stage combine (the stage input never round-trips
+    HBM for the GEMM).  With autograd enabled (training, ``odeint_adjoint``'s VJPs) it is plain torch.
+    ``tensor_cores=False`` forces plain torch everywhere."""
+
+    def __init__(self, dim, hidden, non_linearity="relu", tensor_cores=True, dtype=torch.float32):
+        super(DenseMLP, self).__init__()
+        if non_linearity not in ("relu", "tanh", "softplus"):
+            raise ValueError("non_linearity must be relu, tanh or softplus")
+        self.dim, self.hidden, self.non_linearity, self.tensor_cores = int(dim), int(hidden), non_linearity, tensor_cores
+        self.fc1 = nn.Linear(dim, hidden, dtype=dtype)
+        self.fc2 = nn.Linear(hidden, hidden, dtype=dtype)
+        self.fc3 = nn.Linear(hidden, dim, dtype=dtype)
+        self.nfe = 0
+
+    def uses_tensor_cores(self, x):
+        return (self.tensor_cores and x.is_cuda and x.dtype == torch.float32 and not torch.is_grad_enabled()
+                and self.fc1.weight.dtype == torch.float32 and self.dim % 16 == 0 and self.hidden % 16 == 0
+                and x.shape[-1] == self.dim)
+
+    def _tail(self, h1):
+        h2 = dense_layer(h1, self.fc2.weight, self.fc2.bias, self.non_linearity)
+        return dense_layer(h2, self.fc3.weight, self.fc3.bias, "none")
+
+    def forward_from_stage(self, y0, ks, coefs, state_ptr, ystage):
+        """First layer fed by the stage combine of y0 and the k's (all ``(batch, dim)`` fp32 CUDA tensors)."""
+        self.nfe += 1
+        h1 = dense_layer(y0, self.fc1.weight, self.fc1.bias, self.non_linearity, stage=(ks, coefs, state_ptr, ystage))
+        return self._tail(h1)
+
+    def forward(self, t, x):
+        self.nfe += 1
+        if self.uses_tensor_cores(x):
+            x2 = x.reshape(-1, self.dim)
+            if not x2.is_contiguous():
+                x2 = x2.contiguous()
+            h1 = dense_layer(x2, self.fc1.weight, self.fc1.bias, self.non_linearity)
+            return self._tail(h1).reshape(x.shape)
+        act = {"relu": torch.relu, "tanh": torch.tanh, "softplus": torch.nn.functional.softplus}[self.non_linearity]
+        return self.fc3(act(self.fc2(act(self.fc1(x)))))

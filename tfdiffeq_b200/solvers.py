@@ -337,6 +337,17 @@ class AdaptiveStepsizeODESolver(object):
             func = self.func
             rk_stage, rk_finalize, poll_async = lib.b2ode_rk_stage, lib.b2ode_rk_finalize, lib.b2ode_poll_async
 
+            # tensor-core func (rhs.DenseMLP): the stage combine becomes the A-operand producer of its first layer
+            from .rhs import DenseMLP
+            dense = getattr(self.func, "_b2ode_base", None)
+            if not (self.fused_rhs and isinstance(dense, DenseMLP) and seg.nseg == 1 and len(seg.shapes[0]) == 2 and tab.fsal
+                    and getattr(self.func, "_b2ode_sign", 1.0) > 0 and dense.uses_tensor_cores(s_views[0])):
+                dense = None
+            if dense is not None:
+                f0_view = seg.views(F0)[0]
+                rows = [[(j, b) for j, b in enumerate(tab.beta[i]) if b != 0.0] for i in range(nk - 1)]
+                state_ptr = state_dev.data_ptr()
+
             def run_attempt():
                 """Enqueue one attempt: stage i -> func -> ... -> finalize (+ dense output).  No kernel argument
                 depends on dt / accept / the output cursor: they live in the device state."""
@@ -346,6 +357,16 @@ class AdaptiveStepsizeODESolver(object):
                 k = fo.collect(func(tstage_views[0], s_views), live)
                 ks.append(k)
                 for i in range(1, nk - 1):
+                    if dense is not None and rows[i]:
+                        # no stage kernel: y_i is formed inside the first GEMM's producer; only the last stage
+                        # input (= y1, read by finalize / the dense output / the next commit) is also stored
+                        check(lib.b2ode_set_k(handle, i, fo.pointers(k)))
+                        kt = [f0_view if j == 0 else ks[j - 1][0] for j, _ in rows[i]]
+                        out = dense.forward_from_stage(y0_views[0], kt, [b for _, b in rows[i]], state_ptr,
+                                                       s_views[0] if i == nk - 2 else None)
+                        k = fo.collect((out,), live)
+                        ks.append(k)
+                        continue
                     check(rk_stage(handle, i, fo.pointers(k)))
                     k = fo.collect(func(tstage_views[i], s_views), live)
                     ks.append(k)
