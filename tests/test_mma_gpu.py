@@ -41,7 +41,7 @@ def run_layer(x, W, bias, act, ks=None, coefs=None, dt=None, want_ystage=False):
     L.check(L.lib.b2ode_dense_layer(C.c_void_p(x.data_ptr()), karr, carr, nk,
                                     C.c_void_p(state.data_ptr()) if state is not None else None,
                                     C.c_void_p(ystage.data_ptr()) if ystage is not None else None,
-                                    C.c_void_p(W.data_ptr()), C.c_void_p(bias.data_ptr()) if bias is not None else None,
+                                    C.c_void_p(tf32_round(W).data_ptr()), C.c_void_p(bias.data_ptr()) if bias is not None else None,
                                     C.c_void_p(out.data_ptr()), M, K, N, act,
                                     C.c_void_p(torch.cuda.current_stream().cuda_stream)))
     torch.cuda.synchronize()

@@ -31,7 +31,7 @@ struct DenseParams {
     int nk;
     const b2ode_state *st;               // dt lives here when nk > 0
     float *ystage;                       // optional: also materialise the stage input (needed for the last stage)
-    const float *W;                      // [N, K] row-major (torch nn.Linear.weight): K-major "B" operand
+    const float *W;                      // [N, K] row-major (torch nn.Linear.weight layout), values already rounded to TF32
     const float *bias;                   // [N] or null
     float *out;                          // [M, N]
     int M, K, N;
@@ -93,7 +93,7 @@ __device__ __forceinline__ float apply_act(float v, int act) {
     return v;
 }
 
-__global__ void __launch_bounds__(kMmaThreads, 1) k_dense_layer_tf32(const __grid_constant__ DenseParams p) {
+__global__ void __launch_bounds__(kMmaThreads, 2) k_dense_layer_tf32(const __grid_constant__ DenseParams p) {
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment for the swizzle atoms
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -133,75 +133,107 @@ __global__ void __launch_bounds__(kMmaThreads, 1) k_dense_layer_tf32(const __gri
         const int NT = (p.N - n0) < 256 ? (p.N - n0) : 256;
         const uint32_t idesc = make_idesc_tf32(NT);
         for (int kc = 0; kc < p.K; kc += kKChunk) {
-            // ---- produce the A chunk: 128 rows x 64 columns, as float4 (16-byte) pieces ------------------------
-            for (int f = tid; f < kTileM * (kKChunk / 4); f += kMmaThreads) {
-                const int row = f / (kKChunk / 4), c4 = f % (kKChunk / 4);
-                const int gm = m0 + row, gk = kc + c4 * 4;
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (gm < p.M && gk < p.K) {
-                    const size_t off = (size_t)gm * p.K + gk;
-                    if (gk + 3 < p.K && ((p.K & 3) == 0)) {
-                        v = *reinterpret_cast<const float4 *>(p.x + off);
-                        if (p.nk > 0) {
-                            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            const bool vec_ok = (p.K & 3) == 0;
+            // ---- B chunk first: NT rows (output features) x 64 columns of W[N, K], already TF32-rounded by the host:
+            //      raw 16-byte async copies straight into the swizzled layout (no register staging), zero-filled past K
+            if (vec_ok) {
+                for (int f = tid; f < NT * (kKChunk / 4); f += kMmaThreads) {
+                    const int row = f / (kKChunk / 4), c4 = f % (kKChunk / 4);
+                    const int gk = kc + c4 * 4;
+                    const float *src = p.W + (size_t)(n0 + row) * p.K + (gk < p.K ? gk : 0);
+                    const uint32_t dst = smem_u32(sB + (c4 >> 3) * (256 * 128) + sw128_offset(row, c4 & 7));
+                    const int nbytes = gk < p.K ? 16 : 0;
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
+                }
+            } else {
+                for (int f = tid; f < NT * (kKChunk / 4); f += kMmaThreads) {
+                    const int row = f / (kKChunk / 4), c4 = f % (kKChunk / 4);
+                    const int gk = kc + c4 * 4;
+                    uint32_t e[4] = {0u, 0u, 0u, 0u};
+                    for (int q = 0; q < 4 && gk + q < p.K; ++q) e[q] = __float_as_uint(p.W[(size_t)(n0 + row) * p.K + gk + q]);
+                    *reinterpret_cast<uint4 *>(sB + (c4 >> 3) * (256 * 128) + sw128_offset(row, c4 & 7)) = make_uint4(e[0], e[1], e[2], e[3]);
+                }
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            // ---- A chunk: 128 rows x 64 columns = 16 float4 per thread, in 4 batches of 4 so that 4 x (1 + nk) independent
+            //      16-byte loads are in flight per thread before anything is consumed
+            if (vec_ok) {
+#pragma unroll 1
+                for (int bt = 0; bt < 4; ++bt) {
+                    float4 v[4];
+                    size_t off[4];
+                    bool in[4];
 #pragma unroll
-                            for (int j = 0; j < kMaxNK; ++j) {
-                                if (j < p.nk) {
-                                    const float4 kv = *reinterpret_cast<const float4 *>(p.k[j] + off);
-                                    const float tx = __fmul_rn(cf[j], kv.x), ty = __fmul_rn(cf[j], kv.y);
-                                    const float tz = __fmul_rn(cf[j], kv.z), tw = __fmul_rn(cf[j], kv.w);
-                                    acc.x = j ? __fadd_rn(acc.x, tx) : tx;
-                                    acc.y = j ? __fadd_rn(acc.y, ty) : ty;
-                                    acc.z = j ? __fadd_rn(acc.z, tz) : tz;
-                                    acc.w = j ? __fadd_rn(acc.w, tw) : tw;
-                                }
+                    for (int q = 0; q < 4; ++q) {
+                        const int f = tid + (bt * 4 + q) * kMmaThreads;
+                        const int row = f / (kKChunk / 4), c4 = f % (kKChunk / 4);
+                        const int gm = m0 + row, gk = kc + c4 * 4;
+                        in[q] = gm < p.M && gk < p.K;
+                        off[q] = in[q] ? (size_t)gm * p.K + gk : 0;
+                        v[q] = in[q] ? *reinterpret_cast<const float4 *>(p.x + off[q]) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                    if (p.nk > 0) {
+                        float4 acc[4];
+#pragma unroll 1
+                        for (int j = 0; j < p.nk; ++j) {
+                            float4 kv[4];
+#pragma unroll
+                            for (int q = 0; q < 4; ++q)
+                                kv[q] = in[q] ? *reinterpret_cast<const float4 *>(p.k[j] + off[q]) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            const float c = cf[j];
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const float tx = __fmul_rn(c, kv[q].x), ty = __fmul_rn(c, kv[q].y);
+                                const float tz = __fmul_rn(c, kv[q].z), tw = __fmul_rn(c, kv[q].w);
+                                acc[q].x = j ? __fadd_rn(acc[q].x, tx) : tx;
+                                acc[q].y = j ? __fadd_rn(acc[q].y, ty) : ty;
+                                acc[q].z = j ? __fadd_rn(acc[q].z, tz) : tz;
+                                acc[q].w = j ? __fadd_rn(acc[q].w, tw) : tw;
                             }
-                            v.x = __fadd_rn(v.x, acc.x);
-                            v.y = __fadd_rn(v.y, acc.y);
-                            v.z = __fadd_rn(v.z, acc.z);
-                            v.w = __fadd_rn(v.w, acc.w);
-                            if (p.ystage && n0 == 0) *reinterpret_cast<float4 *>(p.ystage + off) = v;
                         }
-                    } else {
-                        float e[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            v[q].x = __fadd_rn(v[q].x, acc[q].x);
+                            v[q].y = __fadd_rn(v[q].y, acc[q].y);
+                            v[q].z = __fadd_rn(v[q].z, acc[q].z);
+                            v[q].w = __fadd_rn(v[q].w, acc[q].w);
+                            if (p.ystage && n0 == 0 && in[q]) *reinterpret_cast<float4 *>(p.ystage + off[q]) = v[q];
+                        }
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int f = tid + (bt * 4 + q) * kMmaThreads;
+                        const int row = f / (kKChunk / 4), c4 = f % (kKChunk / 4);
+                        const uint4 t = make_uint4(to_tf32(v[q].x), to_tf32(v[q].y), to_tf32(v[q].z), to_tf32(v[q].w));
+                        *reinterpret_cast<uint4 *>(sA + (c4 >> 3) * (kTileM * 128) + sw128_offset(row, c4 & 7)) = t;
+                    }
+                }
+            } else {
+                for (int f = tid; f < kTileM * (kKChunk / 4); f += kMmaThreads) {
+                    const int row = f / (kKChunk / 4), c4 = f % (kKChunk / 4);
+                    const int gm = m0 + row, gk = kc + c4 * 4;
+                    float e[4] = {0.f, 0.f, 0.f, 0.f};
+                    if (gm < p.M) {
                         for (int q = 0; q < 4 && gk + q < p.K; ++q) {
-                            float a = p.x[off + q];
+                            const size_t off = (size_t)gm * p.K + gk + q;
+                            float a = p.x[off];
                             if (p.nk > 0) {
                                 float acc = 0.f;
                                 for (int j = 0; j < p.nk; ++j) {
-                                    const float t = __fmul_rn(cf[j], p.k[j][off + q]);
+                                    const float t = __fmul_rn(cf[j], p.k[j][off]);
                                     acc = j ? __fadd_rn(acc, t) : t;
                                 }
                                 a = __fadd_rn(a, acc);
-                                if (p.ystage && n0 == 0) p.ystage[off + q] = a;
+                                if (p.ystage && n0 == 0) p.ystage[off] = a;
                             }
                             e[q] = a;
                         }
-                        v = make_float4(e[0], e[1], e[2], e[3]);
                     }
+                    const uint4 t = make_uint4(to_tf32(e[0]), to_tf32(e[1]), to_tf32(e[2]), to_tf32(e[3]));
+                    *reinterpret_cast<uint4 *>(sA + (c4 >> 3) * (kTileM * 128) + sw128_offset(row, c4 & 7)) = t;
                 }
-                uint4 t = make_uint4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
-                const int kb = c4 >> 3, chunk = c4 & 7;
-                *reinterpret_cast<uint4 *>(sA + kb * (kTileM * 128) + sw128_offset(row, chunk)) = t;
             }
-            // ---- produce the B chunk: NT rows (output features) x 64 columns of W[N, K] --------------------------
-            for (int f = tid; f < NT * (kKChunk / 4); f += kMmaThreads) {
-                const int row = f / (kKChunk / 4), c4 = f % (kKChunk / 4);
-                const int gn = n0 + row, gk = kc + c4 * 4;
-                float e[4] = {0.f, 0.f, 0.f, 0.f};
-                if (gk < p.K) {
-                    const size_t off = (size_t)gn * p.K + gk;
-                    if (gk + 3 < p.K && ((p.K & 3) == 0)) {
-                        const float4 w = *reinterpret_cast<const float4 *>(p.W + off);
-                        e[0] = w.x; e[1] = w.y; e[2] = w.z; e[3] = w.w;
-                    } else {
-                        for (int q = 0; q < 4 && gk + q < p.K; ++q) e[q] = p.W[off + q];
-                    }
-                }
-                uint4 t = make_uint4(to_tf32(e[0]), to_tf32(e[1]), to_tf32(e[2]), to_tf32(e[3]));
-                const int kb = c4 >> 3, chunk = c4 & 7;
-                *reinterpret_cast<uint4 *>(sB + kb * (256 * 128) + sw128_offset(row, chunk)) = t;
-            }
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
             // make the generic-proxy writes visible to the tensor core (async proxy), then hand over
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;");
@@ -248,12 +280,22 @@ __global__ void __launch_bounds__(kMmaThreads, 1) k_dense_layer_tf32(const __gri
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             if (gm < p.M) {
                 float *dst = p.out + (size_t)gm * p.N + n0 + c0;
+                const bool full = (c0 + 32 <= NT) && ((p.N & 3) == 0);
 #pragma unroll
-                for (int q = 0; q < 32; ++q) {
-                    if (c0 + q < NT) {
-                        float v = __uint_as_float(r[q]);
-                        if (p.bias) v += p.bias[n0 + c0 + q];
-                        dst[q] = apply_act(v, p.act);
+                for (int q = 0; q < 32; q += 4) {
+                    float o[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        float v = __uint_as_float(r[q + u]);
+                        if (p.bias && c0 + q + u < NT) v += p.bias[n0 + c0 + q + u];
+                        o[u] = apply_act(v, p.act);
+                    }
+                    if (full) {
+                        *reinterpret_cast<float4 *>(dst + q) = make_float4(o[0], o[1], o[2], o[3]);
+                    } else {
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            if (c0 + q + u < NT) dst[q + u] = o[u];
                     }
                 }
             }

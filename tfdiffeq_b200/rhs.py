@@ -91,6 +91,23 @@ class CubicMLP(BuiltinRHS):
 _ACT = {None: 0, "none": 0, "relu": 1, "tanh": 2, "softplus": 3}
 
 
+_TF32_CACHE = {}
+
+
+def _tf32_weight(weight):
+    """The B operand rounded to TF32 (round-to-nearest, ties away: what cvt.rna.tf32.f32 does), cached per weight
+    version so the rounding runs once per optimiser step, not once per func evaluation."""
+    key = (weight.data_ptr(), weight._version, tuple(weight.shape))
+    hit = _TF32_CACHE.get(id(weight))
+    if hit is not None and hit[0] == key:
+        return hit[1]
+    with torch.no_grad():
+        i = weight.detach().contiguous().view(torch.int32)
+        r = ((i + 0x1000) & -0x2000).view(torch.float32)
+    _TF32_CACHE[id(weight)] = (key, r)
+    return r
+
+
 def dense_layer(x, weight, bias, act="none", stage=None):
     """``act(x @ weight.T + bias)`` on the tcgen05 tensor cores (fp32 storage, TF32 math): ``b2ode_dense_layer``.
 
@@ -109,7 +126,7 @@ def dense_layer(x, weight, bias, act="none", stage=None):
         carr = (C.c_double * nk)(*coefs)
     _lib.check(_lib.lib.b2ode_dense_layer(
         C.c_void_p(x.data_ptr()), karr, carr, nk, C.c_void_p(state) if state else None,
-        C.c_void_p(ys.data_ptr()) if ys is not None else None, C.c_void_p(weight.data_ptr()),
+        C.c_void_p(ys.data_ptr()) if ys is not None else None, C.c_void_p(_tf32_weight(weight).data_ptr()),
         C.c_void_p(bias.data_ptr()) if bias is not None else None, C.c_void_p(out.data_ptr()), M, K, N, _ACT[act],
         C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)))
     return out
