@@ -18,6 +18,7 @@
 #include "b2ode_dev.cuh"
 
 #include <stdint.h>
+#include <stdlib.h>
 
 constexpr int kMmaThreads = 128;
 constexpr int kTileM = 128;
@@ -93,6 +94,114 @@ __device__ __forceinline__ float apply_act(float v, int act) {
     return v;
 }
 
+// ---- operand producers (shared by the simple kernel and the warp-specialised one) ----------------------------------
+// Fill one K chunk (64 columns) of the B operand (NT rows of W, host-rounded TF32) and of the A operand (128 rows:
+// a plain activation tile, or the Runge-Kutta stage input formed on the fly) in the K-major SWIZZLE_128B layout.
+// Called by `nthr` threads with ids 0..nthr-1 (nthr == 128).
+__device__ __forceinline__ void produce_chunk(const DenseParams &p, uint8_t *sA, uint8_t *sB, int m0, int n0, int NT, int kc,
+                                              int tid, const float (&cf)[kMaxNK]) {
+    const bool vec_ok = (p.K & 3) == 0;
+    // ---- B chunk first: NT rows (output features) x 64 columns of W[N, K], already TF32-rounded by the host:
+    //      raw 16-byte async copies straight into the swizzled layout (no register staging), zero-filled past K
+    if (vec_ok) {
+        for (int f = tid; f < NT * (kKChunk / 4); f += kMmaThreads) {
+            const int row = f / (kKChunk / 4), c4 = f % (kKChunk / 4);
+            const int gk = kc + c4 * 4;
+            const float *src = p.W + (size_t)(n0 + row) * p.K + (gk < p.K ? gk : 0);
+            const uint32_t dst = smem_u32(sB + (c4 >> 3) * (256 * 128) + sw128_offset(row, c4 & 7));
+            const int nbytes = gk < p.K ? 16 : 0;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
+        }
+    } else {
+        for (int f = tid; f < NT * (kKChunk / 4); f += kMmaThreads) {
+            const int row = f / (kKChunk / 4), c4 = f % (kKChunk / 4);
+            const int gk = kc + c4 * 4;
+            uint32_t e[4] = {0u, 0u, 0u, 0u};
+            for (int q = 0; q < 4 && gk + q < p.K; ++q) e[q] = __float_as_uint(p.W[(size_t)(n0 + row) * p.K + gk + q]);
+            *reinterpret_cast<uint4 *>(sB + (c4 >> 3) * (256 * 128) + sw128_offset(row, c4 & 7)) = make_uint4(e[0], e[1], e[2], e[3]);
+        }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    // ---- A chunk: 128 rows x 64 columns = 16 float4 per thread, in 4 batches of 4 so that 4 x (1 + nk) independent
+    //      16-byte loads are in flight per thread before anything is consumed
+    if (vec_ok) {
+#pragma unroll 1
+        for (int bt = 0; bt < 4; ++bt) {
+            float4 v[4];
+            size_t off[4];
+            bool in[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int f = tid + (bt * 4 + q) * kMmaThreads;
+                const int row = f / (kKChunk / 4), c4 = f % (kKChunk / 4);
+                const int gm = m0 + row, gk = kc + c4 * 4;
+                in[q] = gm < p.M && gk < p.K;
+                off[q] = in[q] ? (size_t)gm * p.K + gk : 0;
+                v[q] = in[q] ? *reinterpret_cast<const float4 *>(p.x + off[q]) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            if (p.nk > 0) {
+                float4 acc[4];
+#pragma unroll 1
+                for (int j = 0; j < p.nk; ++j) {
+                    float4 kv[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        kv[q] = in[q] ? *reinterpret_cast<const float4 *>(p.k[j] + off[q]) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    const float c = cf[j];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float tx = __fmul_rn(c, kv[q].x), ty = __fmul_rn(c, kv[q].y);
+                        const float tz = __fmul_rn(c, kv[q].z), tw = __fmul_rn(c, kv[q].w);
+                        acc[q].x = j ? __fadd_rn(acc[q].x, tx) : tx;
+                        acc[q].y = j ? __fadd_rn(acc[q].y, ty) : ty;
+                        acc[q].z = j ? __fadd_rn(acc[q].z, tz) : tz;
+                        acc[q].w = j ? __fadd_rn(acc[q].w, tw) : tw;
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    v[q].x = __fadd_rn(v[q].x, acc[q].x);
+                    v[q].y = __fadd_rn(v[q].y, acc[q].y);
+                    v[q].z = __fadd_rn(v[q].z, acc[q].z);
+                    v[q].w = __fadd_rn(v[q].w, acc[q].w);
+                    if (p.ystage && n0 == 0 && in[q]) *reinterpret_cast<float4 *>(p.ystage + off[q]) = v[q];
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int f = tid + (bt * 4 + q) * kMmaThreads;
+                const int row = f / (kKChunk / 4), c4 = f % (kKChunk / 4);
+                const uint4 t = make_uint4(to_tf32(v[q].x), to_tf32(v[q].y), to_tf32(v[q].z), to_tf32(v[q].w));
+                *reinterpret_cast<uint4 *>(sA + (c4 >> 3) * (kTileM * 128) + sw128_offset(row, c4 & 7)) = t;
+            }
+        }
+    } else {
+        for (int f = tid; f < kTileM * (kKChunk / 4); f += kMmaThreads) {
+            const int row = f / (kKChunk / 4), c4 = f % (kKChunk / 4);
+            const int gm = m0 + row, gk = kc + c4 * 4;
+            float e[4] = {0.f, 0.f, 0.f, 0.f};
+            if (gm < p.M) {
+                for (int q = 0; q < 4 && gk + q < p.K; ++q) {
+                    const size_t off = (size_t)gm * p.K + gk + q;
+                    float a = p.x[off];
+                    if (p.nk > 0) {
+                        float acc = 0.f;
+                        for (int j = 0; j < p.nk; ++j) {
+                            const float t = __fmul_rn(cf[j], p.k[j][off]);
+                            acc = j ? __fadd_rn(acc, t) : t;
+                        }
+                        a = __fadd_rn(a, acc);
+                        if (p.ystage && n0 == 0) p.ystage[off] = a;
+                    }
+                    e[q] = a;
+                }
+            }
+            const uint4 t = make_uint4(to_tf32(e[0]), to_tf32(e[1]), to_tf32(e[2]), to_tf32(e[3]));
+            *reinterpret_cast<uint4 *>(sA + (c4 >> 3) * (kTileM * 128) + sw128_offset(row, c4 & 7)) = t;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(kMmaThreads, 2) k_dense_layer_tf32(const __grid_constant__ DenseParams p) {
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment for the swizzle atoms
@@ -133,106 +242,7 @@ __global__ void __launch_bounds__(kMmaThreads, 2) k_dense_layer_tf32(const __gri
         const int NT = (p.N - n0) < 256 ? (p.N - n0) : 256;
         const uint32_t idesc = make_idesc_tf32(NT);
         for (int kc = 0; kc < p.K; kc += kKChunk) {
-            const bool vec_ok = (p.K & 3) == 0;
-            // ---- B chunk first: NT rows (output features) x 64 columns of W[N, K], already TF32-rounded by the host:
-            //      raw 16-byte async copies straight into the swizzled layout (no register staging), zero-filled past K
-            if (vec_ok) {
-                for (int f = tid; f < NT * (kKChunk / 4); f += kMmaThreads) {
-                    const int row = f / (kKChunk / 4), c4 = f % (kKChunk / 4);
-                    const int gk = kc + c4 * 4;
-                    const float *src = p.W + (size_t)(n0 + row) * p.K + (gk < p.K ? gk : 0);
-                    const uint32_t dst = smem_u32(sB + (c4 >> 3) * (256 * 128) + sw128_offset(row, c4 & 7));
-                    const int nbytes = gk < p.K ? 16 : 0;
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
-                }
-            } else {
-                for (int f = tid; f < NT * (kKChunk / 4); f += kMmaThreads) {
-                    const int row = f / (kKChunk / 4), c4 = f % (kKChunk / 4);
-                    const int gk = kc + c4 * 4;
-                    uint32_t e[4] = {0u, 0u, 0u, 0u};
-                    for (int q = 0; q < 4 && gk + q < p.K; ++q) e[q] = __float_as_uint(p.W[(size_t)(n0 + row) * p.K + gk + q]);
-                    *reinterpret_cast<uint4 *>(sB + (c4 >> 3) * (256 * 128) + sw128_offset(row, c4 & 7)) = make_uint4(e[0], e[1], e[2], e[3]);
-                }
-            }
-            asm volatile("cp.async.commit_group;" ::: "memory");
-            // ---- A chunk: 128 rows x 64 columns = 16 float4 per thread, in 4 batches of 4 so that 4 x (1 + nk) independent
-            //      16-byte loads are in flight per thread before anything is consumed
-            if (vec_ok) {
-#pragma unroll 1
-                for (int bt = 0; bt < 4; ++bt) {
-                    float4 v[4];
-                    size_t off[4];
-                    bool in[4];
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const int f = tid + (bt * 4 + q) * kMmaThreads;
-                        const int row = f / (kKChunk / 4), c4 = f % (kKChunk / 4);
-                        const int gm = m0 + row, gk = kc + c4 * 4;
-                        in[q] = gm < p.M && gk < p.K;
-                        off[q] = in[q] ? (size_t)gm * p.K + gk : 0;
-                        v[q] = in[q] ? *reinterpret_cast<const float4 *>(p.x + off[q]) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
-                    if (p.nk > 0) {
-                        float4 acc[4];
-#pragma unroll 1
-                        for (int j = 0; j < p.nk; ++j) {
-                            float4 kv[4];
-#pragma unroll
-                            for (int q = 0; q < 4; ++q)
-                                kv[q] = in[q] ? *reinterpret_cast<const float4 *>(p.k[j] + off[q]) : make_float4(0.f, 0.f, 0.f, 0.f);
-                            const float c = cf[j];
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                const float tx = __fmul_rn(c, kv[q].x), ty = __fmul_rn(c, kv[q].y);
-                                const float tz = __fmul_rn(c, kv[q].z), tw = __fmul_rn(c, kv[q].w);
-                                acc[q].x = j ? __fadd_rn(acc[q].x, tx) : tx;
-                                acc[q].y = j ? __fadd_rn(acc[q].y, ty) : ty;
-                                acc[q].z = j ? __fadd_rn(acc[q].z, tz) : tz;
-                                acc[q].w = j ? __fadd_rn(acc[q].w, tw) : tw;
-                            }
-                        }
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            v[q].x = __fadd_rn(v[q].x, acc[q].x);
-                            v[q].y = __fadd_rn(v[q].y, acc[q].y);
-                            v[q].z = __fadd_rn(v[q].z, acc[q].z);
-                            v[q].w = __fadd_rn(v[q].w, acc[q].w);
-                            if (p.ystage && n0 == 0 && in[q]) *reinterpret_cast<float4 *>(p.ystage + off[q]) = v[q];
-                        }
-                    }
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const int f = tid + (bt * 4 + q) * kMmaThreads;
-                        const int row = f / (kKChunk / 4), c4 = f % (kKChunk / 4);
-                        const uint4 t = make_uint4(to_tf32(v[q].x), to_tf32(v[q].y), to_tf32(v[q].z), to_tf32(v[q].w));
-                        *reinterpret_cast<uint4 *>(sA + (c4 >> 3) * (kTileM * 128) + sw128_offset(row, c4 & 7)) = t;
-                    }
-                }
-            } else {
-                for (int f = tid; f < kTileM * (kKChunk / 4); f += kMmaThreads) {
-                    const int row = f / (kKChunk / 4), c4 = f % (kKChunk / 4);
-                    const int gm = m0 + row, gk = kc + c4 * 4;
-                    float e[4] = {0.f, 0.f, 0.f, 0.f};
-                    if (gm < p.M) {
-                        for (int q = 0; q < 4 && gk + q < p.K; ++q) {
-                            const size_t off = (size_t)gm * p.K + gk + q;
-                            float a = p.x[off];
-                            if (p.nk > 0) {
-                                float acc = 0.f;
-                                for (int j = 0; j < p.nk; ++j) {
-                                    const float t = __fmul_rn(cf[j], p.k[j][off]);
-                                    acc = j ? __fadd_rn(acc, t) : t;
-                                }
-                                a = __fadd_rn(a, acc);
-                                if (p.ystage && n0 == 0) p.ystage[off] = a;
-                            }
-                            e[q] = a;
-                        }
-                    }
-                    const uint4 t = make_uint4(to_tf32(e[0]), to_tf32(e[1]), to_tf32(e[2]), to_tf32(e[3]));
-                    *reinterpret_cast<uint4 *>(sA + (c4 >> 3) * (kTileM * 128) + sw128_offset(row, c4 & 7)) = t;
-                }
-            }
+            produce_chunk(p, sA, sB, m0, n0, NT, kc, tid, cf);
             asm volatile("cp.async.wait_group 0;" ::: "memory");
             // make the generic-proxy writes visible to the tensor core (async proxy), then hand over
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -309,6 +319,176 @@ __global__ void __launch_bounds__(kMmaThreads, 2) k_dense_layer_tf32(const __gri
 }
 
 // ================================================================================================
+// Warp-specialised, persistent version (the one that is launched by default).
+//   warps 0-3  producers : fill a 2-stage ring of (A chunk, B chunk) shared-memory buffers
+//   warp  4    MMA       : one elected lane issues tcgen05.mma into one of two 256-column TMEM accumulators,
+//                          tcgen05.commit releases the stage back to the producers / hands the accumulator over
+//   warps 5-8  epilogue  : tcgen05.ld (each warp its own 32-lane quarter), bias + activation, fp32 row stores
+// so operand production, tensor-core math and the epilogue of the previous tile overlap.  mbarriers: full[s]
+// (128 producer arrivals), empty[s] (1 commit), tfull[b] (1 commit), tempty[b] (128 epilogue arrivals).
+// ================================================================================================
+constexpr int kWsThreads = 288;
+constexpr int kStages = 2;
+constexpr int kStageBytes = kTileM * 128 * 2 + 256 * 128 * 2;     // A 32 KB + B 64 KB
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
+}
+
+__global__ void __launch_bounds__(kWsThreads, 1) k_dense_layer_tf32_ws(const __grid_constant__ DenseParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    __shared__ __align__(8) uint64_t bar_full[kStages], bar_empty[kStages], bar_tfull[2], bar_tempty[2];
+    __shared__ uint32_t tmem_slot;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tiles_m = (p.M + kTileM - 1) / kTileM;
+    const int tiles_n = (p.N + 255) / 256;
+    const int items = tiles_m * tiles_n;
+    const int chunks = (p.K + kKChunk - 1) / kKChunk;
+
+    if (warp == 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512u));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    if (tid == 0) {
+        for (int i = 0; i < kStages; ++i) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bar_full[i])), "r"(128u));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bar_empty[i])), "r"(1u));
+        }
+        for (int i = 0; i < 2; ++i) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bar_tfull[i])), "r"(1u));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bar_tempty[i])), "r"(128u));
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const uint32_t tmem_base = tmem_slot;
+
+    if (warp < 4) {
+        // ===== producers =====
+        float cf[kMaxNK];
+        if (p.nk > 0) {
+            const float dt = (float)p.st->dt;
+#pragma unroll
+            for (int j = 0; j < kMaxNK; ++j) cf[j] = (j < p.nk) ? __fmul_rn(dt, (float)p.coef[j]) : 0.f;
+        } else {
+#pragma unroll
+            for (int j = 0; j < kMaxNK; ++j) cf[j] = 0.f;
+        }
+        uint32_t it = 0;
+        for (int item = blockIdx.x; item < items; item += gridDim.x) {
+            const int m0 = (item / tiles_n) * kTileM, n0 = (item % tiles_n) * 256;
+            const int NT = (p.N - n0) < 256 ? (p.N - n0) : 256;
+            for (int c = 0; c < chunks; ++c, ++it) {
+                const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
+                mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);                       // the MMAs that read this stage are done
+                uint8_t *sA = smem + s * kStageBytes, *sB = sA + kTileM * 128 * 2;
+                produce_chunk(p, sA, sB, m0, n0, NT, c * kKChunk, tid, cf);
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> async proxy (tensor core)
+                mbar_arrive(smem_u32(&bar_full[s]));
+            }
+        }
+    } else if (warp == 4) {
+        // ===== MMA issuer =====
+        uint32_t it = 0, acc = 0;
+        for (int item = blockIdx.x; item < items; item += gridDim.x, ++acc) {
+            const int n0 = (item % tiles_n) * 256;
+            const int NT = (p.N - n0) < 256 ? (p.N - n0) : 256;
+            const uint32_t idesc = make_idesc_tf32(NT);
+            const uint32_t ab = acc & 1u, aph = (acc >> 1) & 1u;
+            mbar_wait(smem_u32(&bar_tempty[ab]), aph ^ 1u);                        // the epilogue has drained this accumulator
+            asm volatile("tcgen05.fence::after_thread_sync;");
+            const uint32_t tacc = tmem_base + ab * 256u;
+            for (int c = 0; c < chunks; ++c, ++it) {
+                const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
+                mbar_wait(smem_u32(&bar_full[s]), ph);
+                asm volatile("tcgen05.fence::after_thread_sync;");
+                if (lane == 0) {
+                    uint8_t *sA = smem + s * kStageBytes, *sB = sA + kTileM * 128 * 2;
+#pragma unroll
+                    for (int kb = 0; kb < 2; ++kb) {
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks) {
+                            const uint64_t da = make_desc(smem_u32(sA + kb * (kTileM * 128)) + ks * 32);
+                            const uint64_t db = make_desc(smem_u32(sB + kb * (256 * 128)) + ks * 32);
+                            const uint32_t accum = (c > 0 || kb > 0 || ks > 0) ? 1u : 0u;
+                            asm volatile(
+                                "{\n\t.reg .pred p;\n\t"
+                                "setp.ne.b32 p, %4, 0;\n\t"
+                                "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                                ::"r"(tacc), "l"(da), "l"(db), "r"(idesc), "r"(accum)
+                                : "memory");
+                        }
+                    }
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar_empty[s]))
+                                 : "memory");
+                    if (c == chunks - 1)
+                        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar_tfull[ab]))
+                                     : "memory");
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ===== epilogue =====
+        const int q = warp & 3;                                                    // TMEM lane quarter this warp may read
+        uint32_t acc = 0;
+        for (int item = blockIdx.x; item < items; item += gridDim.x, ++acc) {
+            const int m0 = (item / tiles_n) * kTileM, n0 = (item % tiles_n) * 256;
+            const int NT = (p.N - n0) < 256 ? (p.N - n0) : 256;
+            const uint32_t ab = acc & 1u, aph = (acc >> 1) & 1u;
+            mbar_wait(smem_u32(&bar_tfull[ab]), aph);
+            asm volatile("tcgen05.fence::after_thread_sync;");
+            const int gm = m0 + q * 32 + lane;
+            for (int c0 = 0; c0 < NT; c0 += 32) {
+                uint32_t r[32];
+                const uint32_t taddr = tmem_base + ab * 256u + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                      "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+                      "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+                      "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                    : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (gm < p.M) {
+                    float *dst = p.out + (size_t)gm * p.N + n0 + c0;
+                    const bool full = (c0 + 32 <= NT) && ((p.N & 3) == 0);
+#pragma unroll
+                    for (int w = 0; w < 32; w += 4) {
+                        float o[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            float v = __uint_as_float(r[w + u]);
+                            if (p.bias && c0 + w + u < NT) v += p.bias[n0 + c0 + w + u];
+                            o[u] = apply_act(v, p.act);
+                        }
+                        if (full) {
+                            *reinterpret_cast<float4 *>(dst + w) = make_float4(o[0], o[1], o[2], o[3]);
+                        } else {
+#pragma unroll
+                            for (int u = 0; u < 4; ++u)
+                                if (c0 + w + u < NT) dst[w + u] = o[u];
+                        }
+                    }
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;");
+            mbar_arrive(smem_u32(&bar_tempty[ab]));                                // accumulator may be overwritten
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+}
+
+// ================================================================================================
 // host side
 // ================================================================================================
 extern "C" int b2ode_dense_layer(const void *x, const void *const *k, const double *coef, int nk, const void *state,
@@ -337,14 +517,35 @@ extern "C" int b2ode_dense_layer(const void *x, const void *const *k, const doub
     p.K = K;
     p.N = N;
     p.act = act;
-    const size_t smem = 2 * kTileM * 128 + 2 * 256 * 128 + 1024;      // A + B + alignment slack = 99 328 B
-    static bool configured = false;
-    if (!configured) {
-        B2_CUDA(cudaFuncSetAttribute(k_dense_layer_tf32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
+    static int variant = -1;         // B2ODE_DENSE_SIMPLE=1 selects the non-pipelined kernel (kept as a cross-check)
+    if (variant < 0) {
+        const char *e = getenv("B2ODE_DENSE_SIMPLE");
+        variant = (e && e[0] == '1') ? 1 : 0;
     }
-    const int grid = (int)((M + kTileM - 1) / kTileM);
-    k_dense_layer_tf32<<<grid, kMmaThreads, smem, (cudaStream_t)cuda_stream>>>(p);
+    if (variant == 1) {
+        const size_t smem = 2 * kTileM * 128 + 2 * 256 * 128 + 1024;      // A + B + alignment slack = 99 328 B
+        static bool configured = false;
+        if (!configured) {
+            B2_CUDA(cudaFuncSetAttribute(k_dense_layer_tf32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured = true;
+        }
+        const int grid = (int)((M + kTileM - 1) / kTileM);
+        k_dense_layer_tf32<<<grid, kMmaThreads, smem, (cudaStream_t)cuda_stream>>>(p);
+    } else {
+        const size_t smem = (size_t)kStages * kStageBytes + 1024;          // 2 x 96 KB ring + alignment slack
+        static bool configured = false;
+        static int sms = 0;
+        if (!configured) {
+            B2_CUDA(cudaFuncSetAttribute(k_dense_layer_tf32_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int dev = 0;
+            B2_CUDA(cudaGetDevice(&dev));
+            B2_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+            configured = true;
+        }
+        const long long items = ((M + kTileM - 1) / kTileM) * (long long)((N + 255) / 256);
+        const int grid = (int)(items < sms ? items : sms);                 // persistent: one CTA per SM
+        k_dense_layer_tf32_ws<<<grid, kWsThreads, smem, (cudaStream_t)cuda_stream>>>(p);
+    }
     B2_CUDA(cudaGetLastError());
     b2_count_launch();
     return 0;
