@@ -97,14 +97,17 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 // ---- operand producers (shared by the simple kernel and the warp-specialised one) ----------------------------------
 // Fill one K chunk (64 columns) of the B operand (NT rows of W, host-rounded TF32) and of the A operand (128 rows:
 // a plain activation tile, or the Runge-Kutta stage input formed on the fly) in the K-major SWIZZLE_128B layout.
-// Called by `nthr` threads with ids 0..nthr-1 (nthr == 128).
-__device__ __forceinline__ void produce_chunk(const DenseParams &p, uint8_t *sA, uint8_t *sB, int m0, int n0, int NT, int kc,
-                                              int tid, const float (&cf)[kMaxNK]) {
+// Called by NTHR threads with ids 0..NTHR-1.  NK (the number of k's in the stage combine) is a template parameter
+// so that every global load of a batch -- BQ positions x (1 + NK) streams -- is issued before the first one is
+// consumed: the producers are latency-bound, memory-level parallelism is what feeds the tensor core.
+template <int NTHR, int NK>
+__device__ __forceinline__ void produce_chunk_t(const DenseParams &p, uint8_t *sA, uint8_t *sB, int m0, int n0, int NT, int kc,
+                                                int tid, const float (&cf)[kMaxNK]) {
     const bool vec_ok = (p.K & 3) == 0;
     // ---- B chunk first: NT rows (output features) x 64 columns of W[N, K], already TF32-rounded by the host:
     //      raw 16-byte async copies straight into the swizzled layout (no register staging), zero-filled past K
     if (vec_ok) {
-        for (int f = tid; f < NT * (kKChunk / 4); f += kMmaThreads) {
+        for (int f = tid; f < NT * (kKChunk / 4); f += NTHR) {
             const int row = f / (kKChunk / 4), c4 = f % (kKChunk / 4);
             const int gk = kc + c4 * 4;
             const float *src = p.W + (size_t)(n0 + row) * p.K + (gk < p.K ? gk : 0);
@@ -113,7 +116,7 @@ __device__ __forceinline__ void produce_chunk(const DenseParams &p, uint8_t *sA,
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
         }
     } else {
-        for (int f = tid; f < NT * (kKChunk / 4); f += kMmaThreads) {
+        for (int f = tid; f < NT * (kKChunk / 4); f += NTHR) {
             const int row = f / (kKChunk / 4), c4 = f % (kKChunk / 4);
             const int gk = kc + c4 * 4;
             uint32_t e[4] = {0u, 0u, 0u, 0u};
@@ -122,61 +125,65 @@ __device__ __forceinline__ void produce_chunk(const DenseParams &p, uint8_t *sA,
         }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
-    // ---- A chunk: 128 rows x 64 columns = 16 float4 per thread, in 4 batches of 4 so that 4 x (1 + nk) independent
-    //      16-byte loads are in flight per thread before anything is consumed
+    // ---- A chunk: 128 rows x 64 columns = PP float4 per thread
+    constexpr int PP = kTileM * (kKChunk / 4) / NTHR;          // 16 (128 threads) or 8 (256 threads)
+    constexpr int BQ = (NK == 0) ? PP : (PP < 4 ? PP : 4);     // positions per batch
     if (vec_ok) {
 #pragma unroll 1
-        for (int bt = 0; bt < 4; ++bt) {
-            float4 v[4];
-            size_t off[4];
-            bool in[4];
+        for (int b0 = 0; b0 < PP; b0 += BQ) {
+            float4 v[BQ];
+            float4 kv[NK > 0 ? NK : 1][BQ];
+            size_t off[BQ];
+            bool in[BQ];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int f = tid + (bt * 4 + q) * kMmaThreads;
+            for (int q = 0; q < BQ; ++q) {
+                const int f = tid + (b0 + q) * NTHR;
                 const int row = f / (kKChunk / 4), c4 = f % (kKChunk / 4);
                 const int gm = m0 + row, gk = kc + c4 * 4;
                 in[q] = gm < p.M && gk < p.K;
                 off[q] = in[q] ? (size_t)gm * p.K + gk : 0;
-                v[q] = in[q] ? *reinterpret_cast<const float4 *>(p.x + off[q]) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
-            if (p.nk > 0) {
-                float4 acc[4];
-#pragma unroll 1
-                for (int j = 0; j < p.nk; ++j) {
-                    float4 kv[4];
+            // all loads of the batch first ...
 #pragma unroll
-                    for (int q = 0; q < 4; ++q)
-                        kv[q] = in[q] ? *reinterpret_cast<const float4 *>(p.k[j] + off[q]) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    const float c = cf[j];
+            for (int q = 0; q < BQ; ++q)
+                v[q] = in[q] ? *reinterpret_cast<const float4 *>(p.x + off[q]) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const float tx = __fmul_rn(c, kv[q].x), ty = __fmul_rn(c, kv[q].y);
-                        const float tz = __fmul_rn(c, kv[q].z), tw = __fmul_rn(c, kv[q].w);
-                        acc[q].x = j ? __fadd_rn(acc[q].x, tx) : tx;
-                        acc[q].y = j ? __fadd_rn(acc[q].y, ty) : ty;
-                        acc[q].z = j ? __fadd_rn(acc[q].z, tz) : tz;
-                        acc[q].w = j ? __fadd_rn(acc[q].w, tw) : tw;
+            for (int j = 0; j < NK; ++j)
+#pragma unroll
+                for (int q = 0; q < BQ; ++q)
+                    kv[j][q] = in[q] ? *reinterpret_cast<const float4 *>(p.k[j] + off[q]) : make_float4(0.f, 0.f, 0.f, 0.f);
+            // ... then the combine (rk_common.py:51: (dt*beta_j)*k_j summed left to right, then y0 + sum), in fp32
+            if (NK > 0) {
+#pragma unroll
+                for (int q = 0; q < BQ; ++q) {
+                    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int j = 0; j < NK; ++j) {
+                        const float c = cf[j];
+                        const float tx = __fmul_rn(c, kv[j][q].x), ty = __fmul_rn(c, kv[j][q].y);
+                        const float tz = __fmul_rn(c, kv[j][q].z), tw = __fmul_rn(c, kv[j][q].w);
+                        acc.x = j ? __fadd_rn(acc.x, tx) : tx;
+                        acc.y = j ? __fadd_rn(acc.y, ty) : ty;
+                        acc.z = j ? __fadd_rn(acc.z, tz) : tz;
+                        acc.w = j ? __fadd_rn(acc.w, tw) : tw;
                     }
-                }
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    v[q].x = __fadd_rn(v[q].x, acc[q].x);
-                    v[q].y = __fadd_rn(v[q].y, acc[q].y);
-                    v[q].z = __fadd_rn(v[q].z, acc[q].z);
-                    v[q].w = __fadd_rn(v[q].w, acc[q].w);
+                    v[q].x = __fadd_rn(v[q].x, acc.x);
+                    v[q].y = __fadd_rn(v[q].y, acc.y);
+                    v[q].z = __fadd_rn(v[q].z, acc.z);
+                    v[q].w = __fadd_rn(v[q].w, acc.w);
                     if (p.ystage && n0 == 0 && in[q]) *reinterpret_cast<float4 *>(p.ystage + off[q]) = v[q];
                 }
             }
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int f = tid + (bt * 4 + q) * kMmaThreads;
+            for (int q = 0; q < BQ; ++q) {
+                const int f = tid + (b0 + q) * NTHR;
                 const int row = f / (kKChunk / 4), c4 = f % (kKChunk / 4);
                 const uint4 t = make_uint4(to_tf32(v[q].x), to_tf32(v[q].y), to_tf32(v[q].z), to_tf32(v[q].w));
                 *reinterpret_cast<uint4 *>(sA + (c4 >> 3) * (kTileM * 128) + sw128_offset(row, c4 & 7)) = t;
             }
         }
     } else {
-        for (int f = tid; f < kTileM * (kKChunk / 4); f += kMmaThreads) {
+        for (int f = tid; f < kTileM * (kKChunk / 4); f += NTHR) {
             const int row = f / (kKChunk / 4), c4 = f % (kKChunk / 4);
             const int gm = m0 + row, gk = kc + c4 * 4;
             float e[4] = {0.f, 0.f, 0.f, 0.f};
@@ -184,9 +191,10 @@ __device__ __forceinline__ void produce_chunk(const DenseParams &p, uint8_t *sA,
                 for (int q = 0; q < 4 && gk + q < p.K; ++q) {
                     const size_t off = (size_t)gm * p.K + gk + q;
                     float a = p.x[off];
-                    if (p.nk > 0) {
+                    if (NK > 0) {
                         float acc = 0.f;
-                        for (int j = 0; j < p.nk; ++j) {
+#pragma unroll
+                        for (int j = 0; j < NK; ++j) {
                             const float t = __fmul_rn(cf[j], p.k[j][off]);
                             acc = j ? __fadd_rn(acc, t) : t;
                         }
@@ -199,6 +207,22 @@ __device__ __forceinline__ void produce_chunk(const DenseParams &p, uint8_t *sA,
             const uint4 t = make_uint4(to_tf32(e[0]), to_tf32(e[1]), to_tf32(e[2]), to_tf32(e[3]));
             *reinterpret_cast<uint4 *>(sA + (c4 >> 3) * (kTileM * 128) + sw128_offset(row, c4 & 7)) = t;
         }
+    }
+}
+
+template <int NTHR>
+__device__ __forceinline__ void produce_chunk(const DenseParams &p, uint8_t *sA, uint8_t *sB, int m0, int n0, int NT, int kc,
+                                              int tid, const float (&cf)[kMaxNK]) {
+    switch (p.nk) {
+        case 0: produce_chunk_t<NTHR, 0>(p, sA, sB, m0, n0, NT, kc, tid, cf); break;
+        case 1: produce_chunk_t<NTHR, 1>(p, sA, sB, m0, n0, NT, kc, tid, cf); break;
+        case 2: produce_chunk_t<NTHR, 2>(p, sA, sB, m0, n0, NT, kc, tid, cf); break;
+        case 3: produce_chunk_t<NTHR, 3>(p, sA, sB, m0, n0, NT, kc, tid, cf); break;
+        case 4: produce_chunk_t<NTHR, 4>(p, sA, sB, m0, n0, NT, kc, tid, cf); break;
+        case 5: produce_chunk_t<NTHR, 5>(p, sA, sB, m0, n0, NT, kc, tid, cf); break;
+        case 6: produce_chunk_t<NTHR, 6>(p, sA, sB, m0, n0, NT, kc, tid, cf); break;
+        case 7: produce_chunk_t<NTHR, 7>(p, sA, sB, m0, n0, NT, kc, tid, cf); break;
+        default: produce_chunk_t<NTHR, 8>(p, sA, sB, m0, n0, NT, kc, tid, cf); break;
     }
 }
 
@@ -242,7 +266,7 @@ __global__ void __launch_bounds__(kMmaThreads, 2) k_dense_layer_tf32(const __gri
         const int NT = (p.N - n0) < 256 ? (p.N - n0) : 256;
         const uint32_t idesc = make_idesc_tf32(NT);
         for (int kc = 0; kc < p.K; kc += kKChunk) {
-            produce_chunk(p, sA, sB, m0, n0, NT, kc, tid, cf);
+            produce_chunk<kMmaThreads>(p, sA, sB, m0, n0, NT, kc, tid, cf);
             asm volatile("cp.async.wait_group 0;" ::: "memory");
             // make the generic-proxy writes visible to the tensor core (async proxy), then hand over
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -320,14 +344,16 @@ __global__ void __launch_bounds__(kMmaThreads, 2) k_dense_layer_tf32(const __gri
 
 // ================================================================================================
 // Warp-specialised, persistent version (the one that is launched by default).
-//   warps 0-3  producers : fill a 2-stage ring of (A chunk, B chunk) shared-memory buffers
-//   warp  4    MMA       : one elected lane issues tcgen05.mma into one of two 256-column TMEM accumulators,
+//   warps 0-7  producers : fill a 2-stage ring of (A chunk, B chunk) shared-memory buffers
+//   warp  8    MMA       : one elected lane issues tcgen05.mma into one of two 256-column TMEM accumulators,
 //                          tcgen05.commit releases the stage back to the producers / hands the accumulator over
-//   warps 5-8  epilogue  : tcgen05.ld (each warp its own 32-lane quarter), bias + activation, fp32 row stores
+//   warps 9-12 epilogue  : tcgen05.ld (each warp its own 32-lane quarter), bias + activation, fp32 row stores
 // so operand production, tensor-core math and the epilogue of the previous tile overlap.  mbarriers: full[s]
-// (128 producer arrivals), empty[s] (1 commit), tfull[b] (1 commit), tempty[b] (128 epilogue arrivals).
+// (256 producer arrivals), empty[s] (1 commit), tfull[b] (1 commit), tempty[b] (128 epilogue arrivals).
 // ================================================================================================
-constexpr int kWsThreads = 288;
+constexpr int kProdWarps = 8;
+constexpr int kProdThreads = kProdWarps * 32;
+constexpr int kWsThreads = (kProdWarps + 1 + 4) * 32;      // producers + MMA warp + 4 epilogue warps
 constexpr int kStages = 2;
 constexpr int kStageBytes = kTileM * 128 * 2 + 256 * 128 * 2;     // A 32 KB + B 64 KB
 
@@ -347,13 +373,13 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_dense_layer_tf32_ws(const __g
     const int items = tiles_m * tiles_n;
     const int chunks = (p.K + kKChunk - 1) / kKChunk;
 
-    if (warp == 4) {
+    if (warp == kProdWarps) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512u));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     if (tid == 0) {
         for (int i = 0; i < kStages; ++i) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bar_full[i])), "r"(128u));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bar_full[i])), "r"((unsigned)kProdThreads));
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bar_empty[i])), "r"(1u));
         }
         for (int i = 0; i < 2; ++i) {
@@ -367,7 +393,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_dense_layer_tf32_ws(const __g
     asm volatile("tcgen05.fence::after_thread_sync;");
     const uint32_t tmem_base = tmem_slot;
 
-    if (warp < 4) {
+    if (warp < kProdWarps) {
         // ===== producers =====
         float cf[kMaxNK];
         if (p.nk > 0) {
@@ -386,13 +412,13 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_dense_layer_tf32_ws(const __g
                 const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
                 mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);                       // the MMAs that read this stage are done
                 uint8_t *sA = smem + s * kStageBytes, *sB = sA + kTileM * 128 * 2;
-                produce_chunk(p, sA, sB, m0, n0, NT, c * kKChunk, tid, cf);
+                produce_chunk<kProdThreads>(p, sA, sB, m0, n0, NT, c * kKChunk, tid, cf);
                 asm volatile("cp.async.wait_group 0;" ::: "memory");
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> async proxy (tensor core)
                 mbar_arrive(smem_u32(&bar_full[s]));
             }
         }
-    } else if (warp == 4) {
+    } else if (warp == kProdWarps) {
         // ===== MMA issuer =====
         uint32_t it = 0, acc = 0;
         for (int item = blockIdx.x; item < items; item += gridDim.x, ++acc) {
@@ -485,7 +511,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_dense_layer_tf32_ws(const __g
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
-    if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+    if (warp == kProdWarps) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
 }
 
 // ================================================================================================
