@@ -461,7 +461,11 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_dense_layer_tf32_ws(const __g
         }
     } else {
         // ===== epilogue =====
+        // TMEM gives each lane one accumulator ROW (32 consecutive columns per load); storing that directly would make
+        // every warp store touch 32 different rows, 16 bytes each.  The 32 x 32 block is transposed through a padded
+        // shared-memory tile instead, so that each warp store writes 32 consecutive floats (one 128-byte line) of one row.
         const int q = warp & 3;                                                    // TMEM lane quarter this warp may read
+        float *tile = reinterpret_cast<float *>(smem + kStages * kStageBytes) + q * (32 * 33);
         uint32_t acc = 0;
         for (int item = blockIdx.x; item < items; item += gridDim.x, ++acc) {
             const int m0 = (item / tiles_n) * kTileM, n0 = (item % tiles_n) * 256;
@@ -469,7 +473,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_dense_layer_tf32_ws(const __g
             const uint32_t ab = acc & 1u, aph = (acc >> 1) & 1u;
             mbar_wait(smem_u32(&bar_tfull[ab]), aph);
             asm volatile("tcgen05.fence::after_thread_sync;");
-            const int gm = m0 + q * 32 + lane;
+            const int row0 = m0 + q * 32;
             for (int c0 = 0; c0 < NT; c0 += 32) {
                 uint32_t r[32];
                 const uint32_t taddr = tmem_base + ab * 256u + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
@@ -483,26 +487,17 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_dense_layer_tf32_ws(const __g
                       "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
                     : "r"(taddr));
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (gm < p.M) {
-                    float *dst = p.out + (size_t)gm * p.N + n0 + c0;
-                    const bool full = (c0 + 32 <= NT) && ((p.N & 3) == 0);
+                __syncwarp();                                                       // previous block fully read back
 #pragma unroll
-                    for (int w = 0; w < 32; w += 4) {
-                        float o[4];
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            float v = __uint_as_float(r[w + u]);
-                            if (p.bias && c0 + w + u < NT) v += p.bias[n0 + c0 + w + u];
-                            o[u] = apply_act(v, p.act);
-                        }
-                        if (full) {
-                            *reinterpret_cast<float4 *>(dst + w) = make_float4(o[0], o[1], o[2], o[3]);
-                        } else {
-#pragma unroll
-                            for (int u = 0; u < 4; ++u)
-                                if (c0 + w + u < NT) dst[w + u] = o[u];
-                        }
-                    }
+                for (int w = 0; w < 32; ++w) tile[lane * 33 + w] = __uint_as_float(r[w]);   // row = lane (conflict-free: stride 33)
+                __syncwarp();
+                const int col = c0 + lane;                                          // after the transpose a lane owns a column
+                const bool col_ok = col < NT;
+                const float bv = (p.bias && col_ok) ? p.bias[n0 + col] : 0.f;
+                float *dst = p.out + (size_t)row0 * p.N + n0 + col;
+#pragma unroll 8
+                for (int rr = 0; rr < 32; ++rr) {
+                    if (col_ok && row0 + rr < p.M) dst[(size_t)rr * p.N] = apply_act(tile[rr * 33 + lane] + bv, p.act);
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;");
@@ -558,7 +553,7 @@ extern "C" int b2ode_dense_layer(const void *x, const void *const *k, const doub
         const int grid = (int)((M + kTileM - 1) / kTileM);
         k_dense_layer_tf32<<<grid, kMmaThreads, smem, (cudaStream_t)cuda_stream>>>(p);
     } else {
-        const size_t smem = (size_t)kStages * kStageBytes + 1024;          // 2 x 96 KB ring + alignment slack
+        const size_t smem = (size_t)kStages * kStageBytes + 4 * 32 * 33 * sizeof(float) + 1024;   // 2 x 96 KB ring + epilogue tiles + slack
         static bool configured = false;
         static int sms = 0;
         if (!configured) {
