@@ -349,7 +349,7 @@ __global__ void __launch_bounds__(kMmaThreads, 2) k_dense_layer_tf32(const __gri
 //                          tcgen05.commit releases the stage back to the producers / hands the accumulator over
 //   warps 9-12 epilogue  : tcgen05.ld (each warp its own 32-lane quarter), bias + activation, fp32 row stores
 // so operand production, tensor-core math and the epilogue of the previous tile overlap.  mbarriers: full[s]
-// (256 producer arrivals), empty[s] (1 commit), tfull[b] (1 commit), tempty[b] (128 epilogue arrivals).
+// (128 producer arrivals: the group that owns the stage), empty[s] (1 commit), tfull[b] (1 commit), tempty[b] (128 epilogue arrivals).
 // ================================================================================================
 constexpr int kProdWarps = 8;
 constexpr int kProdThreads = kProdWarps * 32;
@@ -379,7 +379,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_dense_layer_tf32_ws(const __g
     }
     if (tid == 0) {
         for (int i = 0; i < kStages; ++i) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bar_full[i])), "r"((unsigned)kProdThreads));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bar_full[i])), "r"((unsigned)(kProdThreads / kStages)));
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bar_empty[i])), "r"(1u));
         }
         for (int i = 0; i < 2; ++i) {
@@ -404,15 +404,20 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_dense_layer_tf32_ws(const __g
 #pragma unroll
             for (int j = 0; j < kMaxNK; ++j) cf[j] = 0.f;
         }
+        // two producer groups of 4 warps, each owning one stage of the ring: group g fills every chunk with
+        // (chunk counter % 2) == g, so the global loads of two consecutive chunks are in flight at the same time
+        const uint32_t grp = (uint32_t)(warp / (kProdWarps / kStages));
+        const int ltid = tid - (int)grp * (kProdThreads / kStages);
         uint32_t it = 0;
         for (int item = blockIdx.x; item < items; item += gridDim.x) {
             const int m0 = (item / tiles_n) * kTileM, n0 = (item % tiles_n) * 256;
             const int NT = (p.N - n0) < 256 ? (p.N - n0) : 256;
             for (int c = 0; c < chunks; ++c, ++it) {
                 const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
+                if (s != grp) continue;
                 mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);                       // the MMAs that read this stage are done
                 uint8_t *sA = smem + s * kStageBytes, *sB = sA + kTileM * 128 * 2;
-                produce_chunk<kProdThreads>(p, sA, sB, m0, n0, NT, c * kKChunk, tid, cf);
+                produce_chunk<kProdThreads / kStages>(p, sA, sB, m0, n0, NT, c * kKChunk, ltid, cf);
                 asm volatile("cp.async.wait_group 0;" ::: "memory");
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> async proxy (tensor core)
                 mbar_arrive(smem_u32(&bar_full[s]));
