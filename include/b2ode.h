@@ -233,6 +233,15 @@ int b2ode_set_k(b2ode_solver *s, int i, const void *const *k_new);
 int b2ode_dense_layer(const void *x, const void *const *k, const double *coef, int nk, const void *state, void *ystage,
                       const void *W, const void *bias, void *out, int64_t M, int K, int N, int act, void *cuda_stream);
 
+/* The whole three-layer func (dense_odenet.py:85-92: fc1 -> act -> fc2 -> act -> fc3) in ONE launch: per 128-row
+ * tile the hidden activations stay in shared memory / TMEM, so an evaluation moves only the input tile(s) and the
+ * output tile through HBM.  out[M, D] = W3 . act(W2 . act(W1 . A + b1) + b2) + b3 with A as in b2ode_dense_layer
+ * (x, or the stage combine of x and k[0..nk)).  W1 [H, D], W2 [H, H], W3 [D, H]; D and H multiples of 16 in
+ * [16, 256].  Weights must already be TF32-rounded (low 13 mantissa bits zero). */
+int b2ode_mlp3(const void *x, const void *const *k, const double *coef, int nk, const void *state, void *ystage,
+               const void *W1, const void *b1, const void *W2, const void *b2, const void *W3, const void *b3, void *out,
+               int64_t M, int D, int H, int act, void *cuda_stream);
+
 /* ---- measurement hooks (bench.py) --------------------------------------------------------------------- */
 unsigned long long b2ode_launch_count(void);            /* kernels launched by this library so far          */
 int b2ode_timing_enable(unsigned family_mask);          /* CUDA-event timing per kernel family; 0 = off     */

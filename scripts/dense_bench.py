@@ -41,7 +41,27 @@ def ours():
 print("B=%d dim=%d hidden=%d" % (B, D, H))
 r0 = timeit("torch fp32 matmul func", torch32, {})
 r1 = timeit("torch TF32 matmul func (allow_tf32)", torchtf32, {})
-r2 = timeit("tcgen05 dense layers, separate stage kernel", ours, {"fused_rhs": False})
-r3 = timeit("tcgen05 dense layers + fused stage combine", ours, {})
+def perlayer():
+    m.tensor_cores = True; torch.backends.cuda.matmul.allow_tf32 = False; m.chain = False
+def chained():
+    m.tensor_cores = True; torch.backends.cuda.matmul.allow_tf32 = False; m.chain = True
+r2 = timeit("tcgen05 per-layer, separate stage kernel", perlayer, {"fused_rhs": False})
+r2b = timeit("tcgen05 per-layer + fused stage combine", perlayer, {})
+ours = chained
+r3 = timeit("tcgen05 chained mlp3 + fused stage combine", ours, {})
 r4 = timeit("   ... + CUDA-graph replay", ours, {"cuda_graph": True})
 print("max|tc - fp32| = %.3e   max|torchTF32 - fp32| = %.3e   scale %.3f" % (float((r3 - r0).abs().max()), float((r1 - r0).abs().max()), float(r0.abs().max())))
+
+# func alone
+x = torch.randn(B, D, device=dev)
+for name, ch in (("per-layer", False), ("chained mlp3", True)):
+    m.tensor_cores = True; m.chain = ch
+    with torch.no_grad():
+        for _ in range(3): m(0.0, x)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(20): m(0.0, x)
+        b.record(); torch.cuda.synchronize()
+    us = a.elapsed_time(b) / 20 * 1e3
+    print("func eval %-14s %8.1f us   %6.1f TFLOP/s" % (name, us, 2.0 * B * (D * H + H * H + H * D) / us / 1e6))

@@ -145,3 +145,96 @@ def test_dense_mlp_trains_through_the_adjoint():
     out[-1].pow(2).mean().backward()
     assert all(p.grad is not None and bool(torch.isfinite(p.grad).all()) for p in m.parameters())
     assert y0.grad is not None
+
+
+# ---- the chained three-layer kernel (b2ode_mlp3) ------------------------------------------------------------------
+
+@torch.no_grad()
+def chain_reference(a, m, act):
+    h = reference(a, m.fc1.weight, m.fc1.bias, act).float()
+    h = reference(h, m.fc2.weight, m.fc2.bias, act).float()
+    return reference(h, m.fc3.weight, m.fc3.bias, 0)
+
+
+@pytest.mark.parametrize("M,D,H", [(128, 64, 256), (1000, 32, 64), (300, 16, 16), (257, 48, 80), (4096, 256, 256),
+                                   (148 * 128 * 2 + 77, 64, 128), (65, 112, 208)])
+@pytest.mark.parametrize("act", ["relu", "tanh"])
+def test_mlp3_matches_chained_tf32_reference(M, D, H, act):
+    import tfdiffeq_b200 as tfd
+    torch.manual_seed(M + D + H)
+    m = tfd.rhs.DenseMLP(D, H, act).to(DEV)
+    x = torch.randn(M, D, device=DEV)
+    out = tfd.rhs.mlp3(x, m.fc1, m.fc2, m.fc3, act)
+    torch.cuda.synchronize()
+    ref = chain_reference(x, m, {"relu": 1, "tanh": 2}[act])
+    err = float((out.double() - ref).abs().max())
+    # TF32 rounding of a hidden activation can flip on a 1-ulp fp32 difference in the accumulator: 2^-11 relative
+    # on one element of a K-term dot product
+    assert err <= 2e-3 * max(1.0, float(ref.abs().max())), err
+    # and it is the same function as the three separate tensor-core layers
+    h1 = tfd.rhs.dense_layer(x, m.fc1.weight, m.fc1.bias, act)
+    h2 = tfd.rhs.dense_layer(h1, m.fc2.weight, m.fc2.bias, act)
+    sep = tfd.rhs.dense_layer(h2, m.fc3.weight, m.fc3.bias, "none")
+    assert float((out - sep).abs().max()) <= 1e-5 * max(1.0, float(sep.abs().max()))
+
+
+def test_mlp3_with_fused_stage_combine_and_repeat_launches():
+    import tfdiffeq_b200 as tfd
+    L = lib()
+    torch.manual_seed(11)
+    M, D, H = 5000, 64, 256
+    m = tfd.rhs.DenseMLP(D, H, "relu").to(DEV)
+    y0 = torch.randn(M, D, device=DEV)
+    ks = [torch.randn(M, D, device=DEV) for _ in range(5)]
+    coefs = [9017 / 3168, -355 / 33, 46732 / 5247, 49 / 176, -5103 / 18656]
+    st = L.State()
+    st.dt = 0.0123
+    state = torch.frombuffer(bytearray(bytes(st)), dtype=torch.uint8).to(DEV)
+    ystage = torch.empty_like(y0)
+    outs = [tfd.rhs.mlp3(y0, m.fc1, m.fc2, m.fc3, "relu", stage=(ks, coefs, state.data_ptr(), ystage)) for _ in range(3)]
+    torch.cuda.synchronize()
+    dt32 = torch.tensor(st.dt, dtype=torch.float32)
+    acc = None
+    for c, k in zip(coefs, ks):
+        term = (dt32 * torch.tensor(c, dtype=torch.float32)).item() * k
+        acc = term if acc is None else acc + term
+    a = y0 + acc
+    assert torch.equal(ystage, a)
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    ref = chain_reference(a, m, 1)
+    assert float((outs[0].double() - ref).abs().max()) <= 2e-3 * max(1.0, float(ref.abs().max()))
+
+
+def test_mlp3_argument_checks_and_per_layer_fallback():
+    import tfdiffeq_b200 as tfd
+    L = lib()
+    x = torch.zeros(4, 24, device=DEV)
+    rc = L.lib.b2ode_mlp3(C.c_void_p(x.data_ptr()), None, None, 0, None, None, C.c_void_p(x.data_ptr()), None,
+                          C.c_void_p(x.data_ptr()), None, C.c_void_p(x.data_ptr()), None, C.c_void_p(x.data_ptr()),
+                          4, 24, 32, 0, None)
+    assert rc == -1 and b"multiples of 16" in L.lib.b2ode_last_error()
+    # widths beyond the activation tile fall back to the per-layer kernels
+    m = tfd.rhs.DenseMLP(32, 512, "relu").to(DEV)
+    assert not m.chained()
+    y = torch.randn(100, 32, device=DEV)
+    with torch.no_grad():
+        a = m(0.0, y)
+        m.tensor_cores = False
+        b = m(0.0, y)
+    assert float((a - b).abs().max()) <= 5e-3 * max(1.0, float(b.abs().max()))
+
+
+def test_dense_mlp_chained_equals_per_layer_through_odeint():
+    import tfdiffeq_b200 as tfd
+    torch.manual_seed(3)
+    m = tfd.rhs.DenseMLP(64, 128, "tanh").to(DEV)
+    y0 = torch.randn(2000, 64, device=DEV)
+    t = torch.tensor([0., 1.0])
+    kw = dict(rtol=1e-4, atol=1e-4, method="dopri5")
+    a = tfd.odeint(m, y0, t, **kw)
+    sa = dict(tfd.last_stats)
+    m.chain = False
+    b = tfd.odeint(m, y0, t, **kw)
+    sb = dict(tfd.last_stats)
+    assert abs(sa["n_accepted"] - sb["n_accepted"]) <= 1
+    assert float((a - b).abs().max()) <= 1e-3 * max(1.0, float(b.abs().max()))

@@ -515,6 +515,268 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_dense_layer_tf32_ws(const __g
 }
 
 // ================================================================================================
+// The whole ODENet-style func in ONE kernel: fc1 -> act -> fc2 -> act -> fc3 chained per 128-row tile, the hidden
+// activations never leave the SM.
+//
+//   ACT   : 128 rows x up to 256 TF32 columns of shared memory (128 KB), the A operand of whichever GEMM is running:
+//           first the (optionally stage-combined) input tile, then act(h1), then act(h2) -- each written in the K-major
+//           SWIZZLE_128B layout by the warps that produced it
+//   ring  : 2 stages x [N rows x 32 columns] of the current layer's weights (<= 32 KB each), streamed by cp.async
+//   TMEM  : acc0 (256 columns: GEMM1, later GEMM3), acc1 (256 columns: GEMM2)
+//   warps : 0-7 producers (input tile + weight stream), 8 MMA issuer, 9-12 epilogue (TMEM -> bias/act -> ACT or -> out)
+// HBM traffic per evaluation: the input tile(s) and the output tile -- (1 + nk) x 4D + 4D bytes per row instead of
+// 4(D + 4H + D) bytes per row through three separate layers.
+// ================================================================================================
+constexpr int kSub = 32;                                   // K columns per weight sub-chunk (one 128-byte swizzle row)
+constexpr int kActBytes = kTileM * 256 * 4;                // 128 KB
+constexpr int kRingStageBytes = 256 * 128;                 // 32 KB
+constexpr int kRingStages = 2;
+
+struct Mlp3Params {
+    DenseParams in;                    // x / k / coef / nk / st / ystage describe the input tile; W, bias, out, N unused here
+    const float *W1, *W2, *W3;         // [H, D], [H, H], [D, H] row-major, TF32-rounded
+    const float *b1, *b2, *b3;
+    float *out;                        // [M, D]
+    int M, D, H, act;
+};
+
+// bias + activation + TF32 rounding of one accumulator block, written as the next GEMM's A operand
+__device__ __forceinline__ void epilogue_to_act(uint8_t *act_buf, uint32_t tmem_acc, int q, int lane, int ncols, const float *bias,
+                                                int act) {
+    const int row = q * 32 + lane;
+    const int ncols_pad = (ncols + kSub - 1) / kSub * kSub;
+    for (int c0 = 0; c0 < ncols_pad; c0 += 32) {
+        uint32_t r[32];
+        const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+              "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+              "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+              "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+            : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        uint8_t *blk = act_buf + (c0 / kSub) * (kTileM * 128);          // K block of 32 columns: [128 rows x 128 B]
+#pragma unroll
+        for (int w = 0; w < 32; w += 4) {
+            uint32_t t[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int col = c0 + w + u;
+                float v = 0.f;
+                if (col < ncols) v = apply_act(__uint_as_float(r[w + u]) + (bias ? bias[col] : 0.f), act);
+                t[u] = to_tf32(v);
+            }
+            *reinterpret_cast<uint4 *>(blk + sw128_offset(row, w >> 2)) = make_uint4(t[0], t[1], t[2], t[3]);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kWsThreads, 1) k_mlp3_tf32(const __grid_constant__ Mlp3Params P) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t *act_buf = smem;                                             // 128 KB
+    uint8_t *ring = smem + kActBytes;                                    // 2 x 32 KB
+    float *tiles = reinterpret_cast<float *>(ring + kRingStages * kRingStageBytes);   // 4 x 32 x 33 floats (final transpose)
+    __shared__ __align__(8) uint64_t bar_full[kRingStages], bar_empty[kRingStages];
+    __shared__ __align__(8) uint64_t bar_a1, bar_actfree, bar_t1, bar_a2, bar_t2, bar_a3, bar_t3, bar_acc0free;
+    __shared__ uint32_t tmem_slot;
+
+    const DenseParams &p = P.in;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int D = P.D, H = P.H;
+    const int tiles_m = (P.M + kTileM - 1) / kTileM;
+    const int sub1 = (D + kSub - 1) / kSub, sub2 = (H + kSub - 1) / kSub, sub3 = sub2;   // weight sub-chunks per layer
+
+    if (warp == kProdWarps) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512u));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    if (tid == 0) {
+        auto init = [](uint64_t *b, unsigned n) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(n)); };
+        for (int i = 0; i < kRingStages; ++i) {
+            init(&bar_full[i], (unsigned)kProdThreads);
+            init(&bar_empty[i], 1u);
+        }
+        init(&bar_a1, (unsigned)kProdThreads);   // input tile written by the producers
+        init(&bar_actfree, 1u);                  // GEMM3 finished reading ACT (commit)
+        init(&bar_t1, 1u);
+        init(&bar_t2, 1u);
+        init(&bar_t3, 1u);
+        init(&bar_a2, 128u);                     // act(h1) written by the epilogue warps
+        init(&bar_a3, 128u);
+        init(&bar_acc0free, 128u);               // final epilogue drained acc0
+        asm volatile("fence.mbarrier_init.release.cluster;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const uint32_t tmem_base = tmem_slot;
+    const uint32_t acc0 = tmem_base, acc1 = tmem_base + 256u;
+
+    if (warp < kProdWarps) {
+        // ===== producers: input tile into ACT, then the weight stream of the three layers =====
+        float cf[kMaxNK];
+#pragma unroll
+        for (int j = 0; j < kMaxNK; ++j) cf[j] = 0.f;
+        if (p.nk > 0) {
+            const float dt = (float)p.st->dt;
+#pragma unroll
+            for (int j = 0; j < kMaxNK; ++j)
+                if (j < p.nk) cf[j] = __fmul_rn(dt, (float)p.coef[j]);
+        }
+        uint32_t it = 0, tcount = 0;
+        for (int tile = blockIdx.x; tile < tiles_m; tile += gridDim.x, ++tcount) {
+            const int m0 = tile * kTileM;
+            mbar_wait(smem_u32(&bar_actfree), (tcount & 1u) ^ 1u);         // previous tile's GEMM3 no longer reads ACT
+            // input tile: D columns in chunks of 64 (produce_chunk's layout = two 32-column K blocks of 16 KB each);
+            // the B half of produce_chunk is disabled by NT = 0
+            for (int kc = 0; kc < D; kc += kKChunk)
+                produce_chunk<kProdThreads>(p, act_buf + (kc / kSub) * (kTileM * 128), nullptr, m0, 0, 0, kc, tid, cf);
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive(smem_u32(&bar_a1));
+            // weights: layer l sub-chunk c = columns [32c, 32c+32) of W_l, all N_l rows
+            for (int l = 0; l < 3; ++l) {
+                const float *W = l == 0 ? P.W1 : (l == 1 ? P.W2 : P.W3);
+                const int Kl = l == 0 ? D : H, Nl = l == 2 ? D : H;
+                const int nsub = l == 0 ? sub1 : sub2;
+                for (int c = 0; c < nsub; ++c, ++it) {
+                    const uint32_t s = it % kRingStages, ph = (it / kRingStages) & 1u;
+                    mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);
+                    uint8_t *dstb = ring + s * kRingStageBytes;
+                    for (int f = tid; f < Nl * 8; f += kProdThreads) {      // 8 x 16-byte pieces per row
+                        const int row = f >> 3, piece = f & 7;
+                        const int gk = c * kSub + piece * 4;
+                        const float *src = W + (size_t)row * Kl + (gk < Kl ? gk : 0);
+                        const int nbytes = gk < Kl ? 16 : 0;
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dstb + sw128_offset(row, piece))),
+                                     "l"(src), "r"(nbytes)
+                                     : "memory");
+                    }
+                    asm volatile("cp.async.commit_group;" ::: "memory");
+                    asm volatile("cp.async.wait_group 0;" ::: "memory");
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    mbar_arrive(smem_u32(&bar_full[s]));
+                }
+            }
+        }
+    } else if (warp == kProdWarps) {
+        // ===== MMA issuer =====
+        uint32_t it = 0, tcount = 0;
+        for (int tile = blockIdx.x; tile < tiles_m; tile += gridDim.x, ++tcount) {
+            const uint32_t tp = tcount & 1u;
+            for (int l = 0; l < 3; ++l) {
+                const int Nl = l == 2 ? D : H;
+                const int nsub = l == 0 ? sub1 : sub2;
+                const uint32_t idesc = make_idesc_tf32(Nl);
+                const uint32_t tacc = l == 1 ? acc1 : acc0;
+                if (l == 0) {
+                    mbar_wait(smem_u32(&bar_acc0free), tp ^ 1u);           // final epilogue of the previous tile drained acc0
+                    mbar_wait(smem_u32(&bar_a1), tp);                      // input tile is in ACT
+                } else if (l == 1) {
+                    mbar_wait(smem_u32(&bar_a2), tp);                      // act(h1) is in ACT (and acc0 has been drained)
+                } else {
+                    mbar_wait(smem_u32(&bar_a3), tp);                      // act(h2) is in ACT
+                }
+                asm volatile("tcgen05.fence::after_thread_sync;");
+                for (int c = 0; c < nsub; ++c, ++it) {
+                    const uint32_t s = it % kRingStages, ph = (it / kRingStages) & 1u;
+                    mbar_wait(smem_u32(&bar_full[s]), ph);
+                    asm volatile("tcgen05.fence::after_thread_sync;");
+                    if (lane == 0) {
+                        const uint32_t a_blk = smem_u32(act_buf + c * (kTileM * 128));
+                        const uint32_t b_blk = smem_u32(ring + s * kRingStageBytes);
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks) {
+                            const uint64_t da = make_desc(a_blk + ks * 32), db = make_desc(b_blk + ks * 32);
+                            const uint32_t accum = (c > 0 || ks > 0) ? 1u : 0u;
+                            asm volatile(
+                                "{\n\t.reg .pred p;\n\t"
+                                "setp.ne.b32 p, %4, 0;\n\t"
+                                "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                                ::"r"(tacc), "l"(da), "l"(db), "r"(idesc), "r"(accum)
+                                : "memory");
+                        }
+                        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar_empty[s]))
+                                     : "memory");
+                        if (c == nsub - 1) {
+                            uint64_t *done = l == 0 ? &bar_t1 : (l == 1 ? &bar_t2 : &bar_t3);
+                            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(done))
+                                         : "memory");
+                            if (l == 2)
+                                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                                                 smem_u32(&bar_actfree))
+                                             : "memory");
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    } else {
+        // ===== epilogue warps =====
+        const int q = warp & 3;
+        float *tile_t = tiles + q * (32 * 33);
+        uint32_t tcount = 0;
+        for (int tile = blockIdx.x; tile < tiles_m; tile += gridDim.x, ++tcount) {
+            const uint32_t tp = tcount & 1u;
+            const int m0 = tile * kTileM;
+            // h1 -> ACT
+            mbar_wait(smem_u32(&bar_t1), tp);
+            asm volatile("tcgen05.fence::after_thread_sync;");
+            epilogue_to_act(act_buf, acc0, q, lane, H, P.b1, P.act);
+            asm volatile("tcgen05.fence::before_thread_sync;");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive(smem_u32(&bar_a2));
+            // h2 -> ACT
+            mbar_wait(smem_u32(&bar_t2), tp);
+            asm volatile("tcgen05.fence::after_thread_sync;");
+            epilogue_to_act(act_buf, acc1, q, lane, H, P.b2, P.act);
+            asm volatile("tcgen05.fence::before_thread_sync;");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive(smem_u32(&bar_a3));
+            // output: acc0 (D columns) -> transposed -> global rows
+            mbar_wait(smem_u32(&bar_t3), tp);
+            asm volatile("tcgen05.fence::after_thread_sync;");
+            const int row0 = m0 + q * 32;
+            for (int c0 = 0; c0 < D; c0 += 32) {
+                uint32_t r[32];
+                const uint32_t taddr = acc0 + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                      "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+                      "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+                      "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                    : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                __syncwarp();
+#pragma unroll
+                for (int w = 0; w < 32; ++w) tile_t[lane * 33 + w] = __uint_as_float(r[w]);
+                __syncwarp();
+                const int col = c0 + lane;
+                const bool col_ok = col < D;
+                const float bv = (P.b3 && col_ok) ? P.b3[col] : 0.f;
+                float *dst = P.out + (size_t)row0 * D + col;
+#pragma unroll 8
+                for (int rr = 0; rr < 32; ++rr)
+                    if (col_ok && row0 + rr < P.M) dst[(size_t)rr * D] = tile_t[rr * 33 + lane] + bv;
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;");
+            mbar_arrive(smem_u32(&bar_acc0free));
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    if (warp == kProdWarps) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+}
+
+// ================================================================================================
 // host side
 // ================================================================================================
 extern "C" int b2ode_dense_layer(const void *x, const void *const *k, const double *coef, int nk, const void *state,
@@ -572,6 +834,59 @@ extern "C" int b2ode_dense_layer(const void *x, const void *const *k, const doub
         const int grid = (int)(items < sms ? items : sms);                 // persistent: one CTA per SM
         k_dense_layer_tf32_ws<<<grid, kWsThreads, smem, (cudaStream_t)cuda_stream>>>(p);
     }
+    B2_CUDA(cudaGetLastError());
+    b2_count_launch();
+    return 0;
+}
+
+// fc1 -> act -> fc2 -> act -> fc3 in one launch (tfdiffeq/models/dense_odenet.py:85-92); see k_mlp3_tf32.
+extern "C" int b2ode_mlp3(const void *x, const void *const *k, const double *coef, int nk, const void *state, void *ystage,
+                          const void *W1, const void *b1, const void *W2, const void *b2, const void *W3, const void *b3, void *out,
+                          int64_t M, int D, int H, int act, void *cuda_stream) {
+    if (!x || !W1 || !W2 || !W3 || !out || M < 1) return b2_fail(B2ODE_EINVAL, "bad mlp3 arguments");
+    if (D < 16 || H < 16 || D > 256 || H > 256 || D % 16 || H % 16)
+        return b2_fail(B2ODE_EINVAL, "mlp3: dim and hidden must be multiples of 16 in [16, 256] (got %d, %d)", D, H);
+    if (nk < 0 || nk > kMaxNK || (nk > 0 && (!k || !coef || !state))) return b2_fail(B2ODE_EINVAL, "bad stage-combine arguments");
+    if (act < 0 || act > 3) return b2_fail(B2ODE_EINVAL, "unknown activation %d", act);
+    if (M > (int64_t)2147483647 - kTileM) return b2_fail(B2ODE_EINVAL, "M too large");
+    Mlp3Params P;
+    memset(&P, 0, sizeof(P));
+    P.in.x = (const float *)x;
+    for (int j = 0; j < nk; ++j) {
+        if (!k[j]) return b2_fail(B2ODE_EINVAL, "k[%d] is null", j);
+        P.in.k[j] = (const float *)k[j];
+        P.in.coef[j] = coef[j];
+    }
+    P.in.nk = nk;
+    P.in.st = (const b2ode_state *)state;
+    P.in.ystage = (float *)ystage;
+    P.in.M = (int)M;
+    P.in.K = D;
+    P.in.N = H;
+    P.W1 = (const float *)W1;
+    P.W2 = (const float *)W2;
+    P.W3 = (const float *)W3;
+    P.b1 = (const float *)b1;
+    P.b2 = (const float *)b2;
+    P.b3 = (const float *)b3;
+    P.out = (float *)out;
+    P.M = (int)M;
+    P.D = D;
+    P.H = H;
+    P.act = act;
+    const size_t smem = (size_t)kActBytes + kRingStages * kRingStageBytes + 4 * 32 * 33 * sizeof(float) + 1024;
+    static bool configured = false;
+    static int sms = 0;
+    if (!configured) {
+        B2_CUDA(cudaFuncSetAttribute(k_mlp3_tf32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int dev = 0;
+        B2_CUDA(cudaGetDevice(&dev));
+        B2_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        configured = true;
+    }
+    const long long tiles = (M + kTileM - 1) / kTileM;
+    const int grid = (int)(tiles < sms ? tiles : sms);
+    k_mlp3_tf32<<<grid, kWsThreads, smem, (cudaStream_t)cuda_stream>>>(P);
     B2_CUDA(cudaGetLastError());
     b2_count_launch();
     return 0;

@@ -132,6 +132,31 @@ def dense_layer(x, weight, bias, act="none", stage=None):
     return out
 
 
+def mlp3(x, fc1, fc2, fc3, act="relu", stage=None):
+    """``fc3(act(fc2(act(fc1(x)))))`` in one launch (``b2ode_mlp3``): hidden activations never reach HBM.
+    ``stage`` as in :func:`dense_layer`."""
+    import ctypes as C
+    M, D = x.shape
+    H = fc1.weight.shape[0]
+    out = torch.empty((M, D), dtype=torch.float32, device=x.device)
+    karr = carr = state = ys = None
+    nk = 0
+    if stage is not None:
+        ks, coefs, state, ys = stage
+        nk = len(ks)
+        karr = (C.c_void_p * nk)(*[k.data_ptr() for k in ks])
+        carr = (C.c_double * nk)(*coefs)
+
+    def ptr(t):
+        return C.c_void_p(t.data_ptr()) if t is not None else None
+    _lib.check(_lib.lib.b2ode_mlp3(
+        ptr(x), karr, carr, nk, C.c_void_p(state) if state else None, ptr(ys),
+        ptr(_tf32_weight(fc1.weight)), ptr(fc1.bias), ptr(_tf32_weight(fc2.weight)), ptr(fc2.bias),
+        ptr(_tf32_weight(fc3.weight)), ptr(fc3.bias), ptr(out), M, D, H, _ACT[act],
+        C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)))
+    return out
+
+
 class DenseMLP(nn.Module):
     """The reference's ``ODEFunc`` (tfdiffeq/models/dense_odenet.py:11-92, time-independent form): fc1 -> act ->
     fc2 -> act -> fc3 on a ``(batch, dim)`` state, counting ``nfe`` like the reference does (:78).
@@ -142,7 +167,7 @@ class DenseMLP(nn.Module):
     HBM for the GEMM).  With autograd enabled (training, ``odeint_adjoint``'s VJPs) it is plain torch.
     ``tensor_cores=False`` forces plain torch everywhere."""
 
-    def __init__(self, dim, hidden, non_linearity="relu", tensor_cores=True, dtype=torch.float32):
+    def __init__(self, dim, hidden, non_linearity="relu", tensor_cores=True, dtype=torch.float32, chain=True):
         super(DenseMLP, self).__init__()
         if non_linearity not in ("relu", "tanh", "softplus"):
             raise ValueError("non_linearity must be relu, tanh or softplus")
@@ -151,11 +176,16 @@ class DenseMLP(nn.Module):
         self.fc2 = nn.Linear(hidden, hidden, dtype=dtype)
         self.fc3 = nn.Linear(hidden, dim, dtype=dtype)
         self.nfe = 0
+        self.chain = chain
 
     def uses_tensor_cores(self, x):
         return (self.tensor_cores and x.is_cuda and x.dtype == torch.float32 and not torch.is_grad_enabled()
                 and self.fc1.weight.dtype == torch.float32 and self.dim % 16 == 0 and self.hidden % 16 == 0
                 and x.shape[-1] == self.dim)
+
+    def chained(self):
+        """One-launch form (``b2ode_mlp3``) when both widths fit the 128 KB activation tile."""
+        return self.chain and self.dim <= 256 and self.hidden <= 256
 
     def _tail(self, h1):
         h2 = dense_layer(h1, self.fc2.weight, self.fc2.bias, self.non_linearity)
@@ -164,6 +194,8 @@ class DenseMLP(nn.Module):
     def forward_from_stage(self, y0, ks, coefs, state_ptr, ystage):
         """First layer fed by the stage combine of y0 and the k's (all ``(batch, dim)`` fp32 CUDA tensors)."""
         self.nfe += 1
+        if self.chained():
+            return mlp3(y0, self.fc1, self.fc2, self.fc3, self.non_linearity, stage=(ks, coefs, state_ptr, ystage))
         h1 = dense_layer(y0, self.fc1.weight, self.fc1.bias, self.non_linearity, stage=(ks, coefs, state_ptr, ystage))
         return self._tail(h1)
 
@@ -173,6 +205,8 @@ class DenseMLP(nn.Module):
             x2 = x.reshape(-1, self.dim)
             if not x2.is_contiguous():
                 x2 = x2.contiguous()
+            if self.chained():
+                return mlp3(x2, self.fc1, self.fc2, self.fc3, self.non_linearity).reshape(x.shape)
             h1 = dense_layer(x2, self.fc1.weight, self.fc1.bias, self.non_linearity)
             return self._tail(h1).reshape(x.shape)
         act = {"relu": torch.relu, "tanh": torch.tanh, "softplus": torch.nn.functional.softplus}[self.non_linearity]
