@@ -236,11 +236,17 @@ int b2ode_dense_layer(const void *x, const void *const *k, const double *coef, i
 /* The whole three-layer func (dense_odenet.py:85-92: fc1 -> act -> fc2 -> act -> fc3) in ONE launch: per 128-row
  * tile the hidden activations stay in shared memory / TMEM, so an evaluation moves only the input tile(s) and the
  * output tile through HBM.  out[M, D] = W3 . act(W2 . act(W1 . A + b1) + b2) + b3 with A as in b2ode_dense_layer
- * (x, or the stage combine of x and k[0..nk)).  W1 [H, D], W2 [H, H], W3 [D, H]; D and H multiples of 16 in
- * [16, 256].  Weights must already be TF32-rounded (low 13 mantissa bits zero). */
+ * (x, or the stage combine of x and k[0..nk)).  W1 [H, D], W2 [H, H], W3 [D, H] in nn.Linear layout; D and H
+ * multiples of 16 in [16, 256].
+ *   b2ode_mlp3_packed_bytes : size of the packed weight image (-1 for unsupported widths)
+ *   b2ode_mlp3_pack         : rounds the weights to TF32 and lays them out as the kernel's shared-memory image
+ *                             (once per weight version; `packed` is caller-owned device memory, 16-byte aligned)
+ *   b2ode_mlp3              : one evaluation */
+int64_t b2ode_mlp3_packed_bytes(int D, int H);
+int b2ode_mlp3_pack(const void *W1, const void *W2, const void *W3, int D, int H, void *packed, void *cuda_stream);
 int b2ode_mlp3(const void *x, const void *const *k, const double *coef, int nk, const void *state, void *ystage,
-               const void *W1, const void *b1, const void *W2, const void *b2, const void *W3, const void *b3, void *out,
-               int64_t M, int D, int H, int act, void *cuda_stream);
+               const void *packed, const void *b1, const void *b2, const void *b3, void *out, int64_t M, int D, int H,
+               int act, void *cuda_stream);
 
 /* ---- measurement hooks (bench.py) --------------------------------------------------------------------- */
 unsigned long long b2ode_launch_count(void);            /* kernels launched by this library so far          */

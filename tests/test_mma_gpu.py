@@ -209,10 +209,11 @@ def test_mlp3_argument_checks_and_per_layer_fallback():
     import tfdiffeq_b200 as tfd
     L = lib()
     x = torch.zeros(4, 24, device=DEV)
-    rc = L.lib.b2ode_mlp3(C.c_void_p(x.data_ptr()), None, None, 0, None, None, C.c_void_p(x.data_ptr()), None,
-                          C.c_void_p(x.data_ptr()), None, C.c_void_p(x.data_ptr()), None, C.c_void_p(x.data_ptr()),
-                          4, 24, 32, 0, None)
+    rc = L.lib.b2ode_mlp3(C.c_void_p(x.data_ptr()), None, None, 0, None, None, C.c_void_p(x.data_ptr()), None, None, None,
+                          C.c_void_p(x.data_ptr()), 4, 24, 32, 0, None)
     assert rc == -1 and b"multiples of 16" in L.lib.b2ode_last_error()
+    assert L.lib.b2ode_mlp3_packed_bytes(24, 32) == -1
+    assert L.lib.b2ode_mlp3_packed_bytes(64, 256) == (2 * 256 + 8 * 256 + 8 * 64) * 128
     # widths beyond the activation tile fall back to the per-layer kernels
     m = tfd.rhs.DenseMLP(32, 512, "relu").to(DEV)
     assert not m.chained()
@@ -238,3 +239,18 @@ def test_dense_mlp_chained_equals_per_layer_through_odeint():
     sb = dict(tfd.last_stats)
     assert abs(sa["n_accepted"] - sb["n_accepted"]) <= 1
     assert float((a - b).abs().max()) <= 1e-3 * max(1.0, float(b.abs().max()))
+
+
+def test_mlp3_repacks_when_a_weight_changes():
+    import tfdiffeq_b200 as tfd
+    torch.manual_seed(4)
+    m = tfd.rhs.DenseMLP(32, 64, "relu").to(DEV)
+    x = torch.randn(300, 32, device=DEV)
+    with torch.no_grad():
+        a = m(0.0, x).clone()
+        m.fc2.weight.mul_(0.5)
+        b = m(0.0, x)
+        m.tensor_cores = False
+        ref = m(0.0, x)
+    assert not torch.equal(a, b)
+    assert float((b - ref).abs().max()) <= 5e-3 * max(1.0, float(ref.abs().max()))

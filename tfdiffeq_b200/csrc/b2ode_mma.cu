@@ -87,6 +87,24 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     } while (!ok);
 }
 
+// compile-time activation: a run-time switch inlined per element bloats the unrolled epilogues past the
+// instruction cache (tanhf + log1pf/expf bodies 32 times over) even when only the relu branch ever executes
+template <int ACT>
+__device__ __forceinline__ float act_t(float v) {
+    if (ACT == 1) return v > 0.f ? v : 0.f;
+    if (ACT == 2) return tanhf(v);
+    if (ACT == 3) return (v > 20.f) ? v : log1pf(expf(v));
+    return v;
+}
+
+// one output column of a transposed 32 x 32 block: bias + activation, one 128-byte line per warp store
+template <int ACT>
+__device__ __forceinline__ void store_column_t(float *dst, const float *tile, int lane, float bv, int ld, int nrows) {
+#pragma unroll 8
+    for (int rr = 0; rr < 32; ++rr)
+        if (rr < nrows) dst[(size_t)rr * ld] = act_t<ACT>(tile[rr * 33 + lane] + bv);
+}
+
 __device__ __forceinline__ float apply_act(float v, int act) {
     if (act == 1) return v > 0.f ? v : 0.f;
     if (act == 2) return tanhf(v);
@@ -500,9 +518,14 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_dense_layer_tf32_ws(const __g
                 const bool col_ok = col < NT;
                 const float bv = (p.bias && col_ok) ? p.bias[n0 + col] : 0.f;
                 float *dst = p.out + (size_t)row0 * p.N + n0 + col;
-#pragma unroll 8
-                for (int rr = 0; rr < 32; ++rr) {
-                    if (col_ok && row0 + rr < p.M) dst[(size_t)rr * p.N] = apply_act(tile[rr * 33 + lane] + bv, p.act);
+                if (col_ok) {
+                    const int nrows = p.M - row0 < 32 ? p.M - row0 : 32;
+                    switch (p.act) {
+                        case 1: store_column_t<1>(dst, tile, lane, bv, p.N, nrows); break;
+                        case 2: store_column_t<2>(dst, tile, lane, bv, p.N, nrows); break;
+                        case 3: store_column_t<3>(dst, tile, lane, bv, p.N, nrows); break;
+                        default: store_column_t<0>(dst, tile, lane, bv, p.N, nrows); break;
+                    }
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;");
@@ -518,31 +541,157 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_dense_layer_tf32_ws(const __g
 // The whole ODENet-style func in ONE kernel: fc1 -> act -> fc2 -> act -> fc3 chained per 128-row tile, the hidden
 // activations never leave the SM.
 //
-//   ACT   : 128 rows x up to 256 TF32 columns of shared memory (128 KB), the A operand of whichever GEMM is running:
+//   ACT   : 128 rows x up to 256 TF32 columns of shared memory (<= 128 KB), the A operand of whichever GEMM is running:
 //           first the (optionally stage-combined) input tile, then act(h1), then act(h2) -- each written in the K-major
 //           SWIZZLE_128B layout by the warps that produced it
-//   ring  : 2 stages x [N rows x 32 columns] of the current layer's weights (<= 32 KB each), streamed by cp.async
+//   ring  : S stages x [N rows x 32 columns] of the current layer's weights.  The weights are packed ONCE per weight
+//           version (k_mlp3_pack) into exactly this shared-memory image -- TF32-rounded, swizzled, zero-padded -- so one
+//           thread streams them with cp.async.bulk (the TMA engine's linear mode) and an mbarrier transaction count
 //   TMEM  : acc0 (256 columns: GEMM1, later GEMM3), acc1 (256 columns: GEMM2)
-//   warps : 0-7 producers (input tile + weight stream), 8 MMA issuer, 9-12 epilogue (TMEM -> bias/act -> ACT or -> out)
+//   warps : 0-7 input producers (the next tile is loaded and stage-combined into REGISTERS while the current tile is in
+//           its GEMMs, then dropped into ACT the moment GEMM3 releases it), 8 MMA issuer, 9-12 epilogue
+//           (TMEM -> bias/act -> ACT, or -> out), 13 weight loader
 // HBM traffic per evaluation: the input tile(s) and the output tile -- (1 + nk) x 4D + 4D bytes per row instead of
-// 4(D + 4H + D) bytes per row through three separate layers.
+// 4(D + 4H + D) bytes per row through three separate layers; the weights stream from L2.
 // ================================================================================================
 constexpr int kSub = 32;                                   // K columns per weight sub-chunk (one 128-byte swizzle row)
-constexpr int kActBytes = kTileM * 256 * 4;                // 128 KB
-constexpr int kRingStageBytes = 256 * 128;                 // 32 KB
-constexpr int kRingStages = 2;
+constexpr int kChainThreads = (kProdWarps + 1 + 4 + 1) * 32;
+constexpr int kLoaderWarp = kProdWarps + 5;
+constexpr int kMaxRing = 8;
+constexpr int kTileScratchBytes = 4 * 32 * 33 * 4;         // the output epilogue's transposition tiles
 
 struct Mlp3Params {
-    DenseParams in;                    // x / k / coef / nk / st / ystage describe the input tile; W, bias, out, N unused here
-    const float *W1, *W2, *W3;         // [H, D], [H, H], [D, H] row-major, TF32-rounded
+    DenseParams in;                    // x / k / coef / nk / st / ystage / M / K(= D) describe the input tile
+    const uint8_t *packed;             // k_mlp3_pack's image: layer 1 sub-chunks, layer 2, layer 3
     const float *b1, *b2, *b3;
     float *out;                        // [M, D]
     int M, D, H, act;
+    int act_bytes, stage_bytes, stages;
 };
 
-// bias + activation + TF32 rounding of one accumulator block, written as the next GEMM's A operand
-__device__ __forceinline__ void epilogue_to_act(uint8_t *act_buf, uint32_t tmem_acc, int q, int lane, int ncols, const float *bias,
-                                                int act) {
+__host__ __device__ inline int mlp3_subs(int K) { return (K + kSub - 1) / kSub; }
+__host__ __device__ inline size_t mlp3_layer_bytes(int N, int K) { return (size_t)mlp3_subs(K) * N * 128; }
+
+// TF32-round, swizzle and zero-pad W[N, K] into sub-chunk images of [N rows x 128 B]
+__global__ void k_mlp3_pack(const float *W1, const float *W2, const float *W3, int D, int H, uint8_t *packed) {
+    const size_t n1 = mlp3_layer_bytes(H, D) / 16, n2 = mlp3_layer_bytes(H, H) / 16, n3 = mlp3_layer_bytes(D, H) / 16;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n1 + n2 + n3; i += (size_t)gridDim.x * blockDim.x) {
+        const float *W;
+        int N, K;
+        size_t j = i;
+        if (j < n1) {
+            W = W1, N = H, K = D;
+        } else if (j < n1 + n2) {
+            W = W2, N = H, K = H, j -= n1;
+        } else {
+            W = W3, N = D, K = H, j -= n1 + n2;
+        }
+        const int q = (int)(j & 7);                       // 16-byte slot inside the 128-byte row of the image
+        const int row = (int)((j >> 3) % N);
+        const int c = (int)((j >> 3) / N);
+        const int piece = q ^ (row & 7);                  // which 4 source columns live in that slot (Swizzle<3,4,3>)
+        uint32_t e[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int gk = c * kSub + piece * 4 + u;
+            e[u] = gk < K ? to_tf32(W[(size_t)row * K + gk]) : 0u;
+        }
+        reinterpret_cast<uint4 *>(packed)[i] = make_uint4(e[0], e[1], e[2], e[3]);
+    }
+}
+
+#ifdef B2ODE_TRACE
+__device__ unsigned long long g_mlp3_trace[16 * 16];
+__device__ __forceinline__ void trace(int tile_no, int slot) {
+    if (blockIdx.x == 0 && tile_no < 16) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g_mlp3_trace[tile_no * 16 + slot] = t;
+    }
+}
+#define TRACE(tile_no, slot) trace((int)(tile_no), slot)
+#else
+#define TRACE(tile_no, slot)
+#endif
+
+// ---- input tile (D <= 64: one 64-column chunk) loaded and stage-combined into registers ----
+template <int NK>
+__device__ __forceinline__ void load_tile_regs_t(const DenseParams &p, int m0, int tid, const float (&cf)[kMaxNK], float4 (&v)[8]) {
+    constexpr int BQ = NK >= 4 ? 2 : 4;
+#pragma unroll
+    for (int b0 = 0; b0 < 8; b0 += BQ) {
+        float4 kv[NK > 0 ? NK : 1][BQ];
+        size_t off[BQ];
+        bool in[BQ];
+#pragma unroll
+        for (int q = 0; q < BQ; ++q) {
+            const int f = tid + (b0 + q) * kProdThreads;
+            const int row = f >> 4, c4 = f & 15;
+            const int gm = m0 + row, gk = c4 * 4;
+            in[q] = gm < p.M && gk < p.K;
+            off[q] = in[q] ? (size_t)gm * p.K + gk : 0;
+        }
+#pragma unroll
+        for (int q = 0; q < BQ; ++q)
+            v[b0 + q] = in[q] ? *reinterpret_cast<const float4 *>(p.x + off[q]) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < NK; ++j)
+#pragma unroll
+            for (int q = 0; q < BQ; ++q)
+                kv[j][q] = in[q] ? *reinterpret_cast<const float4 *>(p.k[j] + off[q]) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (NK > 0) {
+#pragma unroll
+            for (int q = 0; q < BQ; ++q) {
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int j = 0; j < NK; ++j) {
+                    const float c = cf[j];
+                    const float tx = __fmul_rn(c, kv[j][q].x), ty = __fmul_rn(c, kv[j][q].y);
+                    const float tz = __fmul_rn(c, kv[j][q].z), tw = __fmul_rn(c, kv[j][q].w);
+                    acc.x = j ? __fadd_rn(acc.x, tx) : tx;
+                    acc.y = j ? __fadd_rn(acc.y, ty) : ty;
+                    acc.z = j ? __fadd_rn(acc.z, tz) : tz;
+                    acc.w = j ? __fadd_rn(acc.w, tw) : tw;
+                }
+                float4 &r = v[b0 + q];
+                r.x = __fadd_rn(r.x, acc.x);
+                r.y = __fadd_rn(r.y, acc.y);
+                r.z = __fadd_rn(r.z, acc.z);
+                r.w = __fadd_rn(r.w, acc.w);
+                if (p.ystage && in[q]) *reinterpret_cast<float4 *>(p.ystage + off[q]) = r;
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ void load_tile_regs(const DenseParams &p, int m0, int tid, const float (&cf)[kMaxNK], float4 (&v)[8]) {
+    switch (p.nk) {
+        case 0: load_tile_regs_t<0>(p, m0, tid, cf, v); break;
+        case 1: load_tile_regs_t<1>(p, m0, tid, cf, v); break;
+        case 2: load_tile_regs_t<2>(p, m0, tid, cf, v); break;
+        case 3: load_tile_regs_t<3>(p, m0, tid, cf, v); break;
+        case 4: load_tile_regs_t<4>(p, m0, tid, cf, v); break;
+        case 5: load_tile_regs_t<5>(p, m0, tid, cf, v); break;
+        case 6: load_tile_regs_t<6>(p, m0, tid, cf, v); break;
+        case 7: load_tile_regs_t<7>(p, m0, tid, cf, v); break;
+        default: load_tile_regs_t<8>(p, m0, tid, cf, v); break;
+    }
+}
+
+__device__ __forceinline__ void store_tile_regs(uint8_t *act_buf, int tid, const float4 (&v)[8]) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int f = tid + i * kProdThreads;
+        const int row = f >> 4, c4 = f & 15;
+        const uint4 t = make_uint4(to_tf32(v[i].x), to_tf32(v[i].y), to_tf32(v[i].z), to_tf32(v[i].w));
+        *reinterpret_cast<uint4 *>(act_buf + (c4 >> 3) * (kTileM * 128) + sw128_offset(row, c4 & 7)) = t;
+    }
+}
+
+// bias + activation + TF32 rounding of one accumulator block, written as the next GEMM's A operand.
+// `bias` is the shared-memory copy (zero-filled when the layer has none, padded to a multiple of 32).
+template <int ACT>
+__device__ __noinline__ void epilogue_to_act_t(uint8_t *act_buf, uint32_t tmem_acc, int q, int lane, int ncols, const float *bias) {
     const int row = q * 32 + lane;
     const int ncols_pad = (ncols + kSub - 1) / kSub * kSub;
     for (int c0 = 0; c0 < ncols_pad; c0 += 32) {
@@ -561,34 +710,49 @@ __device__ __forceinline__ void epilogue_to_act(uint8_t *act_buf, uint32_t tmem_
         uint8_t *blk = act_buf + (c0 / kSub) * (kTileM * 128);          // K block of 32 columns: [128 rows x 128 B]
 #pragma unroll
         for (int w = 0; w < 32; w += 4) {
+            const float4 bv = *reinterpret_cast<const float4 *>(bias + c0 + w);       // broadcast read
             uint32_t t[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int col = c0 + w + u;
-                float v = 0.f;
-                if (col < ncols) v = apply_act(__uint_as_float(r[w + u]) + (bias ? bias[col] : 0.f), act);
-                t[u] = to_tf32(v);
-            }
+            t[0] = (c0 + w + 0 < ncols) ? to_tf32(act_t<ACT>(__uint_as_float(r[w + 0]) + bv.x)) : 0u;
+            t[1] = (c0 + w + 1 < ncols) ? to_tf32(act_t<ACT>(__uint_as_float(r[w + 1]) + bv.y)) : 0u;
+            t[2] = (c0 + w + 2 < ncols) ? to_tf32(act_t<ACT>(__uint_as_float(r[w + 2]) + bv.z)) : 0u;
+            t[3] = (c0 + w + 3 < ncols) ? to_tf32(act_t<ACT>(__uint_as_float(r[w + 3]) + bv.w)) : 0u;
             *reinterpret_cast<uint4 *>(blk + sw128_offset(row, w >> 2)) = make_uint4(t[0], t[1], t[2], t[3]);
         }
     }
 }
 
-__global__ void __launch_bounds__(kWsThreads, 1) k_mlp3_tf32(const __grid_constant__ Mlp3Params P) {
+__device__ __forceinline__ void epilogue_to_act(uint8_t *act_buf, uint32_t tmem_acc, int q, int lane, int ncols, const float *bias,
+                                                int act) {
+    switch (act) {
+        case 1: epilogue_to_act_t<1>(act_buf, tmem_acc, q, lane, ncols, bias); break;
+        case 2: epilogue_to_act_t<2>(act_buf, tmem_acc, q, lane, ncols, bias); break;
+        case 3: epilogue_to_act_t<3>(act_buf, tmem_acc, q, lane, ncols, bias); break;
+        default: epilogue_to_act_t<0>(act_buf, tmem_acc, q, lane, ncols, bias); break;
+    }
+}
+
+__global__ void __launch_bounds__(kChainThreads, 1) k_mlp3_tf32(const __grid_constant__ Mlp3Params P) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint8_t *act_buf = smem;                                             // 128 KB
-    uint8_t *ring = smem + kActBytes;                                    // 2 x 32 KB
-    float *tiles = reinterpret_cast<float *>(ring + kRingStages * kRingStageBytes);   // 4 x 32 x 33 floats (final transpose)
-    __shared__ __align__(8) uint64_t bar_full[kRingStages], bar_empty[kRingStages];
+    uint8_t *act_buf = smem;
+    uint8_t *ring = smem + P.act_bytes;
+    float *tiles = reinterpret_cast<float *>(ring + (size_t)P.stages * P.stage_bytes);
+    __shared__ __align__(8) uint64_t bar_full[kMaxRing], bar_empty[kMaxRing];
     __shared__ __align__(8) uint64_t bar_a1, bar_actfree, bar_t1, bar_a2, bar_t2, bar_a3, bar_t3, bar_acc0free;
     __shared__ uint32_t tmem_slot;
+    __shared__ __align__(16) float sbias[3][256];
 
     const DenseParams &p = P.in;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int D = P.D, H = P.H;
+    for (int i = tid; i < 3 * 256; i += kChainThreads) {
+        const int l = i >> 8, c = i & 255;
+        const float *b = l == 0 ? P.b1 : (l == 1 ? P.b2 : P.b3);
+        sbias[l][c] = (b && c < (l == 2 ? D : H)) ? b[c] : 0.f;
+    }
     const int tiles_m = (P.M + kTileM - 1) / kTileM;
-    const int sub1 = (D + kSub - 1) / kSub, sub2 = (H + kSub - 1) / kSub, sub3 = sub2;   // weight sub-chunks per layer
+    const int sub1 = mlp3_subs(D), sub2 = mlp3_subs(H);
+    const uint32_t S = (uint32_t)P.stages;
 
     if (warp == kProdWarps) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512u));
@@ -596,9 +760,9 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_mlp3_tf32(const __grid_consta
     }
     if (tid == 0) {
         auto init = [](uint64_t *b, unsigned n) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(n)); };
-        for (int i = 0; i < kRingStages; ++i) {
-            init(&bar_full[i], (unsigned)kProdThreads);
-            init(&bar_empty[i], 1u);
+        for (int i = 0; i < kMaxRing; ++i) {
+            init(&bar_full[i], 1u);              // the loader's expect_tx arrive; the bytes complete the phase
+            init(&bar_empty[i], 1u);             // tcgen05.commit
         }
         init(&bar_a1, (unsigned)kProdThreads);   // input tile written by the producers
         init(&bar_actfree, 1u);                  // GEMM3 finished reading ACT (commit)
@@ -617,7 +781,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_mlp3_tf32(const __grid_consta
     const uint32_t acc0 = tmem_base, acc1 = tmem_base + 256u;
 
     if (warp < kProdWarps) {
-        // ===== producers: input tile into ACT, then the weight stream of the three layers =====
+        // ===== input producers =====
         float cf[kMaxNK];
 #pragma unroll
         for (int j = 0; j < kMaxNK; ++j) cf[j] = 0.f;
@@ -627,39 +791,50 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_mlp3_tf32(const __grid_consta
             for (int j = 0; j < kMaxNK; ++j)
                 if (j < p.nk) cf[j] = __fmul_rn(dt, (float)p.coef[j]);
         }
-        uint32_t it = 0, tcount = 0;
+        const bool prefetch = D <= kKChunk && (D & 3) == 0;
+        uint32_t tcount = 0;
         for (int tile = blockIdx.x; tile < tiles_m; tile += gridDim.x, ++tcount) {
             const int m0 = tile * kTileM;
-            mbar_wait(smem_u32(&bar_actfree), (tcount & 1u) ^ 1u);         // previous tile's GEMM3 no longer reads ACT
-            // input tile: D columns in chunks of 64 (produce_chunk's layout = two 32-column K blocks of 16 KB each);
-            // the B half of produce_chunk is disabled by NT = 0
-            for (int kc = 0; kc < D; kc += kKChunk)
-                produce_chunk<kProdThreads>(p, act_buf + (kc / kSub) * (kTileM * 128), nullptr, m0, 0, 0, kc, tid, cf);
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            if (prefetch) {
+                float4 v[8];
+                load_tile_regs(p, m0, tid, cf, v);                         // overlaps the previous tile's GEMMs
+                TRACE(tcount, 0);
+                mbar_wait(smem_u32(&bar_actfree), (tcount & 1u) ^ 1u);     // previous tile's GEMM3 no longer reads ACT
+                TRACE(tcount, 1);
+                store_tile_regs(act_buf, tid, v);
+            } else {
+                mbar_wait(smem_u32(&bar_actfree), (tcount & 1u) ^ 1u);
+                for (int kc = 0; kc < D; kc += kKChunk)
+                    produce_chunk<kProdThreads>(p, act_buf + (kc / kSub) * (kTileM * 128), nullptr, m0, 0, 0, kc, tid, cf);
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+            }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_arrive(smem_u32(&bar_a1));
-            // weights: layer l sub-chunk c = columns [32c, 32c+32) of W_l, all N_l rows
-            for (int l = 0; l < 3; ++l) {
-                const float *W = l == 0 ? P.W1 : (l == 1 ? P.W2 : P.W3);
-                const int Kl = l == 0 ? D : H, Nl = l == 2 ? D : H;
-                const int nsub = l == 0 ? sub1 : sub2;
-                for (int c = 0; c < nsub; ++c, ++it) {
-                    const uint32_t s = it % kRingStages, ph = (it / kRingStages) & 1u;
-                    mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);
-                    uint8_t *dstb = ring + s * kRingStageBytes;
-                    for (int f = tid; f < Nl * 8; f += kProdThreads) {      // 8 x 16-byte pieces per row
-                        const int row = f >> 3, piece = f & 7;
-                        const int gk = c * kSub + piece * 4;
-                        const float *src = W + (size_t)row * Kl + (gk < Kl ? gk : 0);
-                        const int nbytes = gk < Kl ? 16 : 0;
-                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dstb + sw128_offset(row, piece))),
-                                     "l"(src), "r"(nbytes)
-                                     : "memory");
+            TRACE(tcount, 2);
+        }
+    } else if (warp == kLoaderWarp) {
+        // ===== weight loader: one bulk copy per sub-chunk, completion counted in bytes on the stage's mbarrier =====
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < tiles_m; tile += gridDim.x) {
+                const uint8_t *src = P.packed;
+                for (int l = 0; l < 3; ++l) {
+                    const int Nl = l == 2 ? D : H;
+                    const int nsub = l == 0 ? sub1 : sub2;
+                    const int grp = P.stage_bytes / (Nl * 128);             // K blocks per stage (narrow layers: several)
+                    for (int c = 0; c < nsub; c += grp, ++it) {
+                        const uint32_t bytes = (uint32_t)((nsub - c < grp ? nsub - c : grp) * Nl) * 128u;
+                        const uint32_t s = it % S, ph = (it / S) & 1u;
+                        mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);
+                        const uint32_t bar = smem_u32(&bar_full[s]);
+                        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+                        asm volatile(
+                            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                smem_u32(ring + (size_t)s * P.stage_bytes)),
+                            "l"(src), "r"(bytes), "r"(bar)
+                            : "memory");
+                        src += bytes;
                     }
-                    asm volatile("cp.async.commit_group;" ::: "memory");
-                    asm volatile("cp.async.wait_group 0;" ::: "memory");
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    mbar_arrive(smem_u32(&bar_full[s]));
                 }
             }
         }
@@ -681,28 +856,33 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_mlp3_tf32(const __grid_consta
                 } else {
                     mbar_wait(smem_u32(&bar_a3), tp);                      // act(h2) is in ACT
                 }
+                TRACE(tcount, 3 + l * 2);
                 asm volatile("tcgen05.fence::after_thread_sync;");
-                for (int c = 0; c < nsub; ++c, ++it) {
-                    const uint32_t s = it % kRingStages, ph = (it / kRingStages) & 1u;
+                const int grp = P.stage_bytes / (Nl * 128);
+                for (int c = 0; c < nsub; c += grp, ++it) {
+                    const uint32_t s = it % S, ph = (it / S) & 1u;
+                    const int nb = nsub - c < grp ? nsub - c : grp;
                     mbar_wait(smem_u32(&bar_full[s]), ph);
                     asm volatile("tcgen05.fence::after_thread_sync;");
                     if (lane == 0) {
-                        const uint32_t a_blk = smem_u32(act_buf + c * (kTileM * 128));
-                        const uint32_t b_blk = smem_u32(ring + s * kRingStageBytes);
+                        for (int kb = 0; kb < nb; ++kb) {
+                            const uint32_t a_blk = smem_u32(act_buf + (c + kb) * (kTileM * 128));
+                            const uint32_t b_blk = smem_u32(ring + (size_t)s * P.stage_bytes + (size_t)kb * Nl * 128);
 #pragma unroll
-                        for (int ks = 0; ks < 4; ++ks) {
-                            const uint64_t da = make_desc(a_blk + ks * 32), db = make_desc(b_blk + ks * 32);
-                            const uint32_t accum = (c > 0 || ks > 0) ? 1u : 0u;
-                            asm volatile(
-                                "{\n\t.reg .pred p;\n\t"
-                                "setp.ne.b32 p, %4, 0;\n\t"
-                                "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-                                ::"r"(tacc), "l"(da), "l"(db), "r"(idesc), "r"(accum)
-                                : "memory");
+                            for (int ks = 0; ks < 4; ++ks) {
+                                const uint64_t da = make_desc(a_blk + ks * 32), db = make_desc(b_blk + ks * 32);
+                                const uint32_t accum = (c + kb > 0 || ks > 0) ? 1u : 0u;
+                                asm volatile(
+                                    "{\n\t.reg .pred p;\n\t"
+                                    "setp.ne.b32 p, %4, 0;\n\t"
+                                    "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                                    ::"r"(tacc), "l"(da), "l"(db), "r"(idesc), "r"(accum)
+                                    : "memory");
+                            }
                         }
                         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar_empty[s]))
                                      : "memory");
-                        if (c == nsub - 1) {
+                        if (c + nb == nsub) {
                             uint64_t *done = l == 0 ? &bar_t1 : (l == 1 ? &bar_t2 : &bar_t3);
                             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(done))
                                          : "memory");
@@ -714,6 +894,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_mlp3_tf32(const __grid_consta
                     }
                     __syncwarp();
                 }
+                TRACE(tcount, 4 + l * 2);
             }
         }
     } else {
@@ -726,20 +907,25 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_mlp3_tf32(const __grid_consta
             const int m0 = tile * kTileM;
             // h1 -> ACT
             mbar_wait(smem_u32(&bar_t1), tp);
+            if (q == 0) TRACE(tcount, 9);
             asm volatile("tcgen05.fence::after_thread_sync;");
-            epilogue_to_act(act_buf, acc0, q, lane, H, P.b1, P.act);
+            epilogue_to_act(act_buf, acc0, q, lane, H, sbias[0], P.act);
             asm volatile("tcgen05.fence::before_thread_sync;");
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_arrive(smem_u32(&bar_a2));
+            if (q == 0) TRACE(tcount, 10);
             // h2 -> ACT
             mbar_wait(smem_u32(&bar_t2), tp);
+            if (q == 0) TRACE(tcount, 11);
             asm volatile("tcgen05.fence::after_thread_sync;");
-            epilogue_to_act(act_buf, acc1, q, lane, H, P.b2, P.act);
+            epilogue_to_act(act_buf, acc1, q, lane, H, sbias[1], P.act);
             asm volatile("tcgen05.fence::before_thread_sync;");
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_arrive(smem_u32(&bar_a3));
+            if (q == 0) TRACE(tcount, 12);
             // output: acc0 (D columns) -> transposed -> global rows
             mbar_wait(smem_u32(&bar_t3), tp);
+            if (q == 0) TRACE(tcount, 13);
             asm volatile("tcgen05.fence::after_thread_sync;");
             const int row0 = m0 + q * 32;
             for (int c0 = 0; c0 < D; c0 += 32) {
@@ -761,7 +947,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_mlp3_tf32(const __grid_consta
                 __syncwarp();
                 const int col = c0 + lane;
                 const bool col_ok = col < D;
-                const float bv = (P.b3 && col_ok) ? P.b3[col] : 0.f;
+                const float bv = col_ok ? sbias[2][col] : 0.f;
                 float *dst = P.out + (size_t)row0 * D + col;
 #pragma unroll 8
                 for (int rr = 0; rr < 32; ++rr)
@@ -769,6 +955,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_mlp3_tf32(const __grid_consta
             }
             asm volatile("tcgen05.fence::before_thread_sync;");
             mbar_arrive(smem_u32(&bar_acc0free));
+            if (q == 0) TRACE(tcount, 14);
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
@@ -839,13 +1026,32 @@ extern "C" int b2ode_dense_layer(const void *x, const void *const *k, const doub
     return 0;
 }
 
-// fc1 -> act -> fc2 -> act -> fc3 in one launch (tfdiffeq/models/dense_odenet.py:85-92); see k_mlp3_tf32.
+// ---- fc1 -> act -> fc2 -> act -> fc3 in one launch (tfdiffeq/models/dense_odenet.py:85-92); see k_mlp3_tf32 ----
+static bool mlp3_dims_ok(int D, int H) { return D >= 16 && H >= 16 && D <= 256 && H <= 256 && D % 16 == 0 && H % 16 == 0; }
+
+extern "C" int64_t b2ode_mlp3_packed_bytes(int D, int H) {
+    if (!mlp3_dims_ok(D, H)) return -1;
+    return (int64_t)(mlp3_layer_bytes(H, D) + mlp3_layer_bytes(H, H) + mlp3_layer_bytes(D, H));
+}
+
+extern "C" int b2ode_mlp3_pack(const void *W1, const void *W2, const void *W3, int D, int H, void *packed, void *cuda_stream) {
+    if (!W1 || !W2 || !W3 || !packed) return b2_fail(B2ODE_EINVAL, "null pointer");
+    if (!mlp3_dims_ok(D, H)) return b2_fail(B2ODE_EINVAL, "mlp3: dim and hidden must be multiples of 16 in [16, 256] (got %d, %d)", D, H);
+    if ((uintptr_t)packed & 15) return b2_fail(B2ODE_EINVAL, "packed image must be 16-byte aligned");
+    const int64_t pieces = b2ode_mlp3_packed_bytes(D, H) / 16;
+    const int grid = (int)((pieces + 255) / 256);
+    k_mlp3_pack<<<grid, 256, 0, (cudaStream_t)cuda_stream>>>((const float *)W1, (const float *)W2, (const float *)W3, D, H, (uint8_t *)packed);
+    B2_CUDA(cudaGetLastError());
+    b2_count_launch();
+    return 0;
+}
+
 extern "C" int b2ode_mlp3(const void *x, const void *const *k, const double *coef, int nk, const void *state, void *ystage,
-                          const void *W1, const void *b1, const void *W2, const void *b2, const void *W3, const void *b3, void *out,
-                          int64_t M, int D, int H, int act, void *cuda_stream) {
-    if (!x || !W1 || !W2 || !W3 || !out || M < 1) return b2_fail(B2ODE_EINVAL, "bad mlp3 arguments");
-    if (D < 16 || H < 16 || D > 256 || H > 256 || D % 16 || H % 16)
-        return b2_fail(B2ODE_EINVAL, "mlp3: dim and hidden must be multiples of 16 in [16, 256] (got %d, %d)", D, H);
+                          const void *packed, const void *b1, const void *b2, const void *b3, void *out, int64_t M, int D, int H,
+                          int act, void *cuda_stream) {
+    if (!x || !packed || !out || M < 1) return b2_fail(B2ODE_EINVAL, "bad mlp3 arguments");
+    if (!mlp3_dims_ok(D, H)) return b2_fail(B2ODE_EINVAL, "mlp3: dim and hidden must be multiples of 16 in [16, 256] (got %d, %d)", D, H);
+    if ((uintptr_t)packed & 15) return b2_fail(B2ODE_EINVAL, "packed image must be 16-byte aligned");
     if (nk < 0 || nk > kMaxNK || (nk > 0 && (!k || !coef || !state))) return b2_fail(B2ODE_EINVAL, "bad stage-combine arguments");
     if (act < 0 || act > 3) return b2_fail(B2ODE_EINVAL, "unknown activation %d", act);
     if (M > (int64_t)2147483647 - kTileM) return b2_fail(B2ODE_EINVAL, "M too large");
@@ -863,9 +1069,7 @@ extern "C" int b2ode_mlp3(const void *x, const void *const *k, const double *coe
     P.in.M = (int)M;
     P.in.K = D;
     P.in.N = H;
-    P.W1 = (const float *)W1;
-    P.W2 = (const float *)W2;
-    P.W3 = (const float *)W3;
+    P.packed = (const uint8_t *)packed;
     P.b1 = (const float *)b1;
     P.b2 = (const float *)b2;
     P.b3 = (const float *)b3;
@@ -874,11 +1078,20 @@ extern "C" int b2ode_mlp3(const void *x, const void *const *k, const double *coe
     P.D = D;
     P.H = H;
     P.act = act;
-    const size_t smem = (size_t)kActBytes + kRingStages * kRingStageBytes + 4 * 32 * 33 * sizeof(float) + 1024;
+    // shared memory: ACT (input chunks are produced 64 columns = 2 blocks at a time), the weight ring, the output tiles
+    const int blocks_in = 2 * ((D + kKChunk - 1) / kKChunk), blocks_h = mlp3_subs(H);
+    P.act_bytes = (blocks_in > blocks_h ? blocks_in : blocks_h) * (kTileM * 128);
+    P.stage_bytes = (H > D ? H : D) * 128;
+    const int budget = 227 * 1024 - 4096 - 1024 - P.act_bytes - kTileScratchBytes;      // static (biases, barriers) + alignment slack
+    int stages = budget / P.stage_bytes;
+    if (stages > kMaxRing) stages = kMaxRing;
+    if (stages < 2) return b2_fail(B2ODE_EINVAL, "mlp3: shared memory budget exhausted");
+    P.stages = stages;
+    const size_t smem = (size_t)P.act_bytes + (size_t)stages * P.stage_bytes + kTileScratchBytes + 1024;
     static bool configured = false;
     static int sms = 0;
     if (!configured) {
-        B2_CUDA(cudaFuncSetAttribute(k_mlp3_tf32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        B2_CUDA(cudaFuncSetAttribute(k_mlp3_tf32, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 4096));
         int dev = 0;
         B2_CUDA(cudaGetDevice(&dev));
         B2_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -886,8 +1099,15 @@ extern "C" int b2ode_mlp3(const void *x, const void *const *k, const double *coe
     }
     const long long tiles = (M + kTileM - 1) / kTileM;
     const int grid = (int)(tiles < sms ? tiles : sms);
-    k_mlp3_tf32<<<grid, kWsThreads, smem, (cudaStream_t)cuda_stream>>>(P);
+    k_mlp3_tf32<<<grid, kChainThreads, smem, (cudaStream_t)cuda_stream>>>(P);
     B2_CUDA(cudaGetLastError());
     b2_count_launch();
     return 0;
 }
+
+#ifdef B2ODE_TRACE
+extern "C" int b2ode_debug_mlp3_trace(unsigned long long *out) {
+    B2_CUDA(cudaMemcpyFromSymbol(out, g_mlp3_trace, sizeof(unsigned long long) * 256));
+    return 0;
+}
+#endif

@@ -132,6 +132,30 @@ def dense_layer(x, weight, bias, act="none", stage=None):
     return out
 
 
+_PACK_CACHE = {}
+
+
+def _mlp3_packed(fc1, fc2, fc3):
+    """The three weights as ``b2ode_mlp3``'s shared-memory image, rebuilt only when a weight changes."""
+    import ctypes as C
+    ws = (fc1.weight, fc2.weight, fc3.weight)
+    key = tuple((w.data_ptr(), w._version, tuple(w.shape)) for w in ws)
+    hit = _PACK_CACHE.get(id(fc1))
+    if hit is not None and hit[0] == key:
+        return hit[1]
+    H, D = fc1.weight.shape
+    nbytes = _lib.lib.b2ode_mlp3_packed_bytes(D, H)
+    if nbytes < 0:
+        raise ValueError("mlp3 needs dim and hidden to be multiples of 16 in [16, 256]")
+    packed = torch.empty(nbytes, dtype=torch.uint8, device=fc1.weight.device)
+    cw = [w.detach().contiguous() for w in ws]
+    _lib.check(_lib.lib.b2ode_mlp3_pack(
+        C.c_void_p(cw[0].data_ptr()), C.c_void_p(cw[1].data_ptr()), C.c_void_p(cw[2].data_ptr()), D, H,
+        C.c_void_p(packed.data_ptr()), C.c_void_p(torch.cuda.current_stream(packed.device).cuda_stream)))
+    _PACK_CACHE[id(fc1)] = (key, packed)
+    return packed
+
+
 def mlp3(x, fc1, fc2, fc3, act="relu", stage=None):
     """``fc3(act(fc2(act(fc1(x)))))`` in one launch (``b2ode_mlp3``): hidden activations never reach HBM.
     ``stage`` as in :func:`dense_layer`."""
@@ -151,8 +175,7 @@ def mlp3(x, fc1, fc2, fc3, act="relu", stage=None):
         return C.c_void_p(t.data_ptr()) if t is not None else None
     _lib.check(_lib.lib.b2ode_mlp3(
         ptr(x), karr, carr, nk, C.c_void_p(state) if state else None, ptr(ys),
-        ptr(_tf32_weight(fc1.weight)), ptr(fc1.bias), ptr(_tf32_weight(fc2.weight)), ptr(fc2.bias),
-        ptr(_tf32_weight(fc3.weight)), ptr(fc3.bias), ptr(out), M, D, H, _ACT[act],
+        ptr(_mlp3_packed(fc1, fc2, fc3)), ptr(fc1.bias), ptr(fc2.bias), ptr(fc3.bias), ptr(out), M, D, H, _ACT[act],
         C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)))
     return out
 
