@@ -688,11 +688,16 @@ __device__ __forceinline__ void store_tile_regs(uint8_t *act_buf, int tid, const
     }
 }
 
-// bias + activation + TF32 rounding of one accumulator block, written as the next GEMM's A operand.
-// `bias` is the shared-memory copy (zero-filled when the layer has none, padded to a multiple of 32).
+// bias + activation + TF32 rounding of one accumulator block, written as the next GEMM's A operand, one 32-column
+// K block at a time; each finished K block is handed to the MMA warp through its own mbarrier (`bar_kb`, one arrival
+// per epilogue warp), so the next GEMM runs one K block behind this epilogue instead of after it.
+// `bias` is the shared-memory copy (zero-filled when the layer has none, padded).  ncols is a multiple of 16.
 template <int ACT>
-__device__ __noinline__ void epilogue_to_act_t(uint8_t *act_buf, uint32_t tmem_acc, int q, int lane, int ncols, const float *bias) {
+__device__ __noinline__ void epilogue_to_act_t(uint32_t act_s, uint32_t tmem_acc, int q, int lane, int ncols, const float *bias,
+                                               uint32_t bar_kb) {
     const int row = q * 32 + lane;
+    const uint32_t row_s = act_s + (uint32_t)row * 128u;                  // (row >> 3) * 1024 + (row & 7) * 128
+    const uint32_t rx = (uint32_t)(row & 7);
     const int ncols_pad = (ncols + kSub - 1) / kSub * kSub;
     for (int c0 = 0; c0 < ncols_pad; c0 += 32) {
         uint32_t r[32];
@@ -707,27 +712,36 @@ __device__ __noinline__ void epilogue_to_act_t(uint8_t *act_buf, uint32_t tmem_a
               "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
             : "r"(taddr));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        uint8_t *blk = act_buf + (c0 / kSub) * (kTileM * 128);          // K block of 32 columns: [128 rows x 128 B]
+        const uint32_t blk_s = row_s + (uint32_t)(c0 / kSub) * (kTileM * 128);      // K block of 32 columns: [128 rows x 128 B]
+        const bool second_half = c0 + 16 < ncols;                                  // warp-uniform: ncols is a multiple of 16
 #pragma unroll
         for (int w = 0; w < 32; w += 4) {
-            const float4 bv = *reinterpret_cast<const float4 *>(bias + c0 + w);       // broadcast read
-            uint32_t t[4];
-            t[0] = (c0 + w + 0 < ncols) ? to_tf32(act_t<ACT>(__uint_as_float(r[w + 0]) + bv.x)) : 0u;
-            t[1] = (c0 + w + 1 < ncols) ? to_tf32(act_t<ACT>(__uint_as_float(r[w + 1]) + bv.y)) : 0u;
-            t[2] = (c0 + w + 2 < ncols) ? to_tf32(act_t<ACT>(__uint_as_float(r[w + 2]) + bv.z)) : 0u;
-            t[3] = (c0 + w + 3 < ncols) ? to_tf32(act_t<ACT>(__uint_as_float(r[w + 3]) + bv.w)) : 0u;
-            *reinterpret_cast<uint4 *>(blk + sw128_offset(row, w >> 2)) = make_uint4(t[0], t[1], t[2], t[3]);
+            uint32_t t0 = 0u, t1 = 0u, t2 = 0u, t3 = 0u;
+            if (w < 16 || second_half) {
+                const float4 bv = *reinterpret_cast<const float4 *>(bias + c0 + w);   // broadcast read
+                t0 = to_tf32(act_t<ACT>(__uint_as_float(r[w + 0]) + bv.x));
+                t1 = to_tf32(act_t<ACT>(__uint_as_float(r[w + 1]) + bv.y));
+                t2 = to_tf32(act_t<ACT>(__uint_as_float(r[w + 2]) + bv.z));
+                t3 = to_tf32(act_t<ACT>(__uint_as_float(r[w + 3]) + bv.w));
+            }
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(blk_s + ((((uint32_t)w >> 2) ^ rx) << 4)), "r"(t0), "r"(t1),
+                         "r"(t2), "r"(t3)
+                         : "memory");
         }
+        asm volatile("tcgen05.fence::before_thread_sync;");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> the tensor core's async proxy
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_kb + (uint32_t)(c0 / kSub) * 8u);
     }
 }
 
-__device__ __forceinline__ void epilogue_to_act(uint8_t *act_buf, uint32_t tmem_acc, int q, int lane, int ncols, const float *bias,
-                                                int act) {
+__device__ __forceinline__ void epilogue_to_act(uint32_t act_s, uint32_t tmem_acc, int q, int lane, int ncols, const float *bias,
+                                                int act, uint32_t bar_kb) {
     switch (act) {
-        case 1: epilogue_to_act_t<1>(act_buf, tmem_acc, q, lane, ncols, bias); break;
-        case 2: epilogue_to_act_t<2>(act_buf, tmem_acc, q, lane, ncols, bias); break;
-        case 3: epilogue_to_act_t<3>(act_buf, tmem_acc, q, lane, ncols, bias); break;
-        default: epilogue_to_act_t<0>(act_buf, tmem_acc, q, lane, ncols, bias); break;
+        case 1: epilogue_to_act_t<1>(act_s, tmem_acc, q, lane, ncols, bias, bar_kb); break;
+        case 2: epilogue_to_act_t<2>(act_s, tmem_acc, q, lane, ncols, bias, bar_kb); break;
+        case 3: epilogue_to_act_t<3>(act_s, tmem_acc, q, lane, ncols, bias, bar_kb); break;
+        default: epilogue_to_act_t<0>(act_s, tmem_acc, q, lane, ncols, bias, bar_kb); break;
     }
 }
 
@@ -738,7 +752,8 @@ __global__ void __launch_bounds__(kChainThreads, 1) k_mlp3_tf32(const __grid_con
     uint8_t *ring = smem + P.act_bytes;
     float *tiles = reinterpret_cast<float *>(ring + (size_t)P.stages * P.stage_bytes);
     __shared__ __align__(8) uint64_t bar_full[kMaxRing], bar_empty[kMaxRing];
-    __shared__ __align__(8) uint64_t bar_a1, bar_actfree, bar_t1, bar_a2, bar_t2, bar_a3, bar_t3, bar_acc0free;
+    __shared__ __align__(8) uint64_t bar_a1, bar_actfree, bar_t1, bar_t2, bar_t3;
+    __shared__ __align__(8) uint64_t bar_a2[8], bar_a3[8];             // act(h1) / act(h2), one per 32-column K block
     __shared__ uint32_t tmem_slot;
     __shared__ __align__(16) float sbias[3][256];
 
@@ -769,9 +784,10 @@ __global__ void __launch_bounds__(kChainThreads, 1) k_mlp3_tf32(const __grid_con
         init(&bar_t1, 1u);
         init(&bar_t2, 1u);
         init(&bar_t3, 1u);
-        init(&bar_a2, 128u);                     // act(h1) written by the epilogue warps
-        init(&bar_a3, 128u);
-        init(&bar_acc0free, 128u);               // final epilogue drained acc0
+        for (int i = 0; i < 8; ++i) {
+            init(&bar_a2[i], 4u);                // one arrival per epilogue warp
+            init(&bar_a3[i], 4u);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;");
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
@@ -847,15 +863,12 @@ __global__ void __launch_bounds__(kChainThreads, 1) k_mlp3_tf32(const __grid_con
                 const int Nl = l == 2 ? D : H;
                 const int nsub = l == 0 ? sub1 : sub2;
                 const uint32_t idesc = make_idesc_tf32(Nl);
-                const uint32_t tacc = l == 1 ? acc1 : acc0;
-                if (l == 0) {
-                    mbar_wait(smem_u32(&bar_acc0free), tp ^ 1u);           // final epilogue of the previous tile drained acc0
-                    mbar_wait(smem_u32(&bar_a1), tp);                      // input tile is in ACT
-                } else if (l == 1) {
-                    mbar_wait(smem_u32(&bar_a2), tp);                      // act(h1) is in ACT (and acc0 has been drained)
-                } else {
-                    mbar_wait(smem_u32(&bar_a3), tp);                      // act(h2) is in ACT
-                }
+                // accumulator roles alternate per tile (GEMM1 and GEMM3 -> A, GEMM2 -> B, A/B swapped on odd tiles), so this
+                // tile's GEMM1 can run while the previous tile's output epilogue is still draining ITS accumulator A.
+                // No accumulator-free barrier is needed: A(t+1) = B(t) was drained by E2(t) before GEMM3(t) could finish
+                // (GEMM3 consumes what E2 writes), and B(t+1) = A(t) is drained by E3(t) before the same warps run E1(t+1).
+                const uint32_t tacc = ((l == 1) != (tp == 1u)) ? acc1 : acc0;
+                if (l == 0) mbar_wait(smem_u32(&bar_a1), tp);              // input tile is in ACT
                 TRACE(tcount, 3 + l * 2);
                 asm volatile("tcgen05.fence::after_thread_sync;");
                 const int grp = P.stage_bytes / (Nl * 128);
@@ -864,8 +877,11 @@ __global__ void __launch_bounds__(kChainThreads, 1) k_mlp3_tf32(const __grid_con
                     const int nb = nsub - c < grp ? nsub - c : grp;
                     mbar_wait(smem_u32(&bar_full[s]), ph);
                     asm volatile("tcgen05.fence::after_thread_sync;");
-                    if (lane == 0) {
-                        for (int kb = 0; kb < nb; ++kb) {
+                    for (int kb = 0; kb < nb; ++kb) {
+                        if (l == 1) mbar_wait(smem_u32(&bar_a2[c + kb]), tp);      // this K block of act(h1) is in ACT
+                        if (l == 2) mbar_wait(smem_u32(&bar_a3[c + kb]), tp);
+                        asm volatile("tcgen05.fence::after_thread_sync;");
+                        if (lane == 0) {
                             const uint32_t a_blk = smem_u32(act_buf + (c + kb) * (kTileM * 128));
                             const uint32_t b_blk = smem_u32(ring + (size_t)s * P.stage_bytes + (size_t)kb * Nl * 128);
 #pragma unroll
@@ -880,6 +896,8 @@ __global__ void __launch_bounds__(kChainThreads, 1) k_mlp3_tf32(const __grid_con
                                     : "memory");
                             }
                         }
+                    }
+                    if (lane == 0) {
                         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar_empty[s]))
                                      : "memory");
                         if (c + nb == nsub) {
@@ -909,19 +927,14 @@ __global__ void __launch_bounds__(kChainThreads, 1) k_mlp3_tf32(const __grid_con
             mbar_wait(smem_u32(&bar_t1), tp);
             if (q == 0) TRACE(tcount, 9);
             asm volatile("tcgen05.fence::after_thread_sync;");
-            epilogue_to_act(act_buf, acc0, q, lane, H, sbias[0], P.act);
-            asm volatile("tcgen05.fence::before_thread_sync;");
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            mbar_arrive(smem_u32(&bar_a2));
+            const uint32_t accA = tp ? acc1 : acc0, accB = tp ? acc0 : acc1;
+            epilogue_to_act(smem_u32(act_buf), accA, q, lane, H, sbias[0], P.act, smem_u32(&bar_a2[0]));
             if (q == 0) TRACE(tcount, 10);
             // h2 -> ACT
             mbar_wait(smem_u32(&bar_t2), tp);
             if (q == 0) TRACE(tcount, 11);
             asm volatile("tcgen05.fence::after_thread_sync;");
-            epilogue_to_act(act_buf, acc1, q, lane, H, sbias[1], P.act);
-            asm volatile("tcgen05.fence::before_thread_sync;");
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            mbar_arrive(smem_u32(&bar_a3));
+            epilogue_to_act(smem_u32(act_buf), accB, q, lane, H, sbias[1], P.act, smem_u32(&bar_a3[0]));
             if (q == 0) TRACE(tcount, 12);
             // output: acc0 (D columns) -> transposed -> global rows
             mbar_wait(smem_u32(&bar_t3), tp);
@@ -930,7 +943,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) k_mlp3_tf32(const __grid_con
             const int row0 = m0 + q * 32;
             for (int c0 = 0; c0 < D; c0 += 32) {
                 uint32_t r[32];
-                const uint32_t taddr = acc0 + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+                const uint32_t taddr = accA + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
                 asm volatile(
                     "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
                     "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -954,7 +967,6 @@ __global__ void __launch_bounds__(kChainThreads, 1) k_mlp3_tf32(const __grid_con
                     if (col_ok && row0 + rr < P.M) dst[(size_t)rr * D] = tile_t[rr * 33 + lane] + bv;
             }
             asm volatile("tcgen05.fence::before_thread_sync;");
-            mbar_arrive(smem_u32(&bar_acc0free));
             if (q == 0) TRACE(tcount, 14);
         }
     }
