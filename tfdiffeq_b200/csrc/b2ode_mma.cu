@@ -47,6 +47,16 @@ __device__ __forceinline__ uint32_t to_tf32(float x) {
     return r;
 }
 
+// Round to TF32's 11 significant bits with three FP32 operations (Veltkamp's split, C = 2^13 + 1): round-to-nearest
+// (ties to even), low 13 mantissa bits come out zero, NaN and Inf stay non-finite.  cvt.rna.tf32.f32 has no fast
+// hardware path (ptxas emulates it in ~7 integer/predicate instructions); this is what the activation epilogues use.
+// |x| > 4e34 overflows the intermediate product and yields NaN.
+__device__ __forceinline__ uint32_t to_tf32_fast(float x) {
+    const float g = __fmul_rn(x, 8193.0f);
+    const float d = __fsub_rn(x, g);
+    return __float_as_uint(__fadd_rn(g, d));
+}
+
 // byte offset of (row, 16-byte chunk c in 0..7) inside one [rows x 128 B] K-major SWIZZLE_128B block:
 // 8-row atoms of 1024 B, the chunk index XOR-ed with the row inside the atom (Swizzle<3,4,3>)
 __device__ __forceinline__ uint32_t sw128_offset(int row, int chunk) {
@@ -103,6 +113,22 @@ __device__ __forceinline__ void store_column_t(float *dst, const float *tile, in
 #pragma unroll 8
     for (int rr = 0; rr < 32; ++rr)
         if (rr < nrows) dst[(size_t)rr * ld] = act_t<ACT>(tile[rr * 33 + lane] + bv);
+}
+
+// for waits that last microseconds (keeps the spinning warps off the issue ports the working warps need)
+__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    for (;;) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (ok) break;
+        __nanosleep(64);
+    }
 }
 
 __device__ __forceinline__ float apply_act(float v, int act) {
@@ -558,7 +584,7 @@ constexpr int kSub = 32;                                   // K columns per weig
 constexpr int kChainThreads = (kProdWarps + 1 + 4 + 1) * 32;
 constexpr int kLoaderWarp = kProdWarps + 5;
 constexpr int kMaxRing = 8;
-constexpr int kTileScratchBytes = 4 * 32 * 33 * 4;         // the output epilogue's transposition tiles
+constexpr int kTileScratchBytes = kProdWarps * 32 * 17 * 4;  // the output epilogue's transposition scratch, one per producer warp
 
 struct Mlp3Params {
     DenseParams in;                    // x / k / coef / nk / st / ystage / M / K(= D) describe the input tile
@@ -610,8 +636,13 @@ __device__ __forceinline__ void trace(int tile_no, int slot) {
     }
 }
 #define TRACE(tile_no, slot) trace((int)(tile_no), slot)
+__device__ unsigned long long g_mlp3_clk[80];
+__device__ int g_mlp3_clk_n;
+#define CLK(cond)                                                            \
+    if ((cond) && blockIdx.x == 0 && g_mlp3_clk_n < 80) g_mlp3_clk[g_mlp3_clk_n++] = clock64()
 #else
 #define TRACE(tile_no, slot)
+#define CLK(cond)
 #endif
 
 // ---- input tile (D <= 64: one 64-column chunk) loaded and stage-combined into registers ----
@@ -702,6 +733,7 @@ __device__ __noinline__ void epilogue_to_act_t(uint32_t act_s, uint32_t tmem_acc
     for (int c0 = 0; c0 < ncols_pad; c0 += 32) {
         uint32_t r[32];
         const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+        CLK(q == 0 && lane == 0);
         asm volatile(
             "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
             "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -712,6 +744,7 @@ __device__ __noinline__ void epilogue_to_act_t(uint32_t act_s, uint32_t tmem_acc
               "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
             : "r"(taddr));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        CLK(q == 0 && lane == 0);
         const uint32_t blk_s = row_s + (uint32_t)(c0 / kSub) * (kTileM * 128);      // K block of 32 columns: [128 rows x 128 B]
         const bool second_half = c0 + 16 < ncols;                                  // warp-uniform: ncols is a multiple of 16
 #pragma unroll
@@ -719,17 +752,19 @@ __device__ __noinline__ void epilogue_to_act_t(uint32_t act_s, uint32_t tmem_acc
             uint32_t t0 = 0u, t1 = 0u, t2 = 0u, t3 = 0u;
             if (w < 16 || second_half) {
                 const float4 bv = *reinterpret_cast<const float4 *>(bias + c0 + w);   // broadcast read
-                t0 = to_tf32(act_t<ACT>(__uint_as_float(r[w + 0]) + bv.x));
-                t1 = to_tf32(act_t<ACT>(__uint_as_float(r[w + 1]) + bv.y));
-                t2 = to_tf32(act_t<ACT>(__uint_as_float(r[w + 2]) + bv.z));
-                t3 = to_tf32(act_t<ACT>(__uint_as_float(r[w + 3]) + bv.w));
+                t0 = to_tf32_fast(act_t<ACT>(__uint_as_float(r[w + 0]) + bv.x));
+                t1 = to_tf32_fast(act_t<ACT>(__uint_as_float(r[w + 1]) + bv.y));
+                t2 = to_tf32_fast(act_t<ACT>(__uint_as_float(r[w + 2]) + bv.z));
+                t3 = to_tf32_fast(act_t<ACT>(__uint_as_float(r[w + 3]) + bv.w));
             }
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(blk_s + ((((uint32_t)w >> 2) ^ rx) << 4)), "r"(t0), "r"(t1),
                          "r"(t2), "r"(t3)
                          : "memory");
         }
+        CLK(q == 0 && lane == 0);
         asm volatile("tcgen05.fence::before_thread_sync;");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> the tensor core's async proxy
+        CLK(q == 0 && lane == 0);
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_kb + (uint32_t)(c0 / kSub) * 8u);
     }
@@ -745,6 +780,48 @@ __device__ __forceinline__ void epilogue_to_act(uint32_t act_s, uint32_t tmem_ac
     }
 }
 
+// Output tile: accumulator (D columns) + bias -> global rows.  Run by the eight producer warps after they have
+// dropped the next tile's input into ACT, i.e. off the GEMM / activation-epilogue critical path.  Warp w reads TMEM
+// lane quarter w & 3 (the hardware's per-warp access window) and the 32-column chunks (w >> 2), (w >> 2) + 2, ...
+// TMEM hands each lane one ROW; 16 columns at a time are transposed through a [32][17] shared-memory scratch so that
+// a warp store writes two 64-byte row segments instead of 32 scattered 4-byte words.
+__device__ __forceinline__ void output_tile(const Mlp3Params &P, uint32_t tacc, int warp, int lane, int m0, float *scratch,
+                                            const float *bias) {
+    const int q = warp & 3;
+    const int row0 = m0 + q * 32;
+    const int D = P.D;
+    for (int c0 = 32 * (warp >> 2); c0 < D; c0 += 64) {
+        uint32_t r[32];
+        const uint32_t taddr = tacc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+              "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+              "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+              "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+            : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            if (c0 + half * 16 >= D) break;                               // D is a multiple of 16: warp-uniform
+            __syncwarp();
+#pragma unroll
+            for (int w = 0; w < 16; ++w) scratch[lane * 17 + w] = __uint_as_float(r[half * 16 + w]);
+            __syncwarp();
+            const int col = c0 + half * 16 + (lane & 15);
+            const float bv = bias[col];
+            float *dst = P.out + (size_t)row0 * D + col;
+#pragma unroll 8
+            for (int i = 0; i < 16; ++i) {
+                const int rr = 2 * i + (lane >> 4);
+                if (row0 + rr < P.M) dst[(size_t)rr * D] = scratch[rr * 17 + (lane & 15)] + bv;
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(kChainThreads, 1) k_mlp3_tf32(const __grid_constant__ Mlp3Params P) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -752,7 +829,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) k_mlp3_tf32(const __grid_con
     uint8_t *ring = smem + P.act_bytes;
     float *tiles = reinterpret_cast<float *>(ring + (size_t)P.stages * P.stage_bytes);
     __shared__ __align__(8) uint64_t bar_full[kMaxRing], bar_empty[kMaxRing];
-    __shared__ __align__(8) uint64_t bar_a1, bar_actfree, bar_t1, bar_t2, bar_t3;
+    __shared__ __align__(8) uint64_t bar_a1, bar_actfree, bar_t1, bar_t2, bar_outdone;
     __shared__ __align__(8) uint64_t bar_a2[8], bar_a3[8];             // act(h1) / act(h2), one per 32-column K block
     __shared__ uint32_t tmem_slot;
     __shared__ __align__(16) float sbias[3][256];
@@ -783,7 +860,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) k_mlp3_tf32(const __grid_con
         init(&bar_actfree, 1u);                  // GEMM3 finished reading ACT (commit)
         init(&bar_t1, 1u);
         init(&bar_t2, 1u);
-        init(&bar_t3, 1u);
+        init(&bar_outdone, (unsigned)kProdWarps); // output tile read out of its accumulator (one arrival per producer warp)
         for (int i = 0; i < 8; ++i) {
             init(&bar_a2[i], 4u);                // one arrival per epilogue warp
             init(&bar_a3[i], 4u);
@@ -808,18 +885,20 @@ __global__ void __launch_bounds__(kChainThreads, 1) k_mlp3_tf32(const __grid_con
                 if (j < p.nk) cf[j] = __fmul_rn(dt, (float)p.coef[j]);
         }
         const bool prefetch = D <= kKChunk && (D & 3) == 0;
+        float *scratch = tiles + warp * (32 * 17);
         uint32_t tcount = 0;
+        int prev_m0 = -1;
         for (int tile = blockIdx.x; tile < tiles_m; tile += gridDim.x, ++tcount) {
             const int m0 = tile * kTileM;
             if (prefetch) {
                 float4 v[8];
                 load_tile_regs(p, m0, tid, cf, v);                         // overlaps the previous tile's GEMMs
                 TRACE(tcount, 0);
-                mbar_wait(smem_u32(&bar_actfree), (tcount & 1u) ^ 1u);     // previous tile's GEMM3 no longer reads ACT
+                mbar_wait_backoff(smem_u32(&bar_actfree), (tcount & 1u) ^ 1u);   // previous tile's GEMM3 is complete
                 TRACE(tcount, 1);
                 store_tile_regs(act_buf, tid, v);
             } else {
-                mbar_wait(smem_u32(&bar_actfree), (tcount & 1u) ^ 1u);
+                mbar_wait_backoff(smem_u32(&bar_actfree), (tcount & 1u) ^ 1u);
                 for (int kc = 0; kc < D; kc += kKChunk)
                     produce_chunk<kProdThreads>(p, act_buf + (kc / kSub) * (kTileM * 128), nullptr, m0, 0, 0, kc, tid, cf);
                 asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -827,6 +906,22 @@ __global__ void __launch_bounds__(kChainThreads, 1) k_mlp3_tf32(const __grid_con
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_arrive(smem_u32(&bar_a1));
             TRACE(tcount, 2);
+            if (prev_m0 >= 0) {
+                // the previous tile's output, while this tile is in GEMM1 / its first activation epilogue
+                asm volatile("tcgen05.fence::after_thread_sync;");
+                output_tile(P, ((tcount - 1u) & 1u) ? acc1 : acc0, warp, lane, prev_m0, scratch, sbias[2]);
+                asm volatile("tcgen05.fence::before_thread_sync;");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&bar_outdone));
+                TRACE(tcount - 1u, 14);
+            }
+            prev_m0 = m0;
+        }
+        if (prev_m0 >= 0) {
+            mbar_wait_backoff(smem_u32(&bar_actfree), (tcount & 1u) ^ 1u);       // the last tile's GEMM3
+            asm volatile("tcgen05.fence::after_thread_sync;");
+            output_tile(P, ((tcount - 1u) & 1u) ? acc1 : acc0, warp, lane, prev_m0, scratch, sbias[2]);
+            TRACE(tcount - 1u, 14);
         }
     } else if (warp == kLoaderWarp) {
         // ===== weight loader: one bulk copy per sub-chunk, completion counted in bytes on the stage's mbarrier =====
@@ -864,11 +959,12 @@ __global__ void __launch_bounds__(kChainThreads, 1) k_mlp3_tf32(const __grid_con
                 const int nsub = l == 0 ? sub1 : sub2;
                 const uint32_t idesc = make_idesc_tf32(Nl);
                 // accumulator roles alternate per tile (GEMM1 and GEMM3 -> A, GEMM2 -> B, A/B swapped on odd tiles), so this
-                // tile's GEMM1 can run while the previous tile's output epilogue is still draining ITS accumulator A.
-                // No accumulator-free barrier is needed: A(t+1) = B(t) was drained by E2(t) before GEMM3(t) could finish
-                // (GEMM3 consumes what E2 writes), and B(t+1) = A(t) is drained by E3(t) before the same warps run E1(t+1).
+                // tile's GEMM1 can run while the previous tile's output is still being read out of ITS accumulator A.
+                // A(t+1) = B(t) needs no barrier: E2(t) drained it before GEMM3(t) could finish (GEMM3 consumes what E2
+                // writes).  B(t+1) = A(t) is released by the producer warps' output pass (bar_outdone) before GEMM2(t+1).
                 const uint32_t tacc = ((l == 1) != (tp == 1u)) ? acc1 : acc0;
                 if (l == 0) mbar_wait(smem_u32(&bar_a1), tp);              // input tile is in ACT
+                if (l == 1 && tcount > 0) mbar_wait(smem_u32(&bar_outdone), tp ^ 1u);   // B(t) = A(t-1) has been read out
                 TRACE(tcount, 3 + l * 2);
                 asm volatile("tcgen05.fence::after_thread_sync;");
                 const int grp = P.stage_bytes / (Nl * 128);
@@ -901,13 +997,10 @@ __global__ void __launch_bounds__(kChainThreads, 1) k_mlp3_tf32(const __grid_con
                         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar_empty[s]))
                                      : "memory");
                         if (c + nb == nsub) {
-                            uint64_t *done = l == 0 ? &bar_t1 : (l == 1 ? &bar_t2 : &bar_t3);
+                            // GEMM3 complete = ACT may be refilled AND the output accumulator is final
+                            uint64_t *done = l == 0 ? &bar_t1 : (l == 1 ? &bar_t2 : &bar_actfree);
                             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(done))
                                          : "memory");
-                            if (l == 2)
-                                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                                                 smem_u32(&bar_actfree))
-                                             : "memory");
                         }
                     }
                     __syncwarp();
@@ -918,11 +1011,9 @@ __global__ void __launch_bounds__(kChainThreads, 1) k_mlp3_tf32(const __grid_con
     } else {
         // ===== epilogue warps =====
         const int q = warp & 3;
-        float *tile_t = tiles + q * (32 * 33);
         uint32_t tcount = 0;
         for (int tile = blockIdx.x; tile < tiles_m; tile += gridDim.x, ++tcount) {
             const uint32_t tp = tcount & 1u;
-            const int m0 = tile * kTileM;
             // h1 -> ACT
             mbar_wait(smem_u32(&bar_t1), tp);
             if (q == 0) TRACE(tcount, 9);
@@ -936,38 +1027,6 @@ __global__ void __launch_bounds__(kChainThreads, 1) k_mlp3_tf32(const __grid_con
             asm volatile("tcgen05.fence::after_thread_sync;");
             epilogue_to_act(smem_u32(act_buf), accB, q, lane, H, sbias[1], P.act, smem_u32(&bar_a3[0]));
             if (q == 0) TRACE(tcount, 12);
-            // output: acc0 (D columns) -> transposed -> global rows
-            mbar_wait(smem_u32(&bar_t3), tp);
-            if (q == 0) TRACE(tcount, 13);
-            asm volatile("tcgen05.fence::after_thread_sync;");
-            const int row0 = m0 + q * 32;
-            for (int c0 = 0; c0 < D; c0 += 32) {
-                uint32_t r[32];
-                const uint32_t taddr = accA + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-                      "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-                      "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-                      "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-                    : "r"(taddr));
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                __syncwarp();
-#pragma unroll
-                for (int w = 0; w < 32; ++w) tile_t[lane * 33 + w] = __uint_as_float(r[w]);
-                __syncwarp();
-                const int col = c0 + lane;
-                const bool col_ok = col < D;
-                const float bv = col_ok ? sbias[2][col] : 0.f;
-                float *dst = P.out + (size_t)row0 * D + col;
-#pragma unroll 8
-                for (int rr = 0; rr < 32; ++rr)
-                    if (col_ok && row0 + rr < P.M) dst[(size_t)rr * D] = tile_t[rr * 33 + lane] + bv;
-            }
-            asm volatile("tcgen05.fence::before_thread_sync;");
-            if (q == 0) TRACE(tcount, 14);
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
@@ -1120,6 +1179,9 @@ extern "C" int b2ode_mlp3(const void *x, const void *const *k, const double *coe
 #ifdef B2ODE_TRACE
 extern "C" int b2ode_debug_mlp3_trace(unsigned long long *out) {
     B2_CUDA(cudaMemcpyFromSymbol(out, g_mlp3_trace, sizeof(unsigned long long) * 256));
+    B2_CUDA(cudaMemcpyFromSymbol(out + 256, g_mlp3_clk, sizeof(unsigned long long) * 80));
+    int zero = 0;
+    B2_CUDA(cudaMemcpyToSymbol(g_mlp3_clk_n, &zero, sizeof(int)));
     return 0;
 }
 #endif
