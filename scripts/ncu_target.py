@@ -2,6 +2,7 @@
 
   --workload lorenz    : BASELINE config 2 shape (65 536 x 3 fp64 dopri5), first --npts output points
   --workload headline  : north-star kernel size (65 536 x 128 fp64 dopri5, linear func), 3 output points
+  --workload mlp       : ODENet func rhs.DenseMLP(64, 256) on 131 072 rows (fp32 / TF32 tcgen05), one dopri5 solve
 """
 import argparse
 import os
@@ -28,6 +29,12 @@ if a.workload == "lorenz":
     f = PROBLEMS["lorenz"](backend="torch", device=dev)
     t = torch.arange(a.npts, dtype=torch.float64) * 0.01
     kw = dict(method="dopri5")
+elif a.workload == "mlp":
+    torch.manual_seed(0)
+    f = tfd.rhs.DenseMLP(64, 256, "relu").to(dev)
+    y0 = torch.randn(131072, 64, device=dev)
+    t = torch.tensor([0., 1.])
+    kw = dict(method="dopri5", rtol=1e-3, atol=1e-3)
 else:
     torch.manual_seed(0)
     y0 = torch.randn(65536, 128, dtype=torch.float64, device=dev)

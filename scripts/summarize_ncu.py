@@ -23,7 +23,7 @@ def launches(src, dst):
     for row in csv.DictReader(lines):
         agg.setdefault(row["Kernel Name"], []).append(float(row["Metric Value"]))
     tot = sum(sum(v) for v in agg.values())
-    ours = sum(sum(v) for k, v in agg.items() if k.startswith("void k_") or " k_" in k)
+    ours = sum(sum(v) for k, v in agg.items() if k.startswith("void k_") or k.startswith("k_") or " k_" in k)
     with open(dst, "w") as f:
         f.write("# ncu launch list (gpu__time_duration.sum, --clock-control none): %s\n\n" % src)
         f.write("Per-launch times under ncu are cold-cache and serialised: compare SHARES, not absolutes.\n\n")

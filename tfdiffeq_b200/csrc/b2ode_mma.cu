@@ -584,6 +584,10 @@ constexpr int kSub = 32;                                   // K columns per weig
 constexpr int kChainThreads = (kProdWarps + 1 + 4 + 1) * 32;
 constexpr int kLoaderWarp = kProdWarps + 5;
 constexpr int kMaxRing = 8;
+#ifndef B2_BULK_PIECE
+#define B2_BULK_PIECE 16384
+#endif
+constexpr uint32_t kBulkPiece = B2_BULK_PIECE;   // bytes per cp.async.bulk request
 constexpr int kTileScratchBytes = kProdWarps * 32 * 17 * 4;  // the output epilogue's transposition scratch, one per producer warp
 
 struct Mlp3Params {
@@ -747,20 +751,23 @@ __device__ __noinline__ void epilogue_to_act_t(uint32_t act_s, uint32_t tmem_acc
         CLK(q == 0 && lane == 0);
         const uint32_t blk_s = row_s + (uint32_t)(c0 / kSub) * (kTileM * 128);      // K block of 32 columns: [128 rows x 128 B]
         const bool second_half = c0 + 16 < ncols;                                  // warp-uniform: ncols is a multiple of 16
+        // all 32 values first (independent 5-op chains the scheduler can interleave), then the eight 16-byte stores;
+        // the store asm carries no memory clobber so that nothing pins the bias reads or the math between stores --
+        // the fence below is a volatile asm WITH a clobber and stays behind every one of them
+        uint32_t t[32];
 #pragma unroll
         for (int w = 0; w < 32; w += 4) {
-            uint32_t t0 = 0u, t1 = 0u, t2 = 0u, t3 = 0u;
-            if (w < 16 || second_half) {
-                const float4 bv = *reinterpret_cast<const float4 *>(bias + c0 + w);   // broadcast read
-                t0 = to_tf32_fast(act_t<ACT>(__uint_as_float(r[w + 0]) + bv.x));
-                t1 = to_tf32_fast(act_t<ACT>(__uint_as_float(r[w + 1]) + bv.y));
-                t2 = to_tf32_fast(act_t<ACT>(__uint_as_float(r[w + 2]) + bv.z));
-                t3 = to_tf32_fast(act_t<ACT>(__uint_as_float(r[w + 3]) + bv.w));
-            }
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(blk_s + ((((uint32_t)w >> 2) ^ rx) << 4)), "r"(t0), "r"(t1),
-                         "r"(t2), "r"(t3)
-                         : "memory");
+            const float4 bv = *reinterpret_cast<const float4 *>(bias + c0 + w);       // broadcast read
+            const bool in = w < 16 || second_half;
+            t[w + 0] = in ? to_tf32_fast(act_t<ACT>(__uint_as_float(r[w + 0]) + bv.x)) : 0u;
+            t[w + 1] = in ? to_tf32_fast(act_t<ACT>(__uint_as_float(r[w + 1]) + bv.y)) : 0u;
+            t[w + 2] = in ? to_tf32_fast(act_t<ACT>(__uint_as_float(r[w + 2]) + bv.z)) : 0u;
+            t[w + 3] = in ? to_tf32_fast(act_t<ACT>(__uint_as_float(r[w + 3]) + bv.w)) : 0u;
         }
+#pragma unroll
+        for (int w = 0; w < 32; w += 4)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(blk_s + ((((uint32_t)w >> 2) ^ rx) << 4)), "r"(t[w]),
+                         "r"(t[w + 1]), "r"(t[w + 2]), "r"(t[w + 3]));
         CLK(q == 0 && lane == 0);
         asm volatile("tcgen05.fence::before_thread_sync;");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> the tensor core's async proxy
@@ -939,11 +946,16 @@ __global__ void __launch_bounds__(kChainThreads, 1) k_mlp3_tf32(const __grid_con
                         mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);
                         const uint32_t bar = smem_u32(&bar_full[s]);
                         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-                        asm volatile(
-                            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                                smem_u32(ring + (size_t)s * P.stage_bytes)),
-                            "l"(src), "r"(bytes), "r"(bar)
-                            : "memory");
+                        // (request size is not the limiter: 1 x 32 KB, 2 x 16 KB and 8 x 4 KB per stage time the same,
+                        // profiles/r01_mlp3_chained.md -- the SM's ingest from L2 is)
+                        const uint32_t dst0 = smem_u32(ring + (size_t)s * P.stage_bytes);
+                        for (uint32_t o = 0; o < bytes; o += kBulkPiece) {
+                            const uint32_t nb = bytes - o < kBulkPiece ? bytes - o : kBulkPiece;
+                            asm volatile(
+                                "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst0 + o),
+                                "l"(src + o), "r"(nb), "r"(bar)
+                                : "memory");
+                        }
                         src += bytes;
                     }
                 }
