@@ -17,7 +17,9 @@ Arrays may be numpy arrays (the checker) or torch CPU tensors (``bench.py``'s mu
 baseline: op-for-op eager dispatch, the reference's own execution model); scalars are always numpy
 scalars / python floats so the dtype of every scalar operation is explicit.
 """
+import collections
 import math
+from fractions import Fraction
 import warnings
 
 import numpy as np
@@ -681,6 +683,241 @@ ADAPTIVE = {"dopri5": DOPRI5, "dopri8": DOPRI8, "bosh3": BOSH3, "adaptive_heun":
 FIXED = {"euler": "euler", "midpoint": "midpoint", "rk4": "rk4", "huen": "heun", "heun": "heun"}
 
 
+# --------------------------------------------------------------------------------------------------
+# multistep solvers: fixed_adams.py and adams.py
+# --------------------------------------------------------------------------------------------------
+
+
+def _poly_mul(a, b):
+    out = [Fraction(0)] * (len(a) + len(b) - 1)
+    for i, x in enumerate(a):
+        for j, y in enumerate(b):
+            out[i + j] += x * y
+    return out
+
+
+def _adams_weights(k, shift):
+    """Weights of the k-point Adams formula as exact rationals: integral over [0, 1] of the Lagrange basis on the
+    nodes u = shift, shift - 1, ..., shift - k + 1 (shift = 0: Bashforth, nodes t_n, t_n-1, ...; shift = 1: Moulton,
+    nodes t_n+1, t_n, ...).  Returns (integer numerators, common divisor) like the tables of fixed_adams.py:7-160."""
+    nodes = [Fraction(shift - j) for j in range(k)]
+    w = []
+    for j in range(k):
+        poly, den = [Fraction(1)], Fraction(1)
+        for i in range(k):
+            if i != j:
+                poly = _poly_mul(poly, [-nodes[i], Fraction(1)])
+                den *= nodes[j] - nodes[i]
+        w.append(sum(c / (p + 1) for p, c in enumerate(poly)) / den)
+    div = 1
+    for x in w:
+        div = div * x.denominator // math.gcd(div, x.denominator)
+    return [int(x * div) for x in w], div
+
+
+def has_converged(y0, y1, rtol, atol):
+    """misc.py:129-134: every element within atol + rtol * max(|y0|, |y1|) (element-wise tolerance here)."""
+    for a, b in zip(y0, y1):
+        if _is_torch(a):
+            import torch
+            tol = atol + rtol * torch.maximum(a.abs(), b.abs())
+            ok = bool(((a - b).abs() < tol).all())
+        else:
+            tol = atol + rtol * np.maximum(np.abs(a), np.abs(b))
+            ok = bool(np.all(np.abs(a - b) < tol))
+        if not ok:
+            return False
+    return True
+
+
+class FixedAdams(FixedGrid):
+    """fixed_adams.py:168-212.  implicit=True: 'fixed_adams' (Bashforth predictor + Moulton corrector by functional
+    iteration); implicit=False: 'explicit_adams'.  The first steps (fewer than 3 stored derivatives) are 3/8-rule
+    RK4 steps reusing the stored derivative as k1 (:188-191)."""
+
+    MIN_ORDER, MAX_ORDER, MAX_ITERS = 4, 12, 4
+
+    def __init__(self, func, y0, rtol=1e-3, atol=1e-4, implicit=True, max_iters=4, max_order=12, stats=None, **kw):
+        FixedGrid.__init__(self, func, y0, "adams", stats=stats, **kw)
+        self.rtol, self.atol, self.implicit, self.max_iters = rtol, atol, implicit, max_iters
+        self.max_order = int(min(max_order, self.MAX_ORDER))
+        self.prev_f = collections.deque(maxlen=self.max_order - 1)
+        self.prev_t = None
+
+    def _update_history(self, t, f):
+        if self.prev_t is None or self.prev_t != t:                  # fixed_adams.py:182-185
+            self.prev_f.appendleft(f)
+            self.prev_t = t
+
+    def step_func(self, t, dt, y):
+        sd = type(dt)
+        d = _f(dt)
+        self._update_history(t, self._f(t, y))
+        order = min(len(self.prev_f), self.max_order - 1)
+        if order < self.MIN_ORDER - 1:                               # :190-193, rk_common.py:73-81 with k1 given
+            k1 = self.prev_f[0]
+            k2 = self._f(t + dt / sd(3), tuple(y_ + d * k1_ / 3 for y_, k1_ in zip(y, k1)))
+            k3 = self._f(t + dt * sd(2) / sd(3), tuple(y_ + d * (k1_ / -3 + k2_) for y_, k1_, k2_ in zip(y, k1, k2)))
+            k4 = self._f(t + dt, tuple(y_ + d * (k1_ - k2_ + k3_) for y_, k1_, k2_, k3_ in zip(y, k1, k2, k3)))
+            return tuple((k1_ + 3 * k2_ + 3 * k3_ + k4_) * _f(dt / sd(8)) for k1_, k2_, k3_, k4_ in zip(k1, k2, k3, k4))
+        ab, ab_div = _adams_weights(order, 0)
+        dy = tuple(d * _sdp_py(1 / ab_div, ab, f_) for f_ in zip(*self.prev_f))          # :196-198
+        if self.implicit:
+            am, am_div = _adams_weights(order + 1, 1)
+            delta = tuple(d * _sdp_py(1 / am_div, am[1:], f_) for f_ in zip(*self.prev_f))
+            converged = False
+            f = None
+            for _ in range(self.max_iters):
+                dy_old = dy
+                f = self._f(t + dt, tuple(y_ + dy_ for y_, dy_ in zip(y, dy)))
+                c0 = _f(dt * sd(am[0] / am_div))                      # dt (state dtype) * python float, then * f
+                dy = tuple(c0 * f_ + delta_ for f_, delta_ in zip(f, delta))
+                converged = has_converged(dy_old, dy, self.rtol, self.atol)
+                if converged:
+                    break
+            if not converged:
+                self.stats.not_converged = getattr(self.stats, "not_converged", 0) + 1
+                self.prev_f.pop()                                     # :210 drops the OLDEST stored derivative
+            self._update_history(t, f)                                # :211 no-op: prev_t == t already
+        return dy
+
+
+def _sdp_py(scale, xs, ys):
+    """misc.py:118-121 with a python-float scale and integer coefficients: ((scale * x) * y) summed left to right."""
+    out = None
+    for x, y in zip(xs, ys):
+        term = (scale * x) * y
+        out = term if out is None else out + term
+    return out
+
+
+GAMMA_STAR = [1, -1 / 2, -1 / 12, -1 / 24, -19 / 720, -3 / 160, -863 / 60480, -275 / 24192, -33953 / 3628800,
+              -0.00789255, -0.00678585, -0.00592406, -0.00523669, -0.0046775, -0.00421495, -0.0038269]   # adams.py:16-19
+
+
+class VariableAdams(object):
+    """adams.py:22-211: variable-coefficient Adams-Bashforth-Moulton (Hairer-Norsett-Wanner III.5), orders 1..12.
+
+    Quirks kept: g is stored in a float32 Variable (:34, :51, :56); `first_step` is ignored (:112-115); the
+    predictor uses order - 1 terms (:144-147); the state carried to the next step is the PREDICTOR p_next, not the
+    corrected y_next (:211); a rejected step keeps the order (:172)."""
+
+    MIN_ORDER, MAX_ORDER = 1, 12
+
+    def __init__(self, func, y0, rtol, atol, implicit=True, first_step=None, max_order=12, safety=0.9, ifactor=10.0,
+                 dfactor=0.2, stats=None, **unused):
+        if unused:
+            warnings.warn('{}: Unexpected arguments {}'.format('VariableCoefficientAdamsBashforth', unused))
+        self.func, self.y0 = func, y0
+        self.rtol, self.atol = _listify(rtol, len(y0)), _listify(atol, len(y0))
+        self.max_order = int(max(self.MIN_ORDER, min(max_order, self.MAX_ORDER)))
+        self.safety, self.ifactor, self.dfactor = _tf_f64(safety), _tf_f64(ifactor), _tf_f64(dfactor)
+        self.stats = stats if stats is not None else Stats()
+
+    def _f(self, t, y):
+        self.stats.nfe += 1
+        return self.func(t, y)
+
+    def integrate(self, t):
+        t = np.asarray(t, dtype=np.float64)                           # solvers.py:30
+        assert np.all(t[1:] > t[:-1]), 't must be strictly increasing or decrasing'
+        sd = _np_dtype(self.y0[0]).type
+        f0 = self._f(sd(t[0]), self.y0)
+        first_step = np.float64(select_initial_step(self._f, t[0], self.y0, 2, self.rtol[0], self.atol[0], f0=f0))
+        self.y_n, self.prev_t, self.phi = self.y0, collections.deque([t[0]], maxlen=self.max_order + 1), [f0]
+        self.n_prev_f = 1
+        self.next_t, self.order = t[0] + first_step, 1
+        solution = [self.y0]
+        for i in range(1, len(t)):
+            while t[i] > self.prev_t[0]:                              # adams.py:123-126
+                self._step(t[i])
+            assert t[i] == self.prev_t[0]
+            solution.append(self.y_n)
+        return tuple(_stack(s) for s in zip(*solution))
+
+    def _g_and_explicit_phi(self, next_t, k):
+        """adams.py:29-59."""
+        prev_t, iphi = self.prev_t, self.phi
+        curr_t = prev_t[0]
+        dt = next_t - prev_t[0]
+        g = np.zeros(k + 1, dtype=np.float32)
+        g[0] = 1
+        c = 1.0 / np.arange(1, k + 2).astype(np.float64)
+        ephi = [iphi[0]]
+        beta = np.float64(1.0)
+        sd = _np_dtype(iphi[0][0]).type
+        with np.errstate(all="ignore"):
+            for j in range(1, k):
+                beta = (next_t - prev_t[j - 1]) / (curr_t - prev_t[j]) * beta
+                ephi.append(tuple(p_ * _f(sd(beta)) for p_ in iphi[j]))
+                c = c[:-1] - c[1:] if j == 1 else c[:-1] - c[1:] * dt / (next_t - prev_t[j - 1])
+                g[j] = np.float32(c[0])
+            c = c[:-1] - c[1:] * dt / (next_t - prev_t[k - 1])
+            g[k] = np.float32(c[0])
+        return g, ephi
+
+    @staticmethod
+    def _implicit_phi(ephi, f_n, k):
+        """adams.py:62-77."""
+        k = min(len(ephi) + 1, k)
+        out = [f_n]
+        for j in range(1, k):
+            out.append(tuple(a_ - b_ for a_, b_ in zip(out[j - 1], ephi[j - 1])))
+        return out
+
+    def _error(self, coef, phi_j, tol):
+        """misc.py:250-264 with the tolerance given: mean((coef * phi / tol)**2) per component."""
+        out = []
+        for p_, tol_ in zip(phi_j, tol):
+            ratio = (_f(coef) * p_) / _f(tol_)
+            out.append(_mean(ratio * ratio))
+        return tuple(out)
+
+    def _step(self, final_t):
+        """adams.py:128-211."""
+        y0, order = self.y_n, self.order
+        sd = _np_dtype(y0[0]).type
+        next_t = min(self.next_t, final_t) if not np.isnan(self.next_t) else self.next_t
+        dt = next_t - self.prev_t[0]
+        dtc = sd(dt)
+        g32, phi = self._g_and_explicit_phi(next_t, order)
+        g = g32.astype(sd)
+        m = max(1, order - 1)
+        p_next = tuple(y0_ + scaled_dot_product(dtc, g[:m], phi_[:m]) for y0_, phi_ in zip(y0, tuple(zip(*phi))))
+        next_f0 = self._f(sd(next_t), p_next)
+        iphi_p = self._implicit_phi(phi, next_f0, order + 1)
+        y_next = tuple(p_ + _f(dtc * g[order - 1]) * i_ for p_, i_ in zip(p_next, iphi_p[order - 1]))
+        tol = tuple(sd(a_) + sd(r_) * _nanmax([_absmax(a0), _absmax(a1)])
+                    for a_, r_, a0, a1 in zip(self.atol, self.rtol, y0, y_next))
+        error_k = self._error(dtc * (g[order] - g[order - 1]), iphi_p[order], tol)
+        accept = all(bool(e <= 1) for e in error_k)
+        if not accept:
+            self.stats.n_rej += 1
+            dt_next = optimal_step_size(dt, error_k, self.safety, self.ifactor, self.dfactor, order=order)
+            self.next_t = self.prev_t[0] + dt_next
+            return
+        self.stats.n_acc += 1
+        next_f0 = self._f(sd(next_t), y_next)
+        implicit_phi = self._implicit_phi(phi, next_f0, order + 2)
+        next_order = order
+        if len(self.prev_t) <= 4 or order < 3:
+            next_order = min(order + 1, 3, self.max_order)
+        else:
+            e1 = self._error(dtc * (g[order - 1] - g[order - 2]), iphi_p[order - 1], tol)
+            e2 = self._error(dtc * (g[order - 2] - g[order - 3]), iphi_p[order - 2], tol)
+            if min(e1 + e2) < max(error_k):
+                next_order = order - 1
+            elif order < self.max_order:
+                ep = self._error(dtc * sd(GAMMA_STAR[order]), iphi_p[order], tol)
+                if max(ep) < max(error_k):
+                    next_order = order + 1
+        dt_next = dt if next_order > order else optimal_step_size(dt, error_k, self.safety, self.ifactor,
+                                                                  self.dfactor, order=order + 1)
+        self.prev_t.appendleft(next_t)
+        self.y_n, self.phi, self.order = p_next, implicit_phi, next_order      # :211 the predictor is carried on
+        self.next_t = next_t + dt_next
+
+
 def odeint(func, y0, t, rtol=1e-7, atol=1e-9, method=None, options=None, stats=None):
     """odeint.py:28-81 + misc.py:290-329 (_check_inputs).  y0: array or tuple of arrays; t: 1-D array."""
     tensor_input = False
@@ -708,6 +945,12 @@ def odeint(func, y0, t, rtol=1e-7, atol=1e-9, method=None, options=None, stats=N
         solver = Tsit5(func, y0, rtol, atol, stats=stats, **options)
     elif method in FIXED:
         solver = FixedGrid(func, y0, FIXED[method], stats=stats, **options)
+    elif method == "fixed_adams":
+        solver = FixedAdams(func, y0, rtol=rtol, atol=atol, stats=stats, **options)
+    elif method == "explicit_adams":
+        solver = FixedAdams(func, y0, rtol=rtol, atol=atol, implicit=False, stats=stats, **options)
+    elif method == "adams":
+        solver = VariableAdams(func, y0, rtol, atol, stats=stats, **options)
     else:
         raise KeyError(method)
     sol = solver.integrate(t)

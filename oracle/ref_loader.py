@@ -46,7 +46,8 @@ def load():
     compat = types.ModuleType("tfdiffeq.compat")
 
     def assign(tensor, val):
-        tensor.copy_(val) if hasattr(tensor, "copy_") else None
+        import torch
+        tensor.copy_(val if isinstance(val, torch.Tensor) else torch.as_tensor(val, dtype=tensor.dtype))
         return tensor
     compat.assign = assign
     sys.modules["tfdiffeq.compat"] = compat
@@ -109,6 +110,21 @@ def run_reference(func, y0, t, counters=None, **kw):
             return new
         setattr(cls, meth, wrapped)
         patched.append((cls, meth, orig))
+    # variable-coefficient Adams: a rejected step hands back the same y_n object (adams.py:172), an accepted one the predictor
+    vcls = sys.modules["tfdiffeq.adams"].VariableCoefficientAdamsBashforth
+    vorig = vcls._adaptive_adams_step
+
+    def vwrapped(self, st, final_t, _orig=vorig):
+        dt = float(min(float(st.next_t), float(final_t)) - float(st.prev_t[0]))
+        new = _orig(self, st, final_t)
+        counters.dt_trace.append(dt)
+        if new.y_n is not st.y_n:
+            counters.n_acc += 1
+        else:
+            counters.n_rej += 1
+        return new
+    vcls._adaptive_adams_step = vwrapped
+    patched.append((vcls, "_adaptive_adams_step", vorig))
     try:
         return pkg.odeint(counted, y0, t, **kw)
     finally:

@@ -26,7 +26,24 @@ import torch
 _m = types.ModuleType("tensorflow")
 
 Tensor = torch.Tensor
-Variable = torch.Tensor
+
+
+class _TFIntTensor(torch.Tensor):
+    """``tf.range`` result: TF's true division promotes int32 operands to float64 (torch would give float32);
+    adams.py:41 relies on it (``c = 1 / tf.range(1, k + 2)``)."""
+
+    def __rtruediv__(self, other):
+        return other / self.as_subclass(torch.Tensor).to(torch.float64)
+
+    def __truediv__(self, other):
+        return self.as_subclass(torch.Tensor).to(torch.float64) / other
+
+
+def Variable(initial_value, trainable=True, dtype=None, name=None):  # noqa: N802
+    """adams.py:34 only needs a mutable tensor whose slices can be assigned (``compat.assign(g[j], v)``)."""
+    out = initial_value.clone() if isinstance(initial_value, torch.Tensor) else torch.as_tensor(initial_value)
+    return out if dtype is None else out.to(dtype)
+
 float16, float32, float64 = torch.float16, torch.float32, torch.float64
 int32, int64 = torch.int32, torch.int64
 bool = torch.bool  # noqa: A001  (mirrors tf.bool)
@@ -187,7 +204,8 @@ def equal(a, b):
 
 
 def range(*args, **kw):  # noqa: A001
-    return torch.arange(*args)
+    out = torch.arange(*args)
+    return out.to(torch.int32).as_subclass(_TFIntTensor) if not out.dtype.is_floating_point else out
 
 
 def is_tensor(x):

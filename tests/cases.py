@@ -118,6 +118,32 @@ def build_cases():
     y0tri = np.zeros((8, 16)); y0tri[:, 0] = 1.0; y0tri += 0.01 * rng.standard_normal((8, 16))
     add("tridiag_dopri8", "tridiag", y0tri, np.linspace(0., 20., 11), method="dopri8", rtol=1e-9, atol=1e-9)
     add("tridiag_dopri5", "tridiag", y0tri, np.linspace(0., 20., 11), method="dopri5", rtol=1e-6, atol=1e-6)
+    # --- multistep solvers (fixed_adams.py, adams.py) -----------------------------------------
+    lv0 = np.array([1., 1.])
+    add("lv_fixed_adams", "lv", lv0, np.linspace(0., 2., 201), method="fixed_adams", rtol=1e-6, atol=1e-8, keep=20)
+    # (at the default max_order = 12 the 11-step Bashforth formula is unstable on this problem even at dt = 0.005 -- the
+    #  reference ends in NaN -- so the explicit cases cap the order or use the sine problem)
+    add("lv_explicit_adams", "lv", lv0, np.linspace(0., 2., 401), method="explicit_adams", options=dict(max_order=6), keep=40)
+    add("lv_fixed_adams_order5_iter1", "lv", lv0, np.linspace(0., 2., 201), method="fixed_adams", rtol=1e-6, atol=1e-8,
+        options=dict(max_order=5, max_iters=1), keep=20)
+    add("lv_fixed_adams_f32", "lv", lv0.astype(F32), np.linspace(0., 2., 201), method="fixed_adams", rtol=1e-4, atol=1e-6,
+        dtype="float32", keep=20)
+    add("lv_rev_fixed_adams", "lv", lv0, np.linspace(2., 0., 101), method="fixed_adams", rtol=1e-6, atol=1e-8, keep=10)
+    add("sine_explicit_adams", "sine", np.array([1.0, 0.5]), np.linspace(1., 3., 401), method="explicit_adams", keep=40)
+    add("tuple_fixed_adams", "tuple_decay", (np.linspace(1., 2., 2), np.linspace(0.5, 1.5, 5)),
+        np.linspace(0., 1., 401), method="fixed_adams", rtol=1e-6, atol=1e-8, keep=40)
+    add("lorenz_b16_explicit_adams_step", "lorenz", _lorenz_y0(16), np.arange(11) * 0.05, method="explicit_adams",
+        options=dict(max_order=6))
+    add("lv_adams", "lv", lv0, np.linspace(0., 2., 201), method="adams", rtol=1e-6, atol=1e-8, keep=20)
+    add("lv_adams_order4", "lv", lv0, np.linspace(0., 2., 201), method="adams", rtol=1e-6, atol=1e-8,
+        options=dict(max_order=4), keep=20)
+    add("lv_rev_adams", "lv", lv0, np.linspace(2., 0., 101), method="adams", rtol=1e-6, atol=1e-8, keep=10)
+    add("lv_adams_default_tol", "lv", lv0, np.linspace(0., 1., 11), method="adams")
+    add("tuple_adams", "tuple_decay", (np.linspace(1., 2., 2), np.linspace(0.5, 1.5, 5)),
+        np.linspace(0., 0.5, 6), method="adams", rtol=1e-5, atol=1e-7)
+    add("lorenz_b16_adams", "lorenz", _lorenz_y0(16), np.arange(11) * 0.05, method="adams", rtol=1e-6, atol=1e-8)
+    add("lv_adams_unknown_opt", "lv", lv0, np.linspace(0., 0.2, 3), method="adams", rtol=1e-5, atol=1e-7,
+        options=dict(bogus=1), expect_error="UserWarning")
     return C
 
 
