@@ -219,6 +219,31 @@ int b2ode_fused_fixed_solve(int dtype, int method, int rhs_kind, const double *r
                             int n_steps, int n_out, const void *times, const void *dts, const int32_t *j0,
                             const unsigned char *ends, const void *s1, const void *s2, int sm_count, void *cuda_stream);
 
+/* ---- multistep solvers (tfdiffeq/fixed_adams.py, tfdiffeq/adams.py) ----------------------- */
+
+/* out = base + scale * sum_{j < nterms} coef[j] * x[j]   over all segments; products and sums in the state dtype,
+ * left to right (the order of `dt * _scaled_dot_product(scale, coeffs, f)`, misc.py:118-121, fixed_adams.py:196-204,
+ * adams.py:144-157).  `base` may be NULL (no addend); scale == 1 skips the multiplication.  xs[j * nseg + s] is term
+ * j of segment s; 1 <= nterms <= 16.  Covers the Adams-Bashforth predictor, the Adams-Moulton corrector update,
+ * phi scaling and phi differences (adams.py:46, :73-75), and copies. */
+int b2ode_lincomb(int dtype, int nseg, const int64_t *seg_len, void *const *out, const void *const *base, double scale,
+                  int nterms, const void *const *xs, const double *coef, int sm_count, void *cuda_stream);
+
+/* Per-segment reductions; out[2*s], out[2*s+1] (device doubles), deterministic (fixed combine order).
+ *   B2ODE_RED_ABSMAX2       { max|a|, max|b| }, NaN-propagating                      misc.py:257 / adams.py:160-163
+ *   B2ODE_RED_RATIO_SUMSQ   { sum ((p0[s] * a) / p1[s])^2, 0 }  (the caller divides by the element count)
+ *                                                                                      misc.py:259-264 / adams.py:164-166
+ *   B2ODE_RED_NOT_CONVERGED { number of elements with NOT |a-b| < p1[s] + p0[s]*max(|a|,|b|), 0 }   misc.py:129-134
+ * `workspace`: b2ode_reduce_workspace_bytes(sm_count) bytes of device memory, zero-filled once by the caller and
+ * reusable by later calls on the same stream. */
+#define B2ODE_RED_ABSMAX2 0
+#define B2ODE_RED_RATIO_SUMSQ 1
+#define B2ODE_RED_NOT_CONVERGED 2
+size_t b2ode_reduce_workspace_bytes(int sm_count);
+int b2ode_reduce(int dtype, int mode, int nseg, const int64_t *seg_len, const void *const *a, const void *const *b,
+                 const double *p0, const double *p1, double *out, void *workspace, size_t workspace_bytes, int sm_count,
+                 void *cuda_stream);
+
 /* ---- GEMM-backed func on tensor cores ---------------------------------------------------- */
 
 /* One dense layer of an ODENet-style func (tfdiffeq/models/dense_odenet.py:85-92) on tcgen05 / TMEM:

@@ -123,8 +123,9 @@ def test_api_errors_without_gpu():
         tfd.odeint(f, y0, t, options=dict(first_step=0.1))
     with pytest.raises(KeyError):
         tfd.odeint(f, y0, t, method="nope")
-    with pytest.raises(KeyError):
-        tfd.odeint(f, y0, t, method="adams")                       # multistep solvers are out of scope
+    for m in ("adams", "fixed_adams", "explicit_adams"):           # multistep solvers: same loud failure on CPU tensors
+        with pytest.raises(RuntimeError, match="CUDA tensors only"):
+            tfd.odeint(f, y0, t, method=m)
     # the product has no CPU path: CPU tensors fail loudly instead of silently falling back
     with pytest.raises(RuntimeError, match="CUDA tensors only"):
         tfd.odeint(f, y0, t, method="dopri5")
@@ -138,7 +139,7 @@ def test_api_errors_without_gpu():
     with pytest.raises(ValueError):
         tfd.odeint_adjoint(f, y0, t)                               # func must be an nn.Module
     assert set(tfd.SOLVERS) == {"tsit5", "dopri5", "dopri8", "bosh3", "euler", "midpoint", "rk4", "huen", "heun",
-                                "adaptive_heun"}
+                                "adaptive_heun", "adams", "fixed_adams", "explicit_adams"}      # tfdiffeq/odeint.py:11-25
 
 
 def test_missing_library_fails_loudly(tmp_path):
@@ -155,3 +156,27 @@ def test_product_never_imports_the_oracle():
         if fn.endswith(".py"):
             src = open(os.path.join(pkg, fn)).read()
             assert "np_ref" not in src and "import oracle" not in src and "from oracle" not in src, fn
+
+
+def test_adams_weights_are_exact_and_match_the_oracle():
+    """The product regenerates the Adams-Bashforth / Adams-Moulton tables (tfdiffeq/fixed_adams.py:7-160) from their
+    definition; the oracle does so independently and was compared entry by entry with the reference's literal tables
+    when the golden vectors were made (oracle/make_golden.py)."""
+    from fractions import Fraction
+    from tfdiffeq_b200.multistep import adams_weights
+    for k in range(1, 21):
+        for implicit in (False, True):
+            c, d = adams_weights(k, implicit)
+            assert (c, d) == tuple(np_ref._adams_weights(k, 1 if implicit else 0))
+            assert sum(Fraction(x, d) for x in c) == 1                 # consistency: a constant derivative integrates exactly
+    assert adams_weights(4, False) == ([55, -59, 37, -9], 24)
+    assert adams_weights(4, True) == ([9, 19, -5, 1], 24)
+    assert adams_weights(5, True) == ([251, 646, -264, 106, -19], 720)
+    ref = os.path.join(os.sep, "root", "reference", "tfdiffeq", "fixed_adams.py")
+    if os.path.exists(ref):                                            # build container only
+        ns = {}
+        src = open(ref).read()
+        exec(src[src.index("_BASHFORTH_COEFFICIENTS"):src.index("_MIN_ORDER")], ns)   # the three literal tables, nothing else
+        for k in range(2, 21):
+            assert adams_weights(k, False) == (ns["_BASHFORTH_COEFFICIENTS"][k], ns["_DIVISOR"][k])
+            assert adams_weights(k, True) == (ns["_MOULTON_COEFFICIENTS"][k], ns["_DIVISOR"][k])

@@ -93,6 +93,12 @@ _SIGNATURES = {
     "b2ode_mlp3": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_double), C.c_int, C.c_void_p, C.c_void_p,
                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                              C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "b2ode_lincomb": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_double,
+                                C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_double), C.c_int, C.c_void_p]),
+    "b2ode_reduce_workspace_bytes": (C.c_size_t, [C.c_int]),
+    "b2ode_reduce": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                               C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_void_p, C.c_void_p, C.c_size_t, C.c_int,
+                               C.c_void_p]),
     "b2ode_launch_count": (C.c_ulonglong, []),
     "b2ode_timing_enable": (C.c_int, [C.c_uint]),
     "b2ode_timing_read": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int)]),
@@ -130,3 +136,4 @@ lib = _load()
 def check(rc):
     if rc != 0:
         raise B2odeError("libb2ode call failed (%d): %s" % (rc, lib.b2ode_last_error().decode("utf-8", "replace")))
+RED_ABSMAX2, RED_RATIO_SUMSQ, RED_NOT_CONVERGED = 0, 1, 2

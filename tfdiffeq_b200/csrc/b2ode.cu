@@ -1289,3 +1289,204 @@ extern "C" int b2ode_fixed_op(int dtype, int op, int nseg, const int64_t *seg_le
     if (dtype == B2ODE_F64) return dispatch_fixed<double>(op, grid, (cudaStream_t)cuda_stream, p);
     return dispatch_fixed<float>(op, grid, (cudaStream_t)cuda_stream, p);
 }
+
+// ================================================================================================
+// multistep solvers (tfdiffeq/fixed_adams.py, tfdiffeq/adams.py)
+//
+// Their arithmetic is linear combinations of stored derivative tensors plus three reductions; the step logic
+// (history, order selection, functional iteration) is host code like the reference's.  Two kernels:
+//   k_lincomb : out = base + scale * sum_j coef[j] * x[j]      (products and sums in the state dtype, left to right,
+//               no contraction: the order of `dt * _scaled_dot_product(...)`, misc.py:118-121)
+//   k_reduce  : per segment, two numbers, deterministic (block partials combined in block order by the last block)
+// ================================================================================================
+constexpr int kMaxTerms = 16;
+
+struct LincombParams {
+    SegGeom g;
+    void *out[B2ODE_MAXSEG];
+    const void *base[B2ODE_MAXSEG];
+    const void *x[kMaxTerms][B2ODE_MAXSEG];
+    double coef[kMaxTerms];
+    double scale;
+    int nterms, has_base, has_scale;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) k_lincomb(const __grid_constant__ LincombParams p) {
+    const int s = find_seg(p.g, blockIdx.x);
+    const int bl = blockIdx.x - p.g.blk_begin[s], nb = p.g.blk_begin[s + 1] - p.g.blk_begin[s];
+    T *out = (T *)p.out[s];
+    const T *base = (const T *)p.base[s];
+    const T scale = (T)p.scale;
+    seg_for_each<T>(p.g.n[s], (p.g.vec_mask >> s) & 1u, bl, nb, [&](auto vt, long long i) {
+        constexpr int V = decltype(vt)::value;
+        Pack<T, V> acc;
+#pragma unroll
+        for (int e = 0; e < V; ++e) acc.v[e] = T(0);
+        for (int j = 0; j < p.nterms; ++j) {
+            const Pack<T, V> xv = ld_pack<T, V>((const T *)p.x[j][s], i);
+            const T c = (T)p.coef[j];
+#pragma unroll
+            for (int e = 0; e < V; ++e) {
+                const T term = Ar<T>::mul(c, xv.v[e]);
+                acc.v[e] = j ? Ar<T>::add(acc.v[e], term) : term;
+            }
+        }
+        if (p.has_scale) {
+#pragma unroll
+            for (int e = 0; e < V; ++e) acc.v[e] = Ar<T>::mul(scale, acc.v[e]);
+        }
+        if (p.has_base) {
+            const Pack<T, V> bv = ld_pack<T, V>(base, i);
+#pragma unroll
+            for (int e = 0; e < V; ++e) acc.v[e] = Ar<T>::add(bv.v[e], acc.v[e]);
+        }
+        st_pack<T, V>(out, i, acc);
+    });
+}
+
+extern "C" int b2ode_lincomb(int dtype, int nseg, const int64_t *seg_len, void *const *out, const void *const *base, double scale,
+                             int nterms, const void *const *xs, const double *coef, int sm_count, void *cuda_stream) {
+    if (dtype != B2ODE_F32 && dtype != B2ODE_F64) return b2_fail(B2ODE_EINVAL, "dtype must be 0 or 1");
+    if (nseg < 1 || nseg > B2ODE_MAXSEG || !seg_len || !out) return b2_fail(B2ODE_EINVAL, "bad segment arguments");
+    if (nterms < 1 || nterms > kMaxTerms || !xs || !coef) return b2_fail(B2ODE_EINVAL, "lincomb takes 1..%d terms", kMaxTerms);
+    LincombParams p;
+    memset(&p, 0, sizeof(p));
+    build_geom(&p.g, dtype, nseg, seg_len, sm_count);
+    unsigned mask = 0;
+    for (int s = 0; s < nseg; ++s) {
+        if (seg_len[s] < 0) return b2_fail(B2ODE_EINVAL, "negative segment length");
+        p.out[s] = out[s];
+        p.base[s] = base ? base[s] : nullptr;
+        bool al = aligned16(p.out[s]) && aligned16(p.base[s]);
+        if (seg_len[s] > 0 && (!p.out[s] || (base && !p.base[s]))) return b2_fail(B2ODE_EINVAL, "segment %d has a null operand", s);
+        for (int j = 0; j < nterms; ++j) {
+            p.x[j][s] = xs[(size_t)j * nseg + s];
+            if (seg_len[s] > 0 && !p.x[j][s]) return b2_fail(B2ODE_EINVAL, "term %d of segment %d is null", j, s);
+            al = al && aligned16(p.x[j][s]);
+        }
+        if (al) mask |= 1u << s;
+    }
+    p.g.vec_mask = mask;
+    for (int j = 0; j < nterms; ++j) p.coef[j] = coef[j];
+    p.scale = scale;
+    p.nterms = nterms;
+    p.has_base = base ? 1 : 0;
+    p.has_scale = scale != 1.0 ? 1 : 0;      // 1 * x is exact: skipping it changes nothing
+    const int grid = p.g.blk_begin[nseg];
+    if (dtype == B2ODE_F64) return launch(k_lincomb<double>, grid, (cudaStream_t)cuda_stream, p, B2_FAM_FIXED);
+    return launch(k_lincomb<float>, grid, (cudaStream_t)cuda_stream, p, B2_FAM_FIXED);
+}
+
+struct ReduceParams {
+    SegGeom g;
+    const void *a[B2ODE_MAXSEG];
+    const void *b[B2ODE_MAXSEG];
+    double p0[B2ODE_MAXSEG], p1[B2ODE_MAXSEG];
+    Partial *partials;
+    unsigned *ticket;
+    double *out;
+};
+
+// MODE B2ODE_RED_ABSMAX2   : out = { max|a|, max|b| }                (NaN-propagating; misc.py:257, adams.py:160-163)
+//      B2ODE_RED_RATIO_SUMSQ: out = { sum ((p0 * a) / p1)^2, 0 }     (misc.py:259-264 with error_tol given: adams.py:164-166)
+//      B2ODE_RED_NOT_CONVERGED: out = { #elements with NOT |a-b| < p1 + p0 * max(|a|,|b|), 0 }   (misc.py:129-134)
+template <typename T, int MODE>
+__global__ void __launch_bounds__(kThreads) k_reduce(const __grid_constant__ ReduceParams p) {
+    constexpr unsigned MM = MODE == B2ODE_RED_ABSMAX2 ? 0x3u : 0x0u;
+    const int s = find_seg(p.g, blockIdx.x);
+    const int bl = blockIdx.x - p.g.blk_begin[s], nb = p.g.blk_begin[s + 1] - p.g.blk_begin[s];
+    const T *a = (const T *)p.a[s];
+    const T *b = (const T *)p.b[s];
+    const T p0 = (T)p.p0[s], p1 = (T)p.p1[s];
+    AbsMax<T> ma, mb;
+    double sum = 0.0;
+    seg_for_each<T>(p.g.n[s], (p.g.vec_mask >> s) & 1u, bl, nb, [&](auto vt, long long i) {
+        constexpr int V = decltype(vt)::value;
+        const Pack<T, V> av = ld_pack<T, V>(a, i);
+        if constexpr (MODE == B2ODE_RED_RATIO_SUMSQ) {
+#pragma unroll
+            for (int e = 0; e < V; ++e) {
+                const T r = Ar<T>::div(Ar<T>::mul(p0, av.v[e]), p1);
+                sum += (double)Ar<T>::mul(r, r);
+            }
+        } else {
+            const Pack<T, V> bv = ld_pack<T, V>(b, i);
+#pragma unroll
+            for (int e = 0; e < V; ++e) {
+                if constexpr (MODE == B2ODE_RED_ABSMAX2) {
+                    ma.see(av.v[e]);
+                    mb.see(bv.v[e]);
+                } else {
+                    const T aa = Ar<T>::abs(av.v[e]), ab = Ar<T>::abs(bv.v[e]);
+                    const T mx = (aa != aa || ab != ab) ? (T)NAN : (aa > ab ? aa : ab);
+                    const T tol = Ar<T>::add(p1, Ar<T>::mul(p0, mx));
+                    const T err = Ar<T>::abs(Ar<T>::sub(av.v[e], bv.v[e]));
+                    sum += (err < tol) ? 0.0 : 1.0;
+                }
+            }
+        }
+    });
+    Partial mine = identity<MM>();
+    if (MODE == B2ODE_RED_ABSMAX2) {
+        mine.v[0] = ma.value();
+        mine.v[1] = mb.value();
+    } else {
+        mine.v[0] = sum;
+    }
+    mine = block_reduce<MM>(mine);
+    if (threadIdx.x == 0) p.partials[blockIdx.x] = mine;
+    if (last_block_arrives(p.ticket)) {
+        if ((int)threadIdx.x < p.g.nseg) {
+            const int sg = threadIdx.x;
+            Partial tot = p.partials[p.g.blk_begin[sg]];
+            for (int q = p.g.blk_begin[sg] + 1; q < p.g.blk_begin[sg + 1]; ++q) tot = combine<MM>(tot, p.partials[q]);
+            p.out[2 * sg + 0] = tot.v[0];
+            p.out[2 * sg + 1] = tot.v[1];
+        }
+        if (threadIdx.x == 0) *p.ticket = 0u;                   // ready for the next launch on the same workspace
+    }
+}
+
+extern "C" size_t b2ode_reduce_workspace_bytes(int sm_count) {
+    const int sms = sm_count > 0 ? sm_count : 148;
+    return 64 + sizeof(Partial) * ((size_t)sms * 8 + 2 * B2ODE_MAXSEG);
+}
+
+extern "C" int b2ode_reduce(int dtype, int mode, int nseg, const int64_t *seg_len, const void *const *a, const void *const *b,
+                            const double *p0, const double *p1, double *out, void *workspace, size_t workspace_bytes, int sm_count,
+                            void *cuda_stream) {
+    if (dtype != B2ODE_F32 && dtype != B2ODE_F64) return b2_fail(B2ODE_EINVAL, "dtype must be 0 or 1");
+    if (nseg < 1 || nseg > B2ODE_MAXSEG || !seg_len || !a || !out || !workspace) return b2_fail(B2ODE_EINVAL, "bad segment arguments");
+    if (mode < B2ODE_RED_ABSMAX2 || mode > B2ODE_RED_NOT_CONVERGED) return b2_fail(B2ODE_EINVAL, "unknown reduction %d", mode);
+    if (mode != B2ODE_RED_RATIO_SUMSQ && !b) return b2_fail(B2ODE_EINVAL, "reduction %d needs two operands", mode);
+    if (mode != B2ODE_RED_ABSMAX2 && (!p0 || !p1)) return b2_fail(B2ODE_EINVAL, "reduction %d needs its scalars", mode);
+    if (workspace_bytes < b2ode_reduce_workspace_bytes(sm_count) || ((uintptr_t)workspace & 15u))
+        return b2_fail(B2ODE_EINVAL, "reduce workspace too small or misaligned");
+    ReduceParams p;
+    memset(&p, 0, sizeof(p));
+    build_geom(&p.g, dtype, nseg, seg_len, sm_count);
+    unsigned mask = 0;
+    for (int s = 0; s < nseg; ++s) {
+        if (seg_len[s] < 0) return b2_fail(B2ODE_EINVAL, "negative segment length");
+        p.a[s] = a[s];
+        p.b[s] = b ? b[s] : nullptr;
+        if (seg_len[s] > 0 && (!p.a[s] || (mode != B2ODE_RED_RATIO_SUMSQ && !p.b[s])))
+            return b2_fail(B2ODE_EINVAL, "segment %d has a null operand", s);
+        if (aligned16(p.a[s]) && aligned16(p.b[s])) mask |= 1u << s;
+        p.p0[s] = p0 ? p0[s] : 0.0;
+        p.p1[s] = p1 ? p1[s] : 0.0;
+    }
+    p.g.vec_mask = mask;
+    p.ticket = (unsigned *)workspace;
+    p.partials = (Partial *)((char *)workspace + 64);
+    p.out = out;
+    const int grid = p.g.blk_begin[nseg];
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+#define B2_RED(T)                                                                                                        \
+    (mode == B2ODE_RED_ABSMAX2       ? launch(k_reduce<T, B2ODE_RED_ABSMAX2>, grid, st, p, B2_FAM_FIXED)                 \
+     : mode == B2ODE_RED_RATIO_SUMSQ ? launch(k_reduce<T, B2ODE_RED_RATIO_SUMSQ>, grid, st, p, B2_FAM_FIXED)             \
+                                     : launch(k_reduce<T, B2ODE_RED_NOT_CONVERGED>, grid, st, p, B2_FAM_FIXED))
+    return dtype == B2ODE_F64 ? B2_RED(double) : B2_RED(float);
+#undef B2_RED
+}

@@ -1,12 +1,14 @@
 """Public entry point with the reference's signature and dispatch (tfdiffeq/odeint.py:11-81)."""
 from .misc import _check_inputs
+from .multistep import AdamsBashforth, AdamsBashforthMoulton, VariableCoefficientAdamsBashforth
 from .solvers import (AdaptiveHeunSolver, Bosh3Solver, Dopri5Solver, Dopri8Solver, Euler, Heun, Midpoint, RK4,
                       Tsit5Solver)
 
-# tfdiffeq/odeint.py:11-25.  The three multistep Adams solvers of the reference (explicit_adams, fixed_adams,
-# adams) are outside this engine's scope: asking for them raises KeyError
-# exactly like any unknown method name does in the reference (odeint.py:77).
+# tfdiffeq/odeint.py:11-25
 SOLVERS = {
+    'explicit_adams': AdamsBashforth,
+    'fixed_adams': AdamsBashforthMoulton,
+    'adams': VariableCoefficientAdamsBashforth,
     'tsit5': Tsit5Solver,
     'dopri5': Dopri5Solver,
     'dopri8': Dopri8Solver,
