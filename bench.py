@@ -168,6 +168,75 @@ def run_reference(args, rank, world):
 # ------------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------------
+def tensor_core_func_block(dev, peaks):
+    """the reference's ODENet func (dense_odenet.py:85-92, 64 -> 256 -> 256 -> 64, relu) on 131 072 rows
+    inside dopri5 (rtol = atol = 1e-3, t in [0, 1]; fp32 state, TF32 tensor-core math).  One evaluation = one launch of
+    k_mlp3_tf32; `roofline` is that kernel against the measured dense tensor throughput."""
+    import tfdiffeq_b200 as tfd
+    Bm, Dm, Hm = 131072, 64, 256
+    torch.manual_seed(0)
+    m = tfd.rhs.DenseMLP(Dm, Hm, "relu").to(dev)
+    y0 = torch.randn(Bm, Dm, device=dev)
+    t = torch.tensor([0., 1.])
+    kw = dict(rtol=1e-3, atol=1e-3, method="dopri5")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def solve_ms(reps):
+        ts = []
+        for _ in range(reps):
+            flush.fill_(1)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            tfd.odeint(m, y0, t, **kw)
+            b.record()
+            torch.cuda.synchronize(dev)
+            ts.append(a.elapsed_time(b))
+        return sorted(ts)[len(ts) // 2]
+    for _ in range(2):
+        tfd.odeint(m, y0, t, **kw)
+    ms = solve_ms(5)
+    st = dict(tfd.last_stats)
+    m.tensor_cores = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    solve_ms(1)                                                   # cuBLAS handle / heuristics warm-up
+    ms_fp32 = solve_ms(3)
+    torch.backends.cuda.matmul.allow_tf32 = True
+    solve_ms(1)
+    ms_cublas_tf32 = solve_ms(3)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    m.tensor_cores = True
+    # the kernel alone, timed with events around each launch (inputs 32 MiB, L2 flushed)
+    x = torch.randn(Bm, Dm, device=dev)
+    ev = []
+    with torch.no_grad():
+        for _ in range(3):
+            m(0.0, x)
+        for _ in range(10):
+            flush.fill_(2)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            m(0.0, x)
+            b.record()
+            torch.cuda.synchronize(dev)
+            ev.append(a.elapsed_time(b))
+    k_ms = sorted(ev)[len(ev) // 2]
+    flops = 2.0 * Bm * (Dm * Hm + Hm * Hm + Hm * Dm)
+    tf = flops / (k_ms * 1e-3) / 1e12
+    # MEASURED_PEAKS.json holds dense bf16; TF32 runs at half the bf16 rate on this part
+    bf16 = peaks.get("bf16_tflops")                              # burst figure: this kernel is timed alone
+    peak_tf32 = (float(bf16) / 2.0) if bf16 else 1125.0
+    return {"workload": "odenet_mlp_64x256x256x64_relu_b131072_f32_dopri5", "ms_per_solve": ms, "nfe": st.get("nfe"),
+            "element_steps_per_s": st.get("n_accepted", 0) * Bm * Dm / (ms * 1e-3),
+            "ms_per_solve_torch_fp32_matmul": ms_fp32, "ms_per_solve_cublas_tf32_layers": ms_cublas_tf32,
+            "roofline": {"bound": "tensor", "kernel": "k_mlp3_tf32 (fc1-relu-fc2-relu-fc3 chained, one launch per evaluation)",
+                         "achieved": tf, "peak": peak_tf32,
+                         "peak_source": "half of MEASURED_PEAKS.json bf16_tflops (TF32 = bf16 / 2 on sm_100)" if bf16 else "fallback: 2250 / 2 TFLOP/s nominal",
+                         "unit": "TFLOP/s", "frac": tf / peak_tf32, "avg_launch_ms": k_ms,
+                         "traffic": 35.2e6, "algorithmic_bytes_per_launch": int(2 * Bm * Dm * 4),
+                         "note": "traffic = dram bytes of one ncu --set full capture (profiles/r01_mlp3_chained.md); the kernel is "
+                                 "bound by each SM re-streaming the 384 KB of weights per 128-row tile from L2, not by the MMAs"}}
+
+
 def headline_kernel_roofline(dev, peak):
     """The fused finalize kernel at the north-star size: 65 536 x 128 fp64 (64 MiB per buffer, 8 read streams
     = 512 MiB per launch, far beyond the 126 MB L2), timed with CUDA events around each launch."""
@@ -326,11 +395,20 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0:
         headline = None
         cpu = None
+        tc_func = None
         if world == 1:
             try:
                 headline = headline_kernel_roofline(dev, peak)
             except Exception as e:                                 # noqa: BLE001  (never lose the main line)
                 headline = {"error": repr(e)[:200]}
+            try:
+                try:
+                    peaks_json = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+                except Exception:                                  # noqa: BLE001
+                    peaks_json = {}
+                tc_func = tensor_core_func_block(dev, peaks_json)
+            except Exception as e:                                 # noqa: BLE001
+                tc_func = {"error": repr(e)[:200]}
             if not args.no_cpu_baseline:
                 backend, pt, pn = best_cpu_backend()
                 s = cpu_sample(60 if backend == "numpy" else 30, backend)
@@ -388,6 +466,7 @@ def run_ours(args, rank, world, local_rank):
                     "h2d_bytes_per_step": int(B * DIM * 8 + NPTS * 8), "d2h_bytes_per_step": int(NPTS * B * DIM * 8)},
             "gpu_launches": main_res["launches"],
             "other_paths": others,
+            "tensor_core_func": tc_func,
             "attempts_per_solve": main_res["n_acc"] + main_res["n_rej"],
             "wall_s_timed_region": main_res["wall"],
             "clocks": clocks,
