@@ -255,3 +255,30 @@ def test_mlp3_repacks_when_a_weight_changes():
         ref = m(0.0, x)
     assert not torch.equal(a, b)
     assert float((b - ref).abs().max()) <= 5e-3 * max(1.0, float(ref.abs().max()))
+
+
+@pytest.mark.parametrize("M,D,H", [(128, 64, 256), (256, 64, 256), (1000, 32, 64), (300, 16, 16), (257, 48, 80), (4096, 256, 256),
+                                   (148 * 128 * 2 + 77, 64, 128), (65, 112, 208), (131072, 64, 256)])
+def test_mlp3_cta_pair_kernel_equals_single_cta_kernel(M, D, H, monkeypatch):
+    """k_mlp3_tf32_pair (cta_group::2: two SMs share one weight stream on a 256-row tile) computes the same function,
+    bit for bit, as k_mlp3_tf32: the operands, the MMA shapes per row and the K order are identical."""
+    import tfdiffeq_b200 as tfd
+    torch.manual_seed(M + D + H)
+    m = tfd.rhs.DenseMLP(D, H, "tanh").to(DEV)
+    x = torch.randn(M, D, device=DEV)
+    ks = [torch.randn(M, D, device=DEV) for _ in range(3)]
+    L = lib()
+    st = L.State()
+    st.dt = 0.02
+    state = torch.frombuffer(bytearray(bytes(st)), dtype=torch.uint8).to(DEV)
+    outs = {}
+    for flag in ("0", "1", "1"):
+        monkeypatch.setenv("B2ODE_MLP3_PAIR", flag)
+        ys = torch.empty_like(x)
+        a = tfd.rhs.mlp3(x, m.fc1, m.fc2, m.fc3, "tanh")
+        b = tfd.rhs.mlp3(x, m.fc1, m.fc2, m.fc3, "tanh", stage=(ks, [0.3, -0.2, 0.1], state.data_ptr(), ys))
+        torch.cuda.synchronize()
+        outs.setdefault(flag, []).append((a, b, ys))
+    a0, b0, y0 = outs["0"][0]
+    for a1, b1, y1 in outs["1"]:
+        assert torch.equal(a0, a1) and torch.equal(b0, b1) and torch.equal(y0, y1)
