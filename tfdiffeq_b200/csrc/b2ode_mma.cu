@@ -74,6 +74,53 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
     return d;
 }
 
+// The same descriptor as two 32-bit words.  The high word is a constant; the low word is (address >> 4) | LBO, so a
+// K step of 8 TF32 (32 bytes) is `+ 2` and the next 16 KB block is `+ 1024`.  The MMA-issuing lane is a single thread:
+// every integer instruction it spends on descriptor arithmetic is ~4-5 cycles of MMA issue latency, and the unrolled
+// make_desc() form cost ~300 cycles per MMA against a tensor-pipe floor of 128 (scripts/micro/mma_rate.cu).
+constexpr uint32_t kDescHi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr & 0x3FFFF) >> 4) | (1u << 16); }
+
+// Four accumulating MMAs over one 32-column K block (cta_group 1 or 2).  Executed by ALL 32 lanes of the MMA warp,
+// convergently; `elect.sync` inside the statement picks the one lane that issues.  Written as `if (lane == 0) { mma }`
+// the instruction sits in a divergent region and nvcc feeds every operand through ELECT + R2UR.BROADCAST in a
+// per-thread waterfall loop (~380 cycles per MMA measured, tensor-pipe floor 128); in this form the operands are
+// computed in the uniform datapath and the four UTCHMMA issue back to back.
+template <int CG>
+__device__ __forceinline__ void mma_kblock_tf32(uint32_t tacc, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accum_first) {
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+        const uint64_t da = ((uint64_t)kDescHi << 32) | (uint64_t)(a_lo + 2u * ks);
+        const uint64_t db = ((uint64_t)kDescHi << 32) | (uint64_t)(b_lo + 2u * ks);
+        const uint32_t accum = ks > 0 ? 1u : accum_first;
+        if (CG == 1)
+            asm volatile(
+                "{\n\t.reg .pred p, q;\n\t"
+                "setp.ne.b32 p, %4, 0;\n\t"
+                "elect.sync _|q, 0xffffffff;\n\t"
+                "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tacc),
+                "l"(da), "l"(db), "r"(idesc), "r"(accum)
+                : "memory");
+        else
+            asm volatile(
+                "{\n\t.reg .pred p, q;\n\t"
+                "setp.ne.b32 p, %4, 0;\n\t"
+                "elect.sync _|q, 0xffffffff;\n\t"
+                "@q tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tacc),
+                "l"(da), "l"(db), "r"(idesc), "r"(accum)
+                : "memory");
+    }
+}
+
+// tcgen05.commit by one elected lane of a converged warp (same reasoning)
+__device__ __forceinline__ void commit_elect(uint32_t bar) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar)
+        : "memory");
+}
+
 __device__ __forceinline__ uint32_t make_idesc_tf32(int N) {
     uint32_t d = 0;
     d |= 1u << 4;                                         // D format F32
@@ -84,17 +131,22 @@ __device__ __forceinline__ uint32_t make_idesc_tf32(int N) {
     return d;                                             // A, B K-major; no negate; dense
 }
 
+// The spin loop lives INSIDE the asm statement: to the compiler the wait is one convergent instruction, so the control
+// flow of the calling warp stays provably uniform and the descriptor / barrier-address arithmetic of the MMA-issuing
+// warp is done in the uniform datapath.  With the loop written in C++ (exit condition = a per-thread asm output) every
+// tcgen05.mma operand went through ELECT + R2UR.BROADCAST, ~380 cycles per MMA against a 128-cycle tensor-pipe floor.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"(bar), "r"(parity)
-            : "memory");
-    } while (!ok);
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}" ::"r"(bar),
+        "r"(parity)
+        : "memory");
 }
 
 // compile-time activation: a run-time switch inlined per element bloats the unrolled epilogues past the
@@ -142,18 +194,18 @@ __device__ __forceinline__ void cluster_sync_all() {
 
 // for waits that last microseconds (keeps the spinning warps off the issue ports the working warps need)
 __device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    for (;;) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"(bar), "r"(parity)
-            : "memory");
-        if (ok) break;
-        __nanosleep(64);
-    }
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra WAIT_DONE;\n\t"
+        "nanosleep.u32 64;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}" ::"r"(bar),
+        "r"(parity)
+        : "memory");
 }
 
 __device__ __forceinline__ float apply_act(float v, int act) {
@@ -507,30 +559,14 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_dense_layer_tf32_ws(const __g
                 const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
                 mbar_wait(smem_u32(&bar_full[s]), ph);
                 asm volatile("tcgen05.fence::after_thread_sync;");
-                if (lane == 0) {
-                    uint8_t *sA = smem + s * kStageBytes, *sB = sA + kTileM * 128 * 2;
-#pragma unroll
-                    for (int kb = 0; kb < 2; ++kb) {
-#pragma unroll
-                        for (int ks = 0; ks < 4; ++ks) {
-                            const uint64_t da = make_desc(smem_u32(sA + kb * (kTileM * 128)) + ks * 32);
-                            const uint64_t db = make_desc(smem_u32(sB + kb * (256 * 128)) + ks * 32);
-                            const uint32_t accum = (c > 0 || kb > 0 || ks > 0) ? 1u : 0u;
-                            asm volatile(
-                                "{\n\t.reg .pred p;\n\t"
-                                "setp.ne.b32 p, %4, 0;\n\t"
-                                "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-                                ::"r"(tacc), "l"(da), "l"(db), "r"(idesc), "r"(accum)
-                                : "memory");
-                        }
-                    }
-                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar_empty[s]))
-                                 : "memory");
-                    if (c == chunks - 1)
-                        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar_tfull[ab]))
-                                     : "memory");
+                {
+                    const uint32_t a_lo = desc_lo(smem_u32(smem)) + s * (uint32_t)(kStageBytes >> 4);
+                    const uint32_t b_lo = a_lo + (uint32_t)((kTileM * 128 * 2) >> 4);
+                    mma_kblock_tf32<1>(tacc, a_lo, b_lo, idesc, c > 0 ? 1u : 0u);
+                    mma_kblock_tf32<1>(tacc, a_lo + (uint32_t)((kTileM * 128) >> 4), b_lo + (uint32_t)((256 * 128) >> 4), idesc, 1u);
+                    commit_elect(smem_u32(&bar_empty[s]));
+                    if (c == chunks - 1) commit_elect(smem_u32(&bar_tfull[ab]));
                 }
-                __syncwarp();
             }
         }
     } else {
@@ -610,6 +646,7 @@ constexpr int kEpiWarps = 4;                               // 4, or 8 (two per T
 constexpr int kChainThreads = (kProdWarps + 1 + kEpiWarps + 1) * 32;
 constexpr int kLoaderWarp = kProdWarps + 1 + kEpiWarps;
 constexpr int kMaxRing = 8;
+constexpr int kMlp3ActSlots = 4;           // ACT ring depth of k_mlp3_tf32 (8 = hold the whole activation tile)
 constexpr bool kMlp3PairDefault = false;   // k_mlp3_tf32_pair (cta_group::2) instead of k_mlp3_tf32
 #ifndef B2_BULK_PIECE
 #define B2_BULK_PIECE 16384
@@ -624,6 +661,7 @@ struct Mlp3Params {
     float *out;                        // [M, D]
     int M, D, H, act;
     int act_bytes, stage_bytes, stages;
+    int act_slots;                     // R: ACT holds R K blocks (16 KB each); K block kb lives in slot kb % R
 };
 
 __host__ __device__ inline int mlp3_subs(int K) { return (K + kSub - 1) / kSub; }
@@ -754,9 +792,15 @@ __device__ __forceinline__ void store_tile_regs(uint8_t *act_buf, int tid, const
 // K block at a time; each finished K block is handed to the MMA warp through its own mbarrier (`bar_kb`, one arrival
 // per epilogue warp), so the next GEMM runs one K block behind this epilogue instead of after it.
 // `bias` is the shared-memory copy (zero-filled when the layer has none, padded).  ncols is a multiple of 16.
+//
+// ACT is a ring of R slots: K block kb is written to slot kb % R.  For kb >= R the slot still holds K block kb - R of the
+// same activation matrix until the GEMM that trails this epilogue has consumed it; the MMA warp commits `bar_free + slot`
+// after every K block it consumes, and `gemm_no` (2 * tile + {0: h1, 1: h2}) locates the commit to wait for:
+// every GEMM over K = ncols commits ceil((nblk - slot) / R) times on a slot.
 template <int ACT>
 __device__ __noinline__ void epilogue_to_act_t(uint32_t act_s, uint32_t tmem_acc, int q, int half, int lane, int ncols,
-                                               const float *bias, uint32_t bar_kb, bool pair) {
+                                               const float *bias, uint32_t bar_kb, bool pair, int R, uint32_t bar_free,
+                                               uint32_t gemm_no) {
     const int row = q * 32 + lane;
     const uint32_t row_s = act_s + (uint32_t)row * 128u;                  // (row >> 3) * 1024 + (row & 7) * 128
     const uint32_t rx = (uint32_t)(row & 7);
@@ -776,7 +820,13 @@ __device__ __noinline__ void epilogue_to_act_t(uint32_t act_s, uint32_t tmem_acc
             : "r"(taddr));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         CLK(q == 0 && half == 0 && lane == 0);
-        const uint32_t blk_s = row_s + (uint32_t)(c0 / kSub) * (kTileM * 128);      // K block of 32 columns: [128 rows x 128 B]
+        const int kb = c0 / kSub, slot = kb % R;
+        if (kb >= R) {
+            const int nblk = ncols_pad / kSub;
+            const uint32_t cnt = (uint32_t)((nblk - slot + R - 1) / R);          // commits per GEMM on this slot
+            mbar_wait(bar_free + (uint32_t)slot * 8u, (gemm_no * cnt + (uint32_t)(kb / R) - 1u) & 1u);
+        }
+        const uint32_t blk_s = row_s + (uint32_t)slot * (kTileM * 128);            // K block of 32 columns: [128 rows x 128 B]
         const bool second_half = c0 + 16 < ncols;                                  // warp-uniform: ncols is a multiple of 16
         // all 32 values first (independent 5-op chains the scheduler can interleave), then the eight 16-byte stores;
         // the store asm carries no memory clobber so that nothing pins the bias reads or the math between stores --
@@ -810,12 +860,13 @@ __device__ __noinline__ void epilogue_to_act_t(uint32_t act_s, uint32_t tmem_acc
 }
 
 __device__ __forceinline__ void epilogue_to_act(uint32_t act_s, uint32_t tmem_acc, int q, int half, int lane, int ncols,
-                                                const float *bias, int act, uint32_t bar_kb, bool pair = false) {
+                                                const float *bias, int act, uint32_t bar_kb, bool pair, int R, uint32_t bar_free,
+                                                uint32_t gemm_no) {
     switch (act) {
-        case 1: epilogue_to_act_t<1>(act_s, tmem_acc, q, half, lane, ncols, bias, bar_kb, pair); break;
-        case 2: epilogue_to_act_t<2>(act_s, tmem_acc, q, half, lane, ncols, bias, bar_kb, pair); break;
-        case 3: epilogue_to_act_t<3>(act_s, tmem_acc, q, half, lane, ncols, bias, bar_kb, pair); break;
-        default: epilogue_to_act_t<0>(act_s, tmem_acc, q, half, lane, ncols, bias, bar_kb, pair); break;
+        case 1: epilogue_to_act_t<1>(act_s, tmem_acc, q, half, lane, ncols, bias, bar_kb, pair, R, bar_free, gemm_no); break;
+        case 2: epilogue_to_act_t<2>(act_s, tmem_acc, q, half, lane, ncols, bias, bar_kb, pair, R, bar_free, gemm_no); break;
+        case 3: epilogue_to_act_t<3>(act_s, tmem_acc, q, half, lane, ncols, bias, bar_kb, pair, R, bar_free, gemm_no); break;
+        default: epilogue_to_act_t<0>(act_s, tmem_acc, q, half, lane, ncols, bias, bar_kb, pair, R, bar_free, gemm_no); break;
     }
 }
 
@@ -870,6 +921,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) k_mlp3_tf32(const __grid_con
     __shared__ __align__(8) uint64_t bar_full[kMaxRing], bar_empty[kMaxRing];
     __shared__ __align__(8) uint64_t bar_a1, bar_actfree, bar_t1, bar_t2, bar_outdone;
     __shared__ __align__(8) uint64_t bar_a2[8], bar_a3[8];             // act(h1) / act(h2), one per 32-column K block
+    __shared__ __align__(8) uint64_t bar_hfree[8];                     // ACT slot consumed by the trailing GEMM
     __shared__ uint32_t tmem_slot;
     __shared__ __align__(16) float sbias[3][256];
 
@@ -903,6 +955,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) k_mlp3_tf32(const __grid_con
         for (int i = 0; i < 8; ++i) {
             init(&bar_a2[i], 4u);                // one arrival per epilogue warp
             init(&bar_a3[i], 4u);
+            init(&bar_hfree[i], 1u);             // tcgen05.commit after the K block in that slot
         }
         asm volatile("fence.mbarrier_init.release.cluster;");
     }
@@ -995,6 +1048,10 @@ __global__ void __launch_bounds__(kChainThreads, 1) k_mlp3_tf32(const __grid_con
         }
     } else if (warp == kProdWarps) {
         // ===== MMA issuer =====
+        const uint32_t act_lo = desc_lo(smem_u32(act_buf)), ring_lo = desc_lo(smem_u32(ring));
+        const uint32_t empty_s = smem_u32(&bar_empty[0]), hfree_s = smem_u32(&bar_hfree[0]);
+        const uint32_t R = (uint32_t)P.act_slots;
+        const bool ring_act = sub2 > P.act_slots;
         uint32_t it = 0, tcount = 0;
         for (int tile = blockIdx.x; tile < tiles_m; tile += gridDim.x, ++tcount) {
             const uint32_t tp = tcount & 1u;
@@ -1012,42 +1069,27 @@ __global__ void __launch_bounds__(kChainThreads, 1) k_mlp3_tf32(const __grid_con
                 TRACE(tcount, 3 + l * 2);
                 asm volatile("tcgen05.fence::after_thread_sync;");
                 const int grp = P.stage_bytes / (Nl * 128);
+                const uint32_t b_step = (uint32_t)(Nl * 128) >> 4;          // descriptor units per weight K block
+                uint32_t slot = 0;                                          // ACT slot of K block c + kb (= (c + kb) % R)
                 for (int c = 0; c < nsub; c += grp, ++it) {
                     const uint32_t s = it % S, ph = (it / S) & 1u;
                     const int nb = nsub - c < grp ? nsub - c : grp;
+#ifndef B2_MLP3_NOWAIT_W
                     mbar_wait(smem_u32(&bar_full[s]), ph);
-                    asm volatile("tcgen05.fence::after_thread_sync;");
+#endif
+                    uint32_t b_lo = ring_lo + s * ((uint32_t)P.stage_bytes >> 4);
                     for (int kb = 0; kb < nb; ++kb) {
                         if (l == 1) mbar_wait(smem_u32(&bar_a2[c + kb]), tp);      // this K block of act(h1) is in ACT
                         if (l == 2) mbar_wait(smem_u32(&bar_a3[c + kb]), tp);
                         asm volatile("tcgen05.fence::after_thread_sync;");
-                        if (lane == 0) {
-                            const uint32_t a_blk = smem_u32(act_buf + (c + kb) * (kTileM * 128));
-                            const uint32_t b_blk = smem_u32(ring + (size_t)s * P.stage_bytes + (size_t)kb * Nl * 128);
-#pragma unroll
-                            for (int ks = 0; ks < 4; ++ks) {
-                                const uint64_t da = make_desc(a_blk + ks * 32), db = make_desc(b_blk + ks * 32);
-                                const uint32_t accum = (c + kb > 0 || ks > 0) ? 1u : 0u;
-                                asm volatile(
-                                    "{\n\t.reg .pred p;\n\t"
-                                    "setp.ne.b32 p, %4, 0;\n\t"
-                                    "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-                                    ::"r"(tacc), "l"(da), "l"(db), "r"(idesc), "r"(accum)
-                                    : "memory");
-                            }
-                        }
+                        mma_kblock_tf32<1>(tacc, act_lo + slot * (uint32_t)((kTileM * 128) >> 4), b_lo, idesc, (c + kb) > 0 ? 1u : 0u);
+                        if (ring_act && l > 0) commit_elect(hfree_s + slot * 8u);   // the slot may be overwritten once these MMAs have read it
+                        b_lo += b_step;
+                        if (++slot == R) slot = 0;
                     }
-                    if (lane == 0) {
-                        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar_empty[s]))
-                                     : "memory");
-                        if (c + nb == nsub) {
-                            // GEMM3 complete = ACT may be refilled AND the output accumulator is final
-                            uint64_t *done = l == 0 ? &bar_t1 : (l == 1 ? &bar_t2 : &bar_actfree);
-                            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(done))
-                                         : "memory");
-                        }
-                    }
-                    __syncwarp();
+                    commit_elect(empty_s + s * 8u);
+                    // GEMM3 complete = ACT may be refilled AND the output accumulator is final
+                    if (c + nb == nsub) commit_elect(smem_u32(l == 0 ? &bar_t1 : (l == 1 ? &bar_t2 : &bar_actfree)));
                 }
                 TRACE(tcount, 4 + l * 2);
             }
@@ -1063,13 +1105,15 @@ __global__ void __launch_bounds__(kChainThreads, 1) k_mlp3_tf32(const __grid_con
             if (q == 0 && half == 0) TRACE(tcount, 9);
             asm volatile("tcgen05.fence::after_thread_sync;");
             const uint32_t accA = tp ? acc1 : acc0, accB = tp ? acc0 : acc1;
-            epilogue_to_act(smem_u32(act_buf), accA, q, half, lane, H, sbias[0], P.act, smem_u32(&bar_a2[0]));
+            epilogue_to_act(smem_u32(act_buf), accA, q, half, lane, H, sbias[0], P.act, smem_u32(&bar_a2[0]), false, P.act_slots,
+                            smem_u32(&bar_hfree[0]), 2u * tcount);
             if (q == 0 && half == 0) TRACE(tcount, 10);
             // h2 -> ACT
             mbar_wait(smem_u32(&bar_t2), tp);
             if (q == 0 && half == 0) TRACE(tcount, 11);
             asm volatile("tcgen05.fence::after_thread_sync;");
-            epilogue_to_act(smem_u32(act_buf), accB, q, half, lane, H, sbias[1], P.act, smem_u32(&bar_a3[0]));
+            epilogue_to_act(smem_u32(act_buf), accB, q, half, lane, H, sbias[1], P.act, smem_u32(&bar_a3[0]), false, P.act_slots,
+                            smem_u32(&bar_hfree[0]), 2u * tcount + 1u);
             if (q == 0 && half == 0) TRACE(tcount, 12);
         }
     }
@@ -1097,10 +1141,13 @@ __device__ __forceinline__ uint32_t make_idesc_tf32_m256(int N) {
     return d;
 }
 
-__device__ __forceinline__ void commit_pair(uint64_t *bar) {
-    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
-                 "h"((unsigned short)3)
-                 : "memory");
+__device__ __forceinline__ void commit_pair(uint64_t *bar) {      // by one elected lane of the converged MMA warp
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}" ::"r"(smem_u32(bar)),
+        "h"((unsigned short)3)
+        : "memory");
 }
 
 __global__ void __launch_bounds__(kChainThreads, 1) k_mlp3_tf32_pair(const __grid_constant__ Mlp3Params P) {
@@ -1257,6 +1304,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) k_mlp3_tf32_pair(const __gri
             }
         } else {
             // ===== MMA issuer for the pair =====
+            const uint32_t act_lo = desc_lo(smem_u32(act_buf)), ring_lo = desc_lo(smem_u32(ring));
             uint32_t it = 0, tcount = 0;
             for (int pair = cluster_id; pair < n_pairs; pair += n_clusters, ++tcount) {
                 const uint32_t tp = tcount & 1u;
@@ -1281,27 +1329,12 @@ __global__ void __launch_bounds__(kChainThreads, 1) k_mlp3_tf32_pair(const __gri
                             if (l == 1) mbar_wait_cluster(smem_u32(&bar_a2[c + kb]), tp);
                             if (l == 2) mbar_wait_cluster(smem_u32(&bar_a3[c + kb]), tp);
                             asm volatile("tcgen05.fence::after_thread_sync;");
-                            if (lane == 0) {
-                                const uint32_t a_blk = smem_u32(act_buf + (c + kb) * (kTileM * 128));
-                                const uint32_t b_blk = smem_u32(ring + (size_t)s * P.stage_bytes) + (uint32_t)kb * half;
-#pragma unroll
-                                for (int ks = 0; ks < 4; ++ks) {
-                                    const uint64_t da = make_desc(a_blk + ks * 32), db = make_desc(b_blk + ks * 32);
-                                    const uint32_t accum = (c + kb > 0 || ks > 0) ? 1u : 0u;
-                                    asm volatile(
-                                        "{\n\t.reg .pred p;\n\t"
-                                        "setp.ne.b32 p, %4, 0;\n\t"
-                                        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-                                        ::"r"(tacc), "l"(da), "l"(db), "r"(idesc), "r"(accum)
-                                        : "memory");
-                                }
-                            }
+                            mma_kblock_tf32<2>(tacc, act_lo + (uint32_t)(c + kb) * (uint32_t)((kTileM * 128) >> 4),
+                                               ring_lo + s * ((uint32_t)P.stage_bytes >> 4) + (uint32_t)kb * (half >> 4), idesc,
+                                               (c + kb) > 0 ? 1u : 0u);
                         }
-                        if (lane == 0) {
-                            commit_pair(&bar_empty[s]);
-                            if (c + nb == nsub) commit_pair(l == 0 ? &bar_t1 : (l == 1 ? &bar_t2 : &bar_actfree));
-                        }
-                        __syncwarp();
+                        commit_pair(&bar_empty[s]);
+                        if (c + nb == nsub) commit_pair(l == 0 ? &bar_t1 : (l == 1 ? &bar_t2 : &bar_actfree));
                     }
                     TRACE(tcount, 4 + l * 2);
                 }
@@ -1317,12 +1350,12 @@ __global__ void __launch_bounds__(kChainThreads, 1) k_mlp3_tf32_pair(const __gri
             if (q == 0 && half == 0) TRACE(tcount, 9);
             asm volatile("tcgen05.fence::after_thread_sync;");
             const uint32_t accA = tp ? acc1 : acc0, accB = tp ? acc0 : acc1;
-            epilogue_to_act(smem_u32(act_buf), accA, q, half, lane, H, sbias[0], P.act, smem_u32(&bar_a2[0]), true);
+            epilogue_to_act(smem_u32(act_buf), accA, q, half, lane, H, sbias[0], P.act, smem_u32(&bar_a2[0]), true, 8, 0u, 0u);
             if (q == 0 && half == 0) TRACE(tcount, 10);
             mbar_wait(smem_u32(&bar_t2), tp);
             if (q == 0 && half == 0) TRACE(tcount, 11);
             asm volatile("tcgen05.fence::after_thread_sync;");
-            epilogue_to_act(smem_u32(act_buf), accB, q, half, lane, H, sbias[1], P.act, smem_u32(&bar_a3[0]), true);
+            epilogue_to_act(smem_u32(act_buf), accB, q, half, lane, H, sbias[1], P.act, smem_u32(&bar_a3[0]), true, 8, 0u, 0u);
             if (q == 0 && half == 0) TRACE(tcount, 12);
         }
     }
@@ -1452,7 +1485,14 @@ extern "C" int b2ode_mlp3(const void *x, const void *const *k, const double *coe
     const bool pair = pair_env ? (atoi(pair_env) != 0) : kMlp3PairDefault;
     // shared memory: ACT (input chunks are produced 64 columns = 2 blocks at a time), the weight ring, the output tiles
     const int blocks_in = 2 * ((D + kKChunk - 1) / kKChunk), blocks_h = mlp3_subs(H);
-    P.act_bytes = (blocks_in > blocks_h ? blocks_in : blocks_h) * (kTileM * 128);
+    int slots = blocks_in > blocks_h ? blocks_in : blocks_h;
+    // the single-CTA kernel streams act(h) through a ring of R slots (GEMM2 / GEMM3 trail the epilogues by one K block)
+    // so that the weight ring can be deeper: a stage refill takes ~1.3 us, the MMAs of a K block ~0.4 us
+    const char *slots_env = getenv("B2ODE_MLP3_ACT_SLOTS");
+    int want = slots_env ? atoi(slots_env) : kMlp3ActSlots;
+    if (!pair && want >= 2 && want < slots && want >= blocks_in) slots = want;
+    P.act_slots = pair ? 8 : slots;
+    P.act_bytes = slots * (kTileM * 128);
     P.stage_bytes = (H > D ? H : D) * 128 / (pair ? 2 : 1);
     const int budget = 227 * 1024 - 4096 - 1024 - P.act_bytes - kTileScratchBytes;      // static (biases, barriers) + alignment slack
     int stages = budget / P.stage_bytes;
