@@ -646,7 +646,7 @@ constexpr int kEpiWarps = 4;                               // 4, or 8 (two per T
 constexpr int kChainThreads = (kProdWarps + 1 + kEpiWarps + 1) * 32;
 constexpr int kLoaderWarp = kProdWarps + 1 + kEpiWarps;
 constexpr int kMaxRing = 8;
-constexpr int kMlp3ActSlots = 4;           // ACT ring depth of k_mlp3_tf32 (8 = hold the whole activation tile)
+constexpr int kMlp3ActSlots = 8;           // ACT ring depth of k_mlp3_tf32: 8 = hold the whole activation tile (measured best); 2..7 = ring
 constexpr bool kMlp3PairDefault = false;   // k_mlp3_tf32_pair (cta_group::2) instead of k_mlp3_tf32
 #ifndef B2_BULK_PIECE
 #define B2_BULK_PIECE 16384
@@ -836,10 +836,19 @@ __device__ __noinline__ void epilogue_to_act_t(uint32_t act_s, uint32_t tmem_acc
         for (int w = 0; w < 32; w += 4) {
             const float4 bv = *reinterpret_cast<const float4 *>(bias + c0 + w);       // broadcast read
             const bool in = w < 16 || second_half;
-            t[w + 0] = in ? to_tf32_fast(act_t<ACT>(__uint_as_float(r[w + 0]) + bv.x)) : 0u;
-            t[w + 1] = in ? to_tf32_fast(act_t<ACT>(__uint_as_float(r[w + 1]) + bv.y)) : 0u;
-            t[w + 2] = in ? to_tf32_fast(act_t<ACT>(__uint_as_float(r[w + 2]) + bv.z)) : 0u;
-            t[w + 3] = in ? to_tf32_fast(act_t<ACT>(__uint_as_float(r[w + 3]) + bv.w)) : 0u;
+            // two elements per instruction (Blackwell's packed fp32x2 add / mul / fma: same IEEE results as the scalar
+            // forms): bias add, activation, then the Veltkamp split g = 8193 v, d = v - g, r = g + d
+            float2 v01 = __fadd2_rn(make_float2(__uint_as_float(r[w + 0]), __uint_as_float(r[w + 1])), make_float2(bv.x, bv.y));
+            float2 v23 = __fadd2_rn(make_float2(__uint_as_float(r[w + 2]), __uint_as_float(r[w + 3])), make_float2(bv.z, bv.w));
+            v01 = make_float2(act_t<ACT>(v01.x), act_t<ACT>(v01.y));
+            v23 = make_float2(act_t<ACT>(v23.x), act_t<ACT>(v23.y));
+            const float2 c8193 = make_float2(8193.0f, 8193.0f), m1 = make_float2(-1.0f, -1.0f);
+            const float2 g01 = __fmul2_rn(v01, c8193), g23 = __fmul2_rn(v23, c8193);
+            const float2 r01 = __fadd2_rn(g01, __ffma2_rn(g01, m1, v01)), r23 = __fadd2_rn(g23, __ffma2_rn(g23, m1, v23));
+            t[w + 0] = in ? __float_as_uint(r01.x) : 0u;
+            t[w + 1] = in ? __float_as_uint(r01.y) : 0u;
+            t[w + 2] = in ? __float_as_uint(r23.x) : 0u;
+            t[w + 3] = in ? __float_as_uint(r23.y) : 0u;
         }
 #pragma unroll
         for (int w = 0; w < 32; w += 4)
