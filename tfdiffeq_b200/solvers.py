@@ -40,6 +40,29 @@ def _require_cuda(y0):
     return dev, dt
 
 
+_PINNED_STATE = {}
+_PINNED_BUSY = set()
+
+
+def _pinned_acquire(dev, nbytes=256):
+    """A reusable page-locked landing buffer for device-state polls, one per device and size (page-locking a fresh
+    buffer costs more than launching the whole fused solve).  Returns (buffer, key); hand the key back to
+    `_pinned_release`.  A nested solve on the same device (func calling odeint) gets a private buffer."""
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), int(nbytes))
+    if key in _PINNED_BUSY:
+        return torch.empty(int(nbytes), dtype=torch.uint8).pin_memory(), None
+    buf = _PINNED_STATE.get(key)
+    if buf is None:
+        buf = _PINNED_STATE[key] = torch.empty(int(nbytes), dtype=torch.uint8).pin_memory()
+    _PINNED_BUSY.add(key)
+    return buf, key
+
+
+def _pinned_release(key):
+    if key is not None:
+        _PINNED_BUSY.discard(key)
+
+
 class _Segments(object):
     """Engine-owned flat buffers: one allocation per role, tuple components at 16-byte aligned offsets."""
 
@@ -246,10 +269,13 @@ class AdaptiveStepsizeODESolver(object):
         if rc == -3:          # batch larger than what can stay co-resident: use the generic path
             return None
         check(rc)
-        host = torch.empty(256, dtype=torch.uint8).pin_memory()
-        host.copy_(state_dev, non_blocking=True)
-        stream.synchronize()
-        final = _lib.State.from_buffer_copy(host.numpy().tobytes())
+        host, hkey = _pinned_acquire(dev)
+        try:
+            host.copy_(state_dev, non_blocking=True)
+            stream.synchronize()
+            final = _lib.State.from_buffer_copy(host.numpy().tobytes())
+        finally:
+            _pinned_release(hkey)
         attempts = int(final.n_acc + final.n_rej)
         nfe = 1 + (1 if self.first_step is None else 0) + (tab.n_k - 1) * attempts
         self.stats = dict(n_accepted=int(final.n_acc), n_rejected=int(final.n_rej), nfe=nfe, attempts_enqueued=attempts,
@@ -279,6 +305,7 @@ class AdaptiveStepsizeODESolver(object):
 
         handle = C.c_void_p()
         check(lib.b2ode_adaptive_create(C.byref(handle), C.byref(desc)))
+        pinned_key = None
         try:
             buf = _lib.AdaptiveBuffers()
             buf.state = state_dev.data_ptr()
@@ -434,6 +461,7 @@ class AdaptiveStepsizeODESolver(object):
             stream.synchronize()      # outputs are complete; also keeps Y0/F0/S alive until the kernels ran
             del prev_last, graph_ks, graph
         finally:
+            _pinned_release(pinned_key)
             lib.b2ode_adaptive_destroy(handle)
         return tuple(outs)
 
