@@ -144,6 +144,15 @@ def build_cases():
     add("lorenz_b16_adams", "lorenz", _lorenz_y0(16), np.arange(11) * 0.05, method="adams", rtol=1e-6, atol=1e-8)
     add("lv_adams_unknown_opt", "lv", lv0, np.linspace(0., 0.2, 3), method="adams", rtol=1e-5, atol=1e-7,
         options=dict(bogus=1), expect_error="UserWarning")
+    # --- the reference's DETEST benchmark (tests/DETEST/run.py: [0, 20], dopri5 and adams, tol = rtol = atol) ----------
+    from detest_problems import make as _detest
+    t20 = np.array([0.0, 5.0, 20.0])
+    for nm, method, tol in [("A3", "dopri5", 1e-6), ("B1", "dopri5", 1e-6), ("B4", "dopri5", 1e-9), ("C3", "dopri5", 1e-6),
+                            ("C4", "dopri8", 1e-9), ("D3", "dopri5", 1e-6), ("D5", "dopri5", 1e-3), ("E2", "dopri5", 1e-6),
+                            ("E5", "dopri5", 1e-6), ("B1", "adams", 1e-6), ("C3", "adams", 1e-6), ("E2", "adams", 1e-3),
+                            ("A4", "adams", 1e-6)]:
+        add("detest_%s_%s" % (nm, method), "detest", np.asarray(_detest(nm)[1]), t20, method=method, rtol=tol, atol=tol,
+            pkw=dict(name=nm))
     return C
 
 

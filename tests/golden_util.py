@@ -41,4 +41,6 @@ def dt_trace_rtol(case):
     rounding noise), so the dt trace is a soft check; the hard checks are values and accept/reject counts."""
     if case["dtype"] != "float64":
         return 5e-2
+    if case["method"] == "dopri8" and case["rtol"] <= 1e-9:
+        return 5e-2           # 8th order at 1e-9: the estimate is already at the noise floor on smooth problems
     return 1e-5 if case["rtol"] >= 1e-9 else 5e-2

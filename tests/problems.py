@@ -161,5 +161,16 @@ class TimeDependentTridiag(object):
         return y @ self.Tt + 0.01 * t
 
 
-PROBLEMS = {"constant": Constant, "sine": Sine, "linear": Linear, "lv": LotkaVolterra, "lorenz": Lorenz,
+class Detest(object):
+    """One problem of the reference's DETEST benchmark (tests/DETEST/detest.py), see tests/detest_problems.py."""
+
+    def __init__(self, backend="numpy", dtype="float64", device=None, name="B1"):
+        from detest_problems import make
+        self.f, self.y0, self.exact = make(name, _xp(backend), device)
+
+    def __call__(self, t, y):
+        return self.f(t, y)
+
+
+PROBLEMS = {"detest": Detest, "constant": Constant, "sine": Sine, "linear": Linear, "lv": LotkaVolterra, "lorenz": Lorenz,
             "spiral": Spiral, "spiral_mlp": SpiralMLP, "tuple_decay": TupleDecay, "tridiag": TimeDependentTridiag}
