@@ -180,3 +180,18 @@ def test_adams_weights_are_exact_and_match_the_oracle():
         for k in range(2, 21):
             assert adams_weights(k, False) == (ns["_BASHFORTH_COEFFICIENTS"][k], ns["_DIVISOR"][k])
             assert adams_weights(k, True) == (ns["_MOULTON_COEFFICIENTS"][k], ns["_DIVISOR"][k])
+
+
+def test_multistep_host_controller_matches_the_oracle():
+    """tfdiffeq/misc.py:267-287 restated twice (product host code for the Adams solver, oracle): same numbers."""
+    from tfdiffeq_b200.multistep import _optimal_step_size
+    rng = np.random.default_rng(0)
+    for _ in range(300):
+        dt = float(10 ** rng.uniform(-6, 0))
+        ratios = [float(10 ** rng.uniform(-8, 3)) for _ in range(int(rng.integers(1, 4)))]
+        order = int(rng.integers(1, 13))
+        got = _optimal_step_size(dt, ratios, 0.9, 10.0, 0.2, order)
+        want = float(np_ref.optimal_step_size(dt, tuple(np.float64(r) for r in ratios), 0.9, 10.0, 0.2, order=order))
+        assert got == want or abs(got - want) <= 4e-16 * abs(want), (dt, ratios, order, got, want)
+    assert _optimal_step_size(0.1, [0.0, 0.0], 0.9, 10.0, 0.2, 3) == 1.0
+    assert np.isnan(_optimal_step_size(0.1, [float("nan"), 0.5], 0.9, 10.0, 0.2, 3))
