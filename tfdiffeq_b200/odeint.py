@@ -4,22 +4,13 @@ from .multistep import AdamsBashforth, AdamsBashforthMoulton, VariableCoefficien
 from .solvers import (AdaptiveHeunSolver, Bosh3Solver, Dopri5Solver, Dopri8Solver, Euler, Heun, Midpoint, RK4,
                       Tsit5Solver)
 
-# tfdiffeq/odeint.py:11-25
-SOLVERS = {
-    'explicit_adams': AdamsBashforth,
-    'fixed_adams': AdamsBashforthMoulton,
-    'adams': VariableCoefficientAdamsBashforth,
-    'tsit5': Tsit5Solver,
-    'dopri5': Dopri5Solver,
-    'dopri8': Dopri8Solver,
-    'bosh3': Bosh3Solver,
-    'euler': Euler,
-    'midpoint': Midpoint,
-    'rk4': RK4,
-    'huen': Heun,
-    'heun': Heun,
-    'adaptive_heun': AdaptiveHeunSolver,
-}
+# method name -> solver class; the names (including the historical 'huen' spelling) are the reference's
+# (tfdiffeq/odeint.py:11-25)
+_ADAPTIVE_RK = dict(dopri5=Dopri5Solver, dopri8=Dopri8Solver, bosh3=Bosh3Solver, tsit5=Tsit5Solver,
+                    adaptive_heun=AdaptiveHeunSolver)
+_FIXED_GRID = dict(euler=Euler, midpoint=Midpoint, rk4=RK4, heun=Heun, huen=Heun)
+_MULTISTEP = dict(adams=VariableCoefficientAdamsBashforth, fixed_adams=AdamsBashforthMoulton, explicit_adams=AdamsBashforth)
+SOLVERS = dict(_ADAPTIVE_RK, **_FIXED_GRID, **_MULTISTEP)
 
 
 def odeint(func, y0, t, rtol=1e-7, atol=1e-9, method=None, options=None):
@@ -34,18 +25,12 @@ def odeint(func, y0, t, rtol=1e-7, atol=1e-9, method=None, options=None):
     step-size underflow, non-finite states or ``max_num_steps``; unknown option keys only warn.
     """
     tensor_input, func, y0, t = _check_inputs(func, y0, t)
-    if options is None:
-        options = {}
-    elif method is None:
-        raise ValueError('cannot supply `options` without specifying `method`')
-    if method is None:
-        method = 'dopri5'
-    solver = SOLVERS[method](func, y0, rtol=rtol, atol=atol, **options)
+    if options is not None and method is None:
+        raise ValueError('cannot supply `options` without specifying `method`')      # odeint.py:72-73
+    solver_cls = SOLVERS['dopri5' if method is None else method]                     # unknown name: KeyError (:77)
+    odeint.last_solver = solver = solver_cls(func, y0, rtol=rtol, atol=atol, **(options or {}))
     solution = solver.integrate(t)
-    odeint.last_solver = solver
-    if tensor_input:
-        solution = solution[0]
-    return solution
+    return solution[0] if tensor_input else solution
 
 
 odeint.last_solver = None
