@@ -33,7 +33,7 @@ extern "C" {
 #endif
 
 #define B2ODE_ABI_VERSION 1
-#define B2ODE_MAXSEG 8      /* tuple components per state                      */
+#define B2ODE_MAXSEG 12     /* tuple components per state (odeint_adjoint of an n-tuple needs 2n + 2) */
 #define B2ODE_MAXK 14       /* k-buffers per step (dopri8: 14)                 */
 #define B2ODE_MAXPEERS 8    /* ranks in a shared-step group (one NVSwitch box) */
 
@@ -79,7 +79,7 @@ typedef struct b2ode_state {
     uint64_t xseq;          /* cross-GPU exchange sequence number                        */
     uint64_t klast[B2ODE_MAXSEG]; /* device address of k_{s-1} of the attempt just finalized, per segment:
                                      read by the next attempt's stage 0 when it commits an accepted step  */
-    double reserved_t[7];
+    double reserved_t[3];
 } b2ode_state;
 
 /* Description of an adaptive Runge-Kutta solve.  Restates `_ButcherTableau` (tfdiffeq/rk_common.py:5) plus
@@ -188,6 +188,10 @@ int b2ode_mailbox_close(void *peer_ptr);
 int b2ode_mailbox_destroy(void *dev_ptr);
 /* element count of every segment over the WHOLE group (the mean in misc.py:262 is over all ranks' elements) */
 int b2ode_comm_set_global_len(b2ode_solver *s, const int64_t *global_len);
+/* bit i set: tuple component i is REPLICATED -- every rank holds the whole component with bit-identical values (the
+ * parameter / time adjoints of odeint_adjoint after their all-reduce, tfdiffeq/adjoint.py:97-107): its error-norm
+ * partials are taken from the local rank alone and its global_len is the local length. */
+int b2ode_comm_set_replicated(b2ode_solver *s, unsigned segment_mask);
 
 /* ---- built-in right-hand sides: the whole adaptive solve in one persistent kernel ---------- */
 
@@ -204,6 +208,9 @@ int b2ode_comm_set_global_len(b2ode_solver *s, const int64_t *global_len);
  * Returns B2ODE_ENOMEM when the batch exceeds what the device can keep co-resident (caller falls back to the
  * generic path).  time_sign = -1 integrates the reversed system of tfdiffeq/misc.py:318-321. */
 size_t b2ode_fused_workspace_bytes(int64_t n_trajectories);
+/* Largest per-device batch b2ode_fused_solve keeps co-resident for this tableau / dtype / right-hand side on the
+ * current device (< 0: error).  Asked before launching so that all shards of a shared-step group take the same path. */
+int64_t b2ode_fused_capacity(const b2ode_adaptive_desc *desc, int rhs_kind);
 int b2ode_fused_solve(const b2ode_adaptive_desc *desc, int rhs_kind, const double *rhs_params, int n_rhs_params,
                       const void *rhs_data, double time_sign, const void *y0, void *out, const double *t_out, int n_out, double t_start,
                       double first_step, void *state, void *workspace, size_t workspace_bytes, int rank, int nranks,
@@ -257,6 +264,15 @@ int b2ode_reduce(int dtype, int mode, int nseg, const int64_t *seg_len, const vo
 int b2ode_set_k(b2ode_solver *s, int i, const void *const *k_new);
 int b2ode_dense_layer(const void *x, const void *const *k, const double *coef, int nk, const void *state, void *ystage,
                       const void *W, const void *bias, void *out, int64_t M, int K, int N, int act, void *cuda_stream);
+
+/* Same layer with fp32-accurate products ("3xTF32"): W_hi = tf32(W), W_lo = tf32(W - W_hi), both [N, K]; the kernel
+ * splits A = A_hi + A_lo the same way while staging it and accumulates A_lo.W_hi + A_hi.W_lo + A_hi.W_hi in the fp32
+ * TMEM accumulator (the dropped A_lo.W_lo term is 2^-22 relative).  This is the default numeric mode of the
+ * tensor-core func: it keeps the solution within north_star's 1e-3 fp32 bar of the reference's fp32 matmuls
+ * (tfdiffeq/models/dense_odenet.py:85-92, conv_odenet.py:80-86 1x1 convolutions on NHWC = this GEMM with M = B*H*W). */
+int b2ode_dense_layer_x3(const void *x, const void *const *k, const double *coef, int nk, const void *state, void *ystage,
+                         const void *W_hi, const void *W_lo, const void *bias, void *out, int64_t M, int K, int N, int act,
+                         void *cuda_stream);
 
 /* The whole three-layer func (dense_odenet.py:85-92: fc1 -> act -> fc2 -> act -> fc3) in ONE launch: per 128-row
  * tile the hidden activations stay in shared memory / TMEM, so an evaluation moves only the input tile(s) and the

@@ -52,7 +52,7 @@ def test_argument_validation_codes():
     bad = _desc()
     bad.dtype = 7
     assert lib.b2ode_adaptive_create(C.byref(h), C.byref(bad)) == -1
-    bad = _desc(nseg=9)
+    bad = _desc(nseg=_lib.MAXSEG + 1)
     assert lib.b2ode_adaptive_create(C.byref(h), C.byref(bad)) == -1
     bad = _desc()
     bad.n_k = 99

@@ -6,7 +6,7 @@ module raises ``ImportError``/``OSError`` loudly.  Nothing here imports ``oracle
 import ctypes as C
 import os
 
-MAXSEG = 8
+MAXSEG = 12
 MAXK = 14
 MAXPEERS = 8
 F32, F64 = 0, 1
@@ -27,7 +27,7 @@ class State(C.Structure):
                 ("n_acc", C.c_uint64), ("n_rej", C.c_uint64), ("attempt", C.c_uint64), ("n_steps_adv", C.c_int64),
                 ("accept", C.c_int32), ("done", C.c_int32), ("status", C.c_uint32), ("cursor", C.c_int32),
                 ("emit_j0", C.c_int32), ("emit_j1", C.c_int32), ("ticket", C.c_uint32), ("reserved_u", C.c_uint32),
-                ("xseq", C.c_uint64), ("klast", C.c_uint64 * MAXSEG), ("reserved_t", C.c_double * 7)]
+                ("xseq", C.c_uint64), ("klast", C.c_uint64 * MAXSEG), ("reserved_t", C.c_double * 3)]
 
 
 class AdaptiveDesc(C.Structure):
@@ -73,11 +73,13 @@ _SIGNATURES = {
     "b2ode_poll_sync": (C.c_int, [C.c_void_p, C.c_void_p]),
     "b2ode_comm_attach": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "b2ode_comm_set_global_len": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
+    "b2ode_comm_set_replicated": (C.c_int, [C.c_void_p, C.c_uint]),
     "b2ode_mailbox_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_char_p]),
     "b2ode_mailbox_open": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
     "b2ode_mailbox_close": (C.c_int, [C.c_void_p]),
     "b2ode_mailbox_destroy": (C.c_int, [C.c_void_p]),
     "b2ode_fused_workspace_bytes": (C.c_size_t, [C.c_int64]),
+    "b2ode_fused_capacity": (C.c_int64, [C.POINTER(AdaptiveDesc), C.c_int]),
     "b2ode_fused_fixed_solve": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.c_int, C.c_void_p, C.c_double,
                                           C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
@@ -88,6 +90,9 @@ _SIGNATURES = {
     "b2ode_set_k": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
     "b2ode_dense_layer": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_double), C.c_int, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "b2ode_dense_layer_x3": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_double), C.c_int, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int,
+                                       C.c_void_p]),
     "b2ode_mlp3_packed_bytes": (C.c_int64, [C.c_int, C.c_int]),
     "b2ode_mlp3_pack": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "b2ode_mlp3": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_double), C.c_int, C.c_void_p, C.c_void_p,

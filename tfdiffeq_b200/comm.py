@@ -66,6 +66,7 @@ class SharedStepGroup(object):
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self._own = C.c_void_p()
         self._peers = []
+        self._sums = {}
         lib, check = _lib.lib, _lib.check
         with torch.cuda.device(self.device):
             handle = C.create_string_buffer(64)
@@ -88,25 +89,45 @@ class SharedStepGroup(object):
                     self._peers.append(p)
             dist.barrier(group=group)
 
-    def attach(self, handle, seg):
-        """Called by the solver after ``b2ode_adaptive_bind``."""
+    # Group-wide sums of per-rank integers are needed once per *shape*, not once per solve: the collective (and its
+    # host synchronisation) runs the first time a rank presents a given local tuple and is cached afterwards.
+    # Contract (SPMD): every rank of the group calls odeint with the same sequence of problems, so either all ranks hit
+    # their cache or all ranks miss it.
+    def _sum_cached(self, tag, values):
+        key = (tag,) + tuple(int(v) for v in values)
+        hit = self._sums.get(key)
+        if hit is None:
+            v = torch.tensor([int(x) for x in values], dtype=torch.int64)
+            if dist.get_backend(self.group) == "nccl":
+                v = v.to(self.device)
+            dist.all_reduce(v, group=self.group)
+            hit = self._sums[key] = tuple(int(x) for x in v.cpu().tolist())
+        return hit
+
+    def attach(self, handle, seg, replicated=()):
+        """Called by the solver after ``b2ode_adaptive_bind``.  ``replicated``: indices of tuple components every rank
+        holds in full (identical values on all ranks, e.g. the parameter adjoint after its all-reduce): they are
+        counted once in the error norm instead of being summed over the ranks."""
         lib, check = _lib.lib, _lib.check
         # group-wide element count per component: the mean in misc.py:262 runs over every rank's elements
-        lens = torch.tensor(seg.lens, dtype=torch.int64)
-        if dist.get_backend(self.group) == "nccl":
-            lens = lens.to(self.device)
-        dist.all_reduce(lens, group=self.group)
-        glob = _lib.LenArray(*[int(v) for v in lens.cpu().tolist()])
+        tot = self._sum_cached("lens", seg.lens)
+        glob = _lib.LenArray(*[(seg.lens[i] if i in replicated else tot[i]) for i in range(len(seg.lens))])
         check(lib.b2ode_comm_attach(handle, self.rank, self.world, self._ptrs))
         check(lib.b2ode_comm_set_global_len(handle, glob))
+        mask = 0
+        for i in replicated:
+            mask |= 1 << i
+        check(lib.b2ode_comm_set_replicated(handle, mask))
 
     def global_count(self, n):
         """Sum of a per-rank count over the group (e.g. trajectories, for the mean in the error norm)."""
-        v = torch.tensor([int(n)], dtype=torch.int64)
-        if dist.get_backend(self.group) == "nccl":
-            v = v.to(self.device)
-        dist.all_reduce(v, group=self.group)
-        return int(v.item())
+        return self._sum_cached("count", (n,))[0]
+
+    def agree_fused(self, n_traj, fits):
+        """(group-wide trajectory count, every shard fits the persistent fused kernel): all shards must take the same
+        path, because the fused kernel and the generic kernels use different exchange protocols."""
+        n_glob, unfit = self._sum_cached("fused", (n_traj, 0 if fits else 1))
+        return n_glob, unfit == 0
 
     def close(self):
         lib = _lib.lib

@@ -835,6 +835,14 @@ extern "C" int b2ode_comm_set_global_len(b2ode_solver *s, const int64_t *global_
     return 0;
 }
 
+// Segments every rank holds in full with bit-identical values (e.g. the parameter adjoint of odeint_adjoint after its
+// all-reduce): their partials are taken from the local rank alone; global_len of such a segment is its local length.
+extern "C" int b2ode_comm_set_replicated(b2ode_solver *s, unsigned segment_mask) {
+    if (!s) return b2_fail(B2ODE_EINVAL, "null solver");
+    s->comm.repl_mask = segment_mask;
+    return 0;
+}
+
 #define B2_REQUIRE_BOUND(s)                                              \
     do {                                                                 \
         if (!(s)) return b2_fail(B2ODE_EINVAL, "null solver");              \

@@ -224,6 +224,7 @@ struct Mailbox {
 struct CommParams {
     int rank;
     int nranks;  // 0 or 1: no exchange
+    unsigned repl_mask;   // bit s: segment s is replicated (bit-identical on every rank): its totals are NOT combined
     Mailbox *box[B2ODE_MAXPEERS];
 };
 
@@ -270,6 +271,7 @@ __device__ void group_combine(const CommParams &cp, b2ode_state *st, Partial *to
     if (threadIdx.x == 0) {
         const Mailbox *mine = cp.box[cp.rank];
         for (int s = 0; s < nseg; ++s) {
+            if ((cp.repl_mask >> s) & 1u) continue;      // every rank already holds the whole segment
             Partial p = identity<MM>();
             for (int q = 0; q < cp.nranks; ++q) {
                 const MailSlot *src = &mine->slot[par][q];

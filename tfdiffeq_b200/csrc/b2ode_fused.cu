@@ -635,14 +635,19 @@ __global__ void __launch_bounds__(BT) k_fused_adaptive(const __grid_constant__ F
 // ================================================================================================
 // host side
 // ================================================================================================
+// `capacity` != null: only report how many trajectories this instantiation can keep co-resident on the current device
 template <typename T, typename RHS, int S, int BT>
-static int fused_launch(const FusedParams &p, long long n_traj, cudaStream_t st) {
+static int fused_launch(const FusedParams &p, long long n_traj, cudaStream_t st, long long *capacity = nullptr) {
     void *args[] = {(void *)&p};
     int dev = 0, coop = 0, nsm = 0, per_sm = 0;
     B2_CUDA(cudaGetDevice(&dev));
     B2_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
     B2_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
     B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused_adaptive<T, RHS, S, BT>, BT, 0));
+    if (capacity) {
+        *capacity = coop ? (long long)per_sm * nsm * BT : 0;
+        return 0;
+    }
     if (!coop) return b2_fail(B2ODE_ESTATE, "device does not support cooperative launch");
     const int grid = (int)((n_traj + BT - 1) / BT);
     if (grid > per_sm * nsm)
@@ -655,25 +660,41 @@ static int fused_launch(const FusedParams &p, long long n_traj, cudaStream_t st)
 }
 
 template <typename T, typename RHS>
-static int fused_dispatch_s(const FusedParams &p, int n_k, long long n_traj, cudaStream_t st) {
+static int fused_dispatch_s(const FusedParams &p, int n_k, long long n_traj, cudaStream_t st, long long *capacity) {
     // 512-thread blocks (<= 128 registers per thread) for the tableaus whose k-set fits; 128 otherwise
     switch (n_k) {
-        case 2: return fused_launch<T, RHS, 2, 512>(p, n_traj, st);
-        case 4: return fused_launch<T, RHS, 4, 512>(p, n_traj, st);
-        case 7: return fused_launch<T, RHS, 7, 512>(p, n_traj, st);
-        case 14: return fused_launch<T, RHS, 14, 128>(p, n_traj, st);
+        case 2: return fused_launch<T, RHS, 2, 512>(p, n_traj, st, capacity);
+        case 4: return fused_launch<T, RHS, 4, 512>(p, n_traj, st, capacity);
+        case 7: return fused_launch<T, RHS, 7, 512>(p, n_traj, st, capacity);
+        case 14: return fused_launch<T, RHS, 14, 128>(p, n_traj, st, capacity);
     }
     return b2_fail(B2ODE_EINVAL, "fused solve supports tableaus with 2, 4, 7 or 14 k's (got %d)", n_k);
 }
 
 template <typename T>
-static int fused_dispatch_rhs(const FusedParams &p, int rhs_kind, int n_k, long long n_traj, cudaStream_t st) {
+static int fused_dispatch_rhs(const FusedParams &p, int rhs_kind, int n_k, long long n_traj, cudaStream_t st,
+                              long long *capacity = nullptr) {
     switch (rhs_kind) {
-        case B2ODE_RHS_LORENZ: return fused_dispatch_s<T, RhsLorenz<T>>(p, n_k, n_traj, st);
-        case B2ODE_RHS_LOTKA_VOLTERRA: return fused_dispatch_s<T, RhsLotkaVolterra<T>>(p, n_k, n_traj, st);
-        case B2ODE_RHS_CUBIC_MLP: return fused_dispatch_s<T, RhsCubicMLP<T>>(p, n_k, n_traj, st);
+        case B2ODE_RHS_LORENZ: return fused_dispatch_s<T, RhsLorenz<T>>(p, n_k, n_traj, st, capacity);
+        case B2ODE_RHS_LOTKA_VOLTERRA: return fused_dispatch_s<T, RhsLotkaVolterra<T>>(p, n_k, n_traj, st, capacity);
+        case B2ODE_RHS_CUBIC_MLP: return fused_dispatch_s<T, RhsCubicMLP<T>>(p, n_k, n_traj, st, capacity);
     }
     return b2_fail(B2ODE_EINVAL, "unknown built-in right-hand side %d", rhs_kind);
+}
+
+// Largest batch (trajectories on this device) b2ode_fused_solve can keep co-resident for this tableau / dtype / right-hand
+// side: the host asks BEFORE launching, so that the shards of a shared-step group can agree on one path.  < 0: error.
+extern "C" int64_t b2ode_fused_capacity(const b2ode_adaptive_desc *desc, int rhs_kind) {
+    if (!desc) return b2_fail(B2ODE_EINVAL, "null argument");
+    FusedParams p;
+    memset(&p, 0, sizeof(p));
+    long long cap = 0;
+    int rc;
+    if (desc->dtype == B2ODE_F64) rc = fused_dispatch_rhs<double>(p, rhs_kind, desc->n_k, 0, nullptr, &cap);
+    else if (desc->dtype == B2ODE_F32) rc = fused_dispatch_rhs<float>(p, rhs_kind, desc->n_k, 0, nullptr, &cap);
+    else return b2_fail(B2ODE_EINVAL, "dtype must be 0 or 1");
+    if (rc) return rc < 0 ? rc : -rc;
+    return (int64_t)cap;
 }
 
 static int rhs_dim(int kind) {

@@ -33,6 +33,7 @@ struct DenseParams {
     const b2ode_state *st;               // dt lives here when nk > 0
     float *ystage;                       // optional: also materialise the stage input (needed for the last stage)
     const float *W;                      // [N, K] row-major (torch nn.Linear.weight layout), values already rounded to TF32
+    const float *W_lo;                   // null: plain TF32.  Else tf32(W_fp32 - W): the 3xTF32 split (fp32-accurate products)
     const float *bias;                   // [N] or null
     float *out;                          // [M, N]
     int M, K, N;
@@ -45,6 +46,11 @@ __device__ __forceinline__ uint32_t to_tf32(float x) {
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return r;
+}
+
+// low half of the 3xTF32 split: tf32(x - tf32(x)); the subtraction is exact in fp32
+__device__ __forceinline__ uint32_t tf32_lo(float x) {
+    return to_tf32(__fsub_rn(x, __uint_as_float(to_tf32(x))));
 }
 
 // Round to TF32's 11 significant bits with three FP32 operations (Veltkamp's split, C = 2^13 + 1): round-to-nearest
@@ -221,17 +227,22 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 // Called by NTHR threads with ids 0..NTHR-1.  NK (the number of k's in the stage combine) is a template parameter
 // so that every global load of a batch -- BQ positions x (1 + NK) streams -- is issued before the first one is
 // consumed: the producers are latency-bound, memory-level parallelism is what feeds the tensor core.
+// 3xTF32 (p.W_lo != null): every fp32 operand is split as x = hi + lo with hi = tf32(x), lo = tf32(x - hi), and the
+// product is accumulated in fp32 (TMEM) as A_lo.W_hi + A_hi.W_lo + A_hi.W_hi -- the K loop simply runs three times
+// over the same columns with `mode` selecting which halves are staged (1: A_lo/W_hi, 2: A_hi/W_lo, 0: A_hi/W_hi).
+// The dropped A_lo.W_lo term is 2^-22 relative: the result is as accurate as an fp32 FMA chain.
 template <int NTHR, int NK>
 __device__ __forceinline__ void produce_chunk_t(const DenseParams &p, uint8_t *sA, uint8_t *sB, int m0, int n0, int NT, int kc,
-                                                int tid, const float (&cf)[kMaxNK]) {
+                                                int tid, const float (&cf)[kMaxNK], int mode) {
     const bool vec_ok = (p.K & 3) == 0;
+    const float *Wsrc = (mode == 2) ? p.W_lo : p.W;
     // ---- B chunk first: NT rows (output features) x 64 columns of W[N, K], already TF32-rounded by the host:
     //      raw 16-byte async copies straight into the swizzled layout (no register staging), zero-filled past K
     if (vec_ok) {
         for (int f = tid; f < NT * (kKChunk / 4); f += NTHR) {
             const int row = f / (kKChunk / 4), c4 = f % (kKChunk / 4);
             const int gk = kc + c4 * 4;
-            const float *src = p.W + (size_t)(n0 + row) * p.K + (gk < p.K ? gk : 0);
+            const float *src = Wsrc + (size_t)(n0 + row) * p.K + (gk < p.K ? gk : 0);
             const uint32_t dst = smem_u32(sB + (c4 >> 3) * (256 * 128) + sw128_offset(row, c4 & 7));
             const int nbytes = gk < p.K ? 16 : 0;
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
@@ -241,7 +252,7 @@ __device__ __forceinline__ void produce_chunk_t(const DenseParams &p, uint8_t *s
             const int row = f / (kKChunk / 4), c4 = f % (kKChunk / 4);
             const int gk = kc + c4 * 4;
             uint32_t e[4] = {0u, 0u, 0u, 0u};
-            for (int q = 0; q < 4 && gk + q < p.K; ++q) e[q] = __float_as_uint(p.W[(size_t)(n0 + row) * p.K + gk + q]);
+            for (int q = 0; q < 4 && gk + q < p.K; ++q) e[q] = __float_as_uint(Wsrc[(size_t)(n0 + row) * p.K + gk + q]);
             *reinterpret_cast<uint4 *>(sB + (c4 >> 3) * (256 * 128) + sw128_offset(row, c4 & 7)) = make_uint4(e[0], e[1], e[2], e[3]);
         }
     }
@@ -292,14 +303,15 @@ __device__ __forceinline__ void produce_chunk_t(const DenseParams &p, uint8_t *s
                     v[q].y = __fadd_rn(v[q].y, acc.y);
                     v[q].z = __fadd_rn(v[q].z, acc.z);
                     v[q].w = __fadd_rn(v[q].w, acc.w);
-                    if (p.ystage && n0 == 0 && in[q]) *reinterpret_cast<float4 *>(p.ystage + off[q]) = v[q];
+                    if (p.ystage && n0 == 0 && mode == 0 && in[q]) *reinterpret_cast<float4 *>(p.ystage + off[q]) = v[q];
                 }
             }
 #pragma unroll
             for (int q = 0; q < BQ; ++q) {
                 const int f = tid + (b0 + q) * NTHR;
                 const int row = f / (kKChunk / 4), c4 = f % (kKChunk / 4);
-                const uint4 t = make_uint4(to_tf32(v[q].x), to_tf32(v[q].y), to_tf32(v[q].z), to_tf32(v[q].w));
+                const uint4 t = (mode == 1) ? make_uint4(tf32_lo(v[q].x), tf32_lo(v[q].y), tf32_lo(v[q].z), tf32_lo(v[q].w))
+                                            : make_uint4(to_tf32(v[q].x), to_tf32(v[q].y), to_tf32(v[q].z), to_tf32(v[q].w));
                 *reinterpret_cast<uint4 *>(sA + (c4 >> 3) * (kTileM * 128) + sw128_offset(row, c4 & 7)) = t;
             }
         }
@@ -320,12 +332,13 @@ __device__ __forceinline__ void produce_chunk_t(const DenseParams &p, uint8_t *s
                             acc = j ? __fadd_rn(acc, t) : t;
                         }
                         a = __fadd_rn(a, acc);
-                        if (p.ystage && n0 == 0) p.ystage[off] = a;
+                        if (p.ystage && n0 == 0 && mode == 0) p.ystage[off] = a;
                     }
                     e[q] = a;
                 }
             }
-            const uint4 t = make_uint4(to_tf32(e[0]), to_tf32(e[1]), to_tf32(e[2]), to_tf32(e[3]));
+            const uint4 t = (mode == 1) ? make_uint4(tf32_lo(e[0]), tf32_lo(e[1]), tf32_lo(e[2]), tf32_lo(e[3]))
+                                        : make_uint4(to_tf32(e[0]), to_tf32(e[1]), to_tf32(e[2]), to_tf32(e[3]));
             *reinterpret_cast<uint4 *>(sA + (c4 >> 3) * (kTileM * 128) + sw128_offset(row, c4 & 7)) = t;
         }
     }
@@ -333,17 +346,17 @@ __device__ __forceinline__ void produce_chunk_t(const DenseParams &p, uint8_t *s
 
 template <int NTHR>
 __device__ __forceinline__ void produce_chunk(const DenseParams &p, uint8_t *sA, uint8_t *sB, int m0, int n0, int NT, int kc,
-                                              int tid, const float (&cf)[kMaxNK]) {
+                                              int tid, const float (&cf)[kMaxNK], int mode = 0) {
     switch (p.nk) {
-        case 0: produce_chunk_t<NTHR, 0>(p, sA, sB, m0, n0, NT, kc, tid, cf); break;
-        case 1: produce_chunk_t<NTHR, 1>(p, sA, sB, m0, n0, NT, kc, tid, cf); break;
-        case 2: produce_chunk_t<NTHR, 2>(p, sA, sB, m0, n0, NT, kc, tid, cf); break;
-        case 3: produce_chunk_t<NTHR, 3>(p, sA, sB, m0, n0, NT, kc, tid, cf); break;
-        case 4: produce_chunk_t<NTHR, 4>(p, sA, sB, m0, n0, NT, kc, tid, cf); break;
-        case 5: produce_chunk_t<NTHR, 5>(p, sA, sB, m0, n0, NT, kc, tid, cf); break;
-        case 6: produce_chunk_t<NTHR, 6>(p, sA, sB, m0, n0, NT, kc, tid, cf); break;
-        case 7: produce_chunk_t<NTHR, 7>(p, sA, sB, m0, n0, NT, kc, tid, cf); break;
-        default: produce_chunk_t<NTHR, 8>(p, sA, sB, m0, n0, NT, kc, tid, cf); break;
+        case 0: produce_chunk_t<NTHR, 0>(p, sA, sB, m0, n0, NT, kc, tid, cf, mode); break;
+        case 1: produce_chunk_t<NTHR, 1>(p, sA, sB, m0, n0, NT, kc, tid, cf, mode); break;
+        case 2: produce_chunk_t<NTHR, 2>(p, sA, sB, m0, n0, NT, kc, tid, cf, mode); break;
+        case 3: produce_chunk_t<NTHR, 3>(p, sA, sB, m0, n0, NT, kc, tid, cf, mode); break;
+        case 4: produce_chunk_t<NTHR, 4>(p, sA, sB, m0, n0, NT, kc, tid, cf, mode); break;
+        case 5: produce_chunk_t<NTHR, 5>(p, sA, sB, m0, n0, NT, kc, tid, cf, mode); break;
+        case 6: produce_chunk_t<NTHR, 6>(p, sA, sB, m0, n0, NT, kc, tid, cf, mode); break;
+        case 7: produce_chunk_t<NTHR, 7>(p, sA, sB, m0, n0, NT, kc, tid, cf, mode); break;
+        default: produce_chunk_t<NTHR, 8>(p, sA, sB, m0, n0, NT, kc, tid, cf, mode); break;
     }
 }
 
@@ -386,8 +399,11 @@ __global__ void __launch_bounds__(kMmaThreads, 2) k_dense_layer_tf32(const __gri
     for (int n0 = 0; n0 < p.N; n0 += 256) {
         const int NT = (p.N - n0) < 256 ? (p.N - n0) : 256;
         const uint32_t idesc = make_idesc_tf32(NT);
+        const int passes = p.W_lo ? 3 : 1;
+        for (int pass = 0; pass < passes; ++pass)
         for (int kc = 0; kc < p.K; kc += kKChunk) {
-            produce_chunk<kMmaThreads>(p, sA, sB, m0, n0, NT, kc, tid, cf);
+            const int mode = p.W_lo ? (pass == 0 ? 1 : pass == 1 ? 2 : 0) : 0;
+            produce_chunk<kMmaThreads>(p, sA, sB, m0, n0, NT, kc, tid, cf, mode);
             asm volatile("cp.async.wait_group 0;" ::: "memory");
             // make the generic-proxy writes visible to the tensor core (async proxy), then hand over
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -401,7 +417,7 @@ __global__ void __launch_bounds__(kMmaThreads, 2) k_dense_layer_tf32(const __gri
                     for (int ks = 0; ks < 4; ++ks) {
                         const uint64_t da = make_desc(smem_u32(sA + kb * (kTileM * 128)) + ks * 32);
                         const uint64_t db = make_desc(smem_u32(sB + kb * (256 * 128)) + ks * 32);
-                        const uint32_t accum = (kc > 0 || kb > 0 || ks > 0) ? 1u : 0u;
+                        const uint32_t accum = (pass > 0 || kc > 0 || kb > 0 || ks > 0) ? 1u : 0u;
                         asm volatile(
                             "{\n\t.reg .pred p;\n\t"
                             "setp.ne.b32 p, %4, 0;\n\t"
@@ -492,7 +508,8 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_dense_layer_tf32_ws(const __g
     const int tiles_m = (p.M + kTileM - 1) / kTileM;
     const int tiles_n = (p.N + 255) / 256;
     const int items = tiles_m * tiles_n;
-    const int chunks = (p.K + kKChunk - 1) / kKChunk;
+    const int kchunks = (p.K + kKChunk - 1) / kKChunk;
+    const int chunks = p.W_lo ? 3 * kchunks : kchunks;      // 3xTF32: three passes over K (A_lo.W_hi, A_hi.W_lo, A_hi.W_hi)
 
     if (warp == kProdWarps) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512u));
@@ -538,7 +555,9 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_dense_layer_tf32_ws(const __g
                 if (s != grp) continue;
                 mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);                       // the MMAs that read this stage are done
                 uint8_t *sA = smem + s * kStageBytes, *sB = sA + kTileM * 128 * 2;
-                produce_chunk<kProdThreads / kStages>(p, sA, sB, m0, n0, NT, c * kKChunk, ltid, cf);
+                const int pass = c / kchunks;
+                const int mode = p.W_lo ? (pass == 0 ? 1 : pass == 1 ? 2 : 0) : 0;
+                produce_chunk<kProdThreads / kStages>(p, sA, sB, m0, n0, NT, (c - pass * kchunks) * kKChunk, ltid, cf, mode);
                 asm volatile("cp.async.wait_group 0;" ::: "memory");
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> async proxy (tensor core)
                 mbar_arrive(smem_u32(&bar_full[s]));
@@ -1377,9 +1396,28 @@ __global__ void __launch_bounds__(kChainThreads, 1) k_mlp3_tf32_pair(const __gri
 // ================================================================================================
 // host side
 // ================================================================================================
-extern "C" int b2ode_dense_layer(const void *x, const void *const *k, const double *coef, int nk, const void *state,
-                                 void *ystage, const void *W, const void *bias, void *out, int64_t M, int K, int N, int act,
-                                 void *cuda_stream) {
+// cudaFuncSetAttribute is per device and the persistent grids are sized from the SM count: keep both per device ordinal
+// (a process may drive several GPUs)
+constexpr int kMaxDev = 64;
+struct MmaDevCfg {
+    bool dense_simple, dense_ws, mlp3;
+    int sms;
+};
+static MmaDevCfg g_mma_dev[kMaxDev];
+
+static int mma_dev(MmaDevCfg **cfg) {
+    int dev = 0;
+    B2_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= kMaxDev) return b2_fail(B2ODE_EINVAL, "device ordinal %d out of range", dev);
+    MmaDevCfg *c = &g_mma_dev[dev];
+    if (c->sms == 0) B2_CUDA(cudaDeviceGetAttribute(&c->sms, cudaDevAttrMultiProcessorCount, dev));
+    *cfg = c;
+    return 0;
+}
+
+static int dense_layer_impl(const void *x, const void *const *k, const double *coef, int nk, const void *state,
+                            void *ystage, const void *W, const void *W_lo, const void *bias, void *out, int64_t M, int K, int N,
+                            int act, void *cuda_stream) {
     if (!x || !W || !out || M < 1 || K < 1 || N < 1) return b2_fail(B2ODE_EINVAL, "bad dense-layer arguments");
     if (N % 16 != 0) return b2_fail(B2ODE_EINVAL, "dense layer: N must be a multiple of 16 (got %d)", N);
     if (nk < 0 || nk > kMaxNK || (nk > 0 && (!k || !coef || !state))) return b2_fail(B2ODE_EINVAL, "bad stage-combine arguments");
@@ -1397,12 +1435,18 @@ extern "C" int b2ode_dense_layer(const void *x, const void *const *k, const doub
     p.st = (const b2ode_state *)state;
     p.ystage = (float *)ystage;
     p.W = (const float *)W;
+    p.W_lo = (const float *)W_lo;
     p.bias = (const float *)bias;
     p.out = (float *)out;
     p.M = (int)M;
     p.K = K;
     p.N = N;
     p.act = act;
+    MmaDevCfg *dc = nullptr;
+    {
+        const int rc = mma_dev(&dc);
+        if (rc) return rc;
+    }
     static int variant = -1;         // B2ODE_DENSE_SIMPLE=1 selects the non-pipelined kernel (kept as a cross-check)
     if (variant < 0) {
         const char *e = getenv("B2ODE_DENSE_SIMPLE");
@@ -1410,31 +1454,40 @@ extern "C" int b2ode_dense_layer(const void *x, const void *const *k, const doub
     }
     if (variant == 1) {
         const size_t smem = 2 * kTileM * 128 + 2 * 256 * 128 + 1024;      // A + B + alignment slack = 99 328 B
-        static bool configured = false;
-        if (!configured) {
+        if (!dc->dense_simple) {
             B2_CUDA(cudaFuncSetAttribute(k_dense_layer_tf32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured = true;
+            dc->dense_simple = true;
         }
         const int grid = (int)((M + kTileM - 1) / kTileM);
         k_dense_layer_tf32<<<grid, kMmaThreads, smem, (cudaStream_t)cuda_stream>>>(p);
     } else {
         const size_t smem = (size_t)kStages * kStageBytes + 4 * 32 * 33 * sizeof(float) + 1024;   // 2 x 96 KB ring + epilogue tiles + slack
-        static bool configured = false;
-        static int sms = 0;
-        if (!configured) {
+        if (!dc->dense_ws) {
             B2_CUDA(cudaFuncSetAttribute(k_dense_layer_tf32_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            int dev = 0;
-            B2_CUDA(cudaGetDevice(&dev));
-            B2_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-            configured = true;
+            dc->dense_ws = true;
         }
         const long long items = ((M + kTileM - 1) / kTileM) * (long long)((N + 255) / 256);
-        const int grid = (int)(items < sms ? items : sms);                 // persistent: one CTA per SM
+        const int grid = (int)(items < dc->sms ? items : dc->sms);         // persistent: one CTA per SM
         k_dense_layer_tf32_ws<<<grid, kWsThreads, smem, (cudaStream_t)cuda_stream>>>(p);
     }
     B2_CUDA(cudaGetLastError());
     b2_count_launch();
     return 0;
+}
+
+extern "C" int b2ode_dense_layer(const void *x, const void *const *k, const double *coef, int nk, const void *state,
+                                 void *ystage, const void *W, const void *bias, void *out, int64_t M, int K, int N, int act,
+                                 void *cuda_stream) {
+    return dense_layer_impl(x, k, coef, nk, state, ystage, W, nullptr, bias, out, M, K, N, act, cuda_stream);
+}
+
+// 3xTF32: W_hi = tf32(W), W_lo = tf32(W - W_hi), both [N, K]; the kernel splits A the same way on the fly and accumulates
+// A_lo.W_hi + A_hi.W_lo + A_hi.W_hi in fp32 -- products as accurate as fp32 FMAs at three times the tensor-core work.
+extern "C" int b2ode_dense_layer_x3(const void *x, const void *const *k, const double *coef, int nk, const void *state,
+                                    void *ystage, const void *W_hi, const void *W_lo, const void *bias, void *out, int64_t M, int K,
+                                    int N, int act, void *cuda_stream) {
+    if (!W_lo) return b2_fail(B2ODE_EINVAL, "W_lo is null");
+    return dense_layer_impl(x, k, coef, nk, state, ystage, W_hi, W_lo, bias, out, M, K, N, act, cuda_stream);
 }
 
 // ---- fc1 -> act -> fc2 -> act -> fc3 in one launch (tfdiffeq/models/dense_odenet.py:85-92); see k_mlp3_tf32 ----
@@ -1509,16 +1562,17 @@ extern "C" int b2ode_mlp3(const void *x, const void *const *k, const double *coe
     if (stages < 2) return b2_fail(B2ODE_EINVAL, "mlp3: shared memory budget exhausted");
     P.stages = stages;
     const size_t smem = (size_t)P.act_bytes + (size_t)stages * P.stage_bytes + kTileScratchBytes + 1024;
-    static bool configured = false;
-    static int sms = 0;
-    if (!configured) {
+    MmaDevCfg *dc = nullptr;
+    {
+        const int rc = mma_dev(&dc);
+        if (rc) return rc;
+    }
+    if (!dc->mlp3) {
         B2_CUDA(cudaFuncSetAttribute(k_mlp3_tf32, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 4096));
         B2_CUDA(cudaFuncSetAttribute(k_mlp3_tf32_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 4096));
-        int dev = 0;
-        B2_CUDA(cudaGetDevice(&dev));
-        B2_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        configured = true;
+        dc->mlp3 = true;
     }
+    const int sms = dc->sms;
     const long long tiles = (M + kTileM - 1) / kTileM;
     if (pair) {
         const long long pairs = (tiles + 1) / 2;

@@ -299,6 +299,7 @@ class VariableCoefficientAdamsBashforth(object):
     def __init__(self, func, y0, rtol, atol, implicit=True, first_step=None, max_order=_MAX_ORDER, safety=0.9, ifactor=10.0,
                  dfactor=0.2, **unused_kwargs):
         unused_kwargs.pop('shared_step_group', None)
+        unused_kwargs.pop('replicated_components', None)
         unused_kwargs.pop('cuda_graph', None)
         unused_kwargs.pop('fused_rhs', None)
         _handle_unused_kwargs(self, unused_kwargs)

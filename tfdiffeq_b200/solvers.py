@@ -162,6 +162,8 @@ class AdaptiveStepsizeODESolver(object):
     def __init__(self, func, y0, rtol, atol, first_step=None, safety=0.9, ifactor=10.0, dfactor=0.2,
                  max_num_steps=2 ** 31 - 1, **unused_kwargs):
         self.comm = unused_kwargs.pop("shared_step_group", None)     # extension: SURVEY 8(e)
+        # with a group: tuple components every rank holds in full, bit-identical (odeint_adjoint's batch-summed adjoints)
+        self.replicated = tuple(unused_kwargs.pop("replicated_components", ()))
         # extension: capture one attempt (the func calls included) into a CUDA graph and replay it.  Opt-in,
         # because python-side effects of func (e.g. an `nfe` counter on the module) happen once, at capture.
         self.cuda_graph = bool(unused_kwargs.pop("cuda_graph", False))
@@ -255,9 +257,18 @@ class AdaptiveStepsizeODESolver(object):
         weights = base.rhs_data(dtype, dev)
         first = float("nan") if self.first_step is None else _tf_f64(self.first_step)
         rank, world, boxes, n_glob = 0, 1, None, n_traj
+        fits = int(lib.b2ode_fused_capacity(C.byref(desc), base.kind)) >= n_traj
         if self.comm is not None:
             rank, world, boxes = self.comm.rank, self.comm.world, self.comm._ptrs
-            n_glob = self.comm.global_count(n_traj)
+            # the shards of a group must take the same path (the fused kernel and the generic kernels speak different
+            # exchange protocols): agree on "every shard fits" and on the group-wide trajectory count in one cached call
+            n_glob, fits = self.comm.agree_fused(n_traj, fits)
+        if not fits:
+            import warnings
+            warnings.warn("tfdiffeq_b200: batch of %d trajectories per GPU exceeds what the persistent fused kernel can keep "
+                          "co-resident; using the generic per-stage path (an order of magnitude slower for a built-in "
+                          "right-hand side)" % n_traj, RuntimeWarning)
+            return None
         stream = torch.cuda.current_stream(dev)
         rc = lib.b2ode_fused_solve(C.byref(desc), base.kind, prm_arr, len(prm),
                                    C.c_void_p(weights.data_ptr()) if weights is not None else None,
@@ -266,8 +277,6 @@ class AdaptiveStepsizeODESolver(object):
                                    n_out, float(t_host[0]), first, C.c_void_p(state_dev.data_ptr()),
                                    C.c_void_p(workspace.data_ptr()), ws_bytes, rank, world, boxes, n_glob,
                                    C.c_void_p(stream.cuda_stream))
-        if rc == -3:          # batch larger than what can stay co-resident: use the generic path
-            return None
         check(rc)
         host, hkey = _pinned_acquire(dev)
         try:
@@ -305,7 +314,7 @@ class AdaptiveStepsizeODESolver(object):
 
         handle = C.c_void_p()
         check(lib.b2ode_adaptive_create(C.byref(handle), C.byref(desc)))
-        pinned_key = None
+        stream = torch.cuda.current_stream(dev)
         try:
             buf = _lib.AdaptiveBuffers()
             buf.state = state_dev.data_ptr()
@@ -317,10 +326,9 @@ class AdaptiveStepsizeODESolver(object):
             buf.tstage = tstage.data_ptr()
             buf.t_out = t_dev.data_ptr()
             buf.n_out = n_out
-            stream = torch.cuda.current_stream(dev)
             check(lib.b2ode_adaptive_bind(handle, C.byref(buf), C.c_void_p(stream.cuda_stream)))
             if self.comm is not None:
-                self.comm.attach(handle, seg)
+                self.comm.attach(handle, seg, self.replicated)
 
             fo = _FuncOutputs(seg, (Y0, F0, S))
             y0_views, s_views = seg.views(Y0), seg.views(S)
@@ -365,10 +373,12 @@ class AdaptiveStepsizeODESolver(object):
             rk_stage, rk_finalize, poll_async = lib.b2ode_rk_stage, lib.b2ode_rk_finalize, lib.b2ode_poll_async
 
             # tensor-core func (rhs.DenseMLP): the stage combine becomes the A-operand producer of its first layer
-            from .rhs import DenseMLP
+            from .rhs import Conv2dODEFunc, DenseMLP
             dense = getattr(self.func, "_b2ode_base", None)
-            if not (self.fused_rhs and isinstance(dense, DenseMLP) and seg.nseg == 1 and len(seg.shapes[0]) == 2 and tab.fsal
-                    and getattr(self.func, "_b2ode_sign", 1.0) > 0 and dense.uses_tensor_cores(s_views[0])):
+            if not (self.fused_rhs and seg.nseg == 1 and tab.fsal and getattr(self.func, "_b2ode_sign", 1.0) > 0
+                    and ((isinstance(dense, DenseMLP) and len(seg.shapes[0]) == 2)
+                         or (isinstance(dense, Conv2dODEFunc) and len(seg.shapes[0]) == 4))
+                    and dense.uses_tensor_cores(s_views[0])):
                 dense = None
             if dense is not None:
                 f0_view = seg.views(F0)[0]
@@ -458,10 +468,12 @@ class AdaptiveStepsizeODESolver(object):
             last_stats.update(self.stats)
             if final.status:
                 self._raise(final, s_views, y0_views)
-            stream.synchronize()      # outputs are complete; also keeps Y0/F0/S alive until the kernels ran
             del prev_last, graph_ks, graph
         finally:
-            _pinned_release(pinned_key)
+            # also on the error paths (status != 0 seen early, func raising mid-attempt): attempts and raw
+            # cudaMemcpyAsync polls into `pinned` may still be in flight -- drain them before the pinned ring, the
+            # engine buffers and the native handle are released
+            stream.synchronize()
             lib.b2ode_adaptive_destroy(handle)
         return tuple(outs)
 
@@ -525,6 +537,7 @@ class FixedGridODESolver(object):
         unused_kwargs.pop('rtol', None)
         unused_kwargs.pop('atol', None)
         unused_kwargs.pop('shared_step_group', None)     # a fixed grid needs no exchange between shards
+        unused_kwargs.pop('replicated_components', None)
         unused_kwargs.pop('cuda_graph', None)
         self.fused_rhs = bool(unused_kwargs.pop("fused_rhs", True))
         _handle_unused_kwargs(self, unused_kwargs)
