@@ -116,3 +116,43 @@ def test_config4_conv_odefunc_forward_vs_oracle_and_adjoint_gradient():
     fd = (lp - lm) / (2 * eps)
     # ReLU kinks make the finite difference itself O(eps)-inaccurate; smooth funcs are checked to 5e-6 in test_adjoint_gpu.py
     assert abs(fd - g_dir) <= 5e-3 * max(abs(fd), 1e-3), (fd, g_dir)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# BASELINE config 2 in full: 65 536 x 3 fp64 Lorenz, dopri5 defaults, all 1 000 output points (what bench.py times)
+# ----------------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def cfg2_oracle():
+    """One full oracle solve (about half a minute of numpy), shared by the three engine paths below."""
+    rng = np.random.default_rng(0)
+    y0 = np.array([1., 1., 1.]) + 0.1 * rng.standard_normal((65536, 3))
+    t = np.arange(1000) * 0.01
+    st = np_ref.Stats()
+    ref = np_ref.odeint(PROBLEMS["lorenz"](backend="numpy"), y0, t, rtol=1e-7, atol=1e-9, method="dopri5", stats=st)
+    assert (st.n_acc, st.n_rej, st.nfe) == (390, 54, 2666)            # SURVEY 8(c) known-answer vector
+    return y0, t, ref, st
+
+
+@pytest.mark.parametrize("path", ["fused_rhs", "external_func_eager", "external_func_cuda_graph"])
+def test_config2_full_batch_full_horizon_vs_oracle(cfg2_oracle, path):
+    """The benchmarked solve itself: same accepted / rejected / NFE counts as the oracle over the WHOLE horizon, values
+    within north_star's 1e-6 fp64 bar for t <= 5 (Lorenz is chaotic, parity horizon t <= 10; the tail
+    t in (5, 10) is checked at 1e-4, which a 1-ulp difference in pow() amplified by e^{0.9 t} stays far below)."""
+    import tfdiffeq_b200 as tfd
+    y0, t, ref, st = cfg2_oracle
+    if path == "fused_rhs":
+        f, opts = tfd.rhs.Lorenz(), {}
+    else:
+        f, opts = PROBLEMS["lorenz"](backend="torch", device=DEV), ({"cuda_graph": True} if path.endswith("graph") else {})
+    got = tfd.odeint(f, torch.tensor(y0, device=DEV), torch.tensor(t), rtol=1e-7, atol=1e-9, method="dopri5", options=opts)
+    s = dict(tfd.last_stats)
+    assert s["fused_rhs"] == (path == "fused_rhs")
+    assert (s["n_accepted"], s["n_rejected"], s["nfe"]) == (st.n_acc, st.n_rej, st.nfe) == (390, 54, 2666)
+    got = got.cpu().numpy()
+    scale = np.maximum(np.abs(ref), 1.0)
+    rel = np.abs(got - ref) / scale
+    head = float(rel[:501].max())          # t <= 5.0
+    tail = float(rel.max())                # t <= 9.99
+    print("cfg2 %s: max rel err t<=5: %.3e, whole horizon: %.3e" % (path, head, tail))
+    assert head <= 1e-6, head
+    assert tail <= 1e-4, tail

@@ -97,3 +97,24 @@ def test_oracle_torch_backend_matches_numpy():
     b = np_ref.odeint(ft, torch.from_numpy(y0), t, stats=s2)
     assert (s1.n_acc, s1.n_rej, s1.nfe) == (s2.n_acc, s2.n_rej, s2.nfe)
     assert np.max(np.abs(a - b.numpy())) < 1e-10
+
+
+def test_gradient_fixtures_are_self_consistent(golden_dir):
+    """tests/golden/grad_*.npz hold the UNMODIFIED reference adjoint's gradients next to gradients back-propagated
+    through this oracle's discrete solver (oracle/make_golden_grads.py).  Two independent routes to the same derivative
+    must agree to the solver tolerance (the dopri8 dense output is 4th order, rk4 is a fixed grid: looser)."""
+    import glob
+    import os
+    files = sorted(glob.glob(os.path.join(golden_dir, "grad_*.npz")))
+    assert len(files) >= 7
+    loose = {"spiral3_dopri8": 2e-4, "spiral3_rk4": 2e-2, "mlp_tanh_f32": 5e-3, "mlp_tanh_dopri5": 5e-5}
+    for f in files:
+        name = os.path.basename(f)[5:-4]
+        g = np.load(f)
+        tol = loose.get(name, 2e-6)
+        for k in g.files:
+            if k.startswith("bp_"):
+                a, b = g[k[3:]], g[k]
+                assert a.shape == b.shape
+                assert np.max(np.abs(a - b)) <= tol * max(1.0, np.max(np.abs(b))), (name, k)
+        assert np.all(np.isfinite(g["g_t"])) and g["g_t"].shape == g["t"].shape
