@@ -161,6 +161,40 @@ class TimeDependentTridiag(object):
         return y @ self.Tt + 0.01 * t
 
 
+class BatchedLinear(object):
+    """SURVEY 8(d) row K, the north-star kernel microbenchmark: y' = y @ A on a (batch, dim) state with
+    A = -0.5 I + 0.05 N(0,1) (seeded), i.e. tests/problems.py:43-68's LinearODE batched over rows."""
+
+    def __init__(self, backend="numpy", dtype="float64", device=None, dim=128, seed=0):
+        rng = np.random.default_rng(seed)
+        self.A = _const(backend, -0.5 * np.eye(dim) + 0.05 * rng.standard_normal((dim, dim)), dtype, device)
+
+    def __call__(self, t, y):
+        return y @ self.A
+
+
+class Kepler(object):
+    """DETEST D-class (tests/DETEST/detest.py:263-283) stacked: `orbits` two-body orbits per row, state (..., 4 * orbits)
+    laid out [x, y, vx, vy] per orbit; eccentricities spread over 0.1 .. 0.9 (BASELINE config 5's reject-stress system:
+    32 orbits = dim 128).  `y0(batch, seed)` perturbs the reference initial data [1-e, 0, 0, sqrt((1+e)/(1-e))]."""
+
+    def __init__(self, backend="numpy", dtype="float64", device=None, orbits=32):
+        self.xp, self.orbits = _xp(backend), orbits
+
+    def __call__(self, t, y):
+        xp = self.xp
+        s = y.reshape(y.shape[:-1] + (self.orbits, 4))
+        x, yy, vx, vy = s[..., 0], s[..., 1], s[..., 2], s[..., 3]
+        r3 = (x * x + yy * yy) ** 1.5
+        return xp.stack([vx, vy, -x / r3, -yy / r3], -1).reshape(y.shape)
+
+    def y0(self, batch, seed=0):
+        ecc = 0.1 + 0.8 * np.arange(self.orbits) / max(self.orbits - 1, 1)
+        base = np.stack([1 - ecc, np.zeros_like(ecc), np.zeros_like(ecc), np.sqrt((1 + ecc) / (1 - ecc))], -1).reshape(-1)
+        rng = np.random.default_rng(seed)
+        return base[None, :] * (1.0 + 0.01 * rng.standard_normal((batch, base.size)))
+
+
 class Detest(object):
     """One problem of the reference's DETEST benchmark (tests/DETEST/detest.py), see tests/detest_problems.py."""
 
@@ -172,5 +206,5 @@ class Detest(object):
         return self.f(t, y)
 
 
-PROBLEMS = {"detest": Detest, "constant": Constant, "sine": Sine, "linear": Linear, "lv": LotkaVolterra, "lorenz": Lorenz,
+PROBLEMS = {"batched_linear": BatchedLinear, "kepler": Kepler, "detest": Detest, "constant": Constant, "sine": Sine, "linear": Linear, "lv": LotkaVolterra, "lorenz": Lorenz,
             "spiral": Spiral, "spiral_mlp": SpiralMLP, "tuple_decay": TupleDecay, "tridiag": TimeDependentTridiag}

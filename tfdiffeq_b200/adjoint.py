@@ -19,6 +19,10 @@ def _flatten(seq):
     return torch.cat(flat) if len(flat) > 0 else torch.tensor([])
 
 
+# statistics of the most recent odeint_adjoint call: the forward solve and every backward (augmented) solve
+last_stats = {"forward": None, "backward": []}
+
+
 def _group_of(options):
     return (options or {}).get("shared_step_group") if isinstance(options, dict) else None
 
@@ -45,6 +49,9 @@ class _OdeintAdjoint(torch.autograd.Function):
                              options=options["options"])                                      # adjoint.py:54
         finally:
             _rhs._FORCE_ACCURATE[0] -= 1
+        from . import solvers as _solvers
+        last_stats["forward"] = dict(_solvers.last_stats)
+        last_stats["backward"] = []
         ctx.save_for_backward(t, flat_params, *ans)
         return ans
 
@@ -119,6 +126,8 @@ class _OdeintAdjoint(torch.autograd.Function):
                     aug_ans = odeint(augmented_dynamics, aug_y0, torch.stack([t[i], t[i - 1]]),
                                      rtol=opts["adjoint_rtol"], atol=opts["adjoint_atol"], method=opts["adjoint_method"],
                                      options=adj_options)                                     # adjoint.py:148-153
+                    from . import solvers as _solvers
+                    last_stats["backward"].append(dict(_solvers.last_stats))
                     adj_y = tuple(a[1] for a in aug_ans[n_tensors:2 * n_tensors])
                     adj_time = aug_ans[2 * n_tensors][1]
                     adj_params = aug_ans[2 * n_tensors + 1][1]
