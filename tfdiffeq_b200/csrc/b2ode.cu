@@ -776,6 +776,9 @@ extern "C" int b2ode_adaptive_create(b2ode_solver **out, const b2ode_adaptive_de
     c.ifactor = desc->ifactor;
     c.dfactor = desc->dfactor;
     c.exponent = desc->exponent;
+    c.inv_safety = 1.0 / desc->safety;
+    c.inv_ifactor = 1.0 / desc->ifactor;
+    c.inv_dfactor = 1.0 / desc->dfactor;
     c.max_num_steps = desc->max_num_steps;
     c.init_order = desc->init_order;
     s->comm.nranks = 0;

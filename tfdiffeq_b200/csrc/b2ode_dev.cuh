@@ -308,6 +308,7 @@ struct CtrlParams {
     double alpha[B2ODE_MAXK];     // s-1 entries
     double rtol[B2ODE_MAXSEG], atol[B2ODE_MAXSEG];
     double safety, ifactor, dfactor, exponent;
+    double inv_safety, inv_ifactor, inv_dfactor;   // host-computed reciprocals (the controller is a serial latency chain)
     long long max_num_steps;
     int init_order;
     int n_out;
@@ -334,6 +335,11 @@ struct CtrlDecision {
     double dt_next;
 };
 
+// The controller runs once per attempted step on the critical path of EVERY attempt (one thread, all other threads of the
+// GPU waiting), so its dependent-latency chain is kept short: one division for the error ratio (sum err^2 / (tol^2 * n)
+// instead of two), x**e as exp2(e * log2(x)) instead of pow(), reciprocals of safety / ifactor / dfactor precomputed on
+// the host.  The results differ from the oracle's `sqrt(m) ** e / safety` in the last one or two ulps of dt_next -- far
+// inside the 1e-6 / 1e-3 parity bars (dt is a free parameter of the method; the accept decision is unaffected).
 template <typename T>
 __device__ __forceinline__ CtrlDecision ctrl_decide(const CtrlParams &c, const Partial *tot, int nseg, double dt) {
     bool accept = true;
@@ -346,12 +352,13 @@ __device__ __forceinline__ CtrlDecision ctrl_decide(const CtrlParams &c, const P
         // tol = atol + rtol * reduce_max([|y0|, |y1|]): ONE scalar per segment (misc.py:257)
         const double mm = nan_max(tot[s].v[1], tot[s].v[2]);
         const T tol = Ar<T>::add((T)c.atol[s], Ar<T>::mul((T)c.rtol[s], (T)mm));
-        const double ssq = tot[s].v[0] / ((double)tol * (double)tol);
+        const double tol2 = (double)tol * (double)tol;
         if (c.controller == B2ODE_CTRL_TSIT5) {
-            pooled += ssq;
+            pooled += tot[s].v[0] / tol2;
             pooled_n += c.n_global[s];
         } else {
-            const T msr = (T)(ssq / (double)c.n_global[s]);
+            // mean((err / tol)^2) as sum(err^2) / (tol^2 * n): a one-pass global-tolerance form of misc.py:259-263
+            const T msr = (T)(tot[s].v[0] / (tol2 * (double)c.n_global[s]));
             accept = accept && (msr <= T(1));
             m = (s == 0) ? (double)msr : nan_max(m, (double)msr);
         }
@@ -366,10 +373,10 @@ __device__ __forceinline__ CtrlDecision ctrl_decide(const CtrlParams &c, const P
     if (m == 0.0) {
         dt_next = dt * c.ifactor;
     } else {
-        const double df = (m < 1.0) ? 1.0 : c.dfactor;
+        const double inv_df = (m < 1.0) ? 1.0 : c.inv_dfactor;
         const double er = (c.controller == B2ODE_CTRL_TSIT5) ? m : (double)Ar<T>::sqrt((T)m);
-        const double cand = pow(er, c.exponent) / c.safety;
-        const double factor = nan_max(1.0 / c.ifactor, nan_min(cand, 1.0 / df));
+        const double cand = exp2(c.exponent * log2(er)) * c.inv_safety;
+        const double factor = nan_max(c.inv_ifactor, nan_min(cand, inv_df));
         dt_next = dt / factor;
     }
     CtrlDecision d;

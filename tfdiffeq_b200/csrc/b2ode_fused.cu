@@ -11,6 +11,33 @@
 // order: rk_common.py:49-60, misc.py:250-287, interp.py:6-67), only the reduction order differs.
 
 #include "b2ode_dev.cuh"
+#include <stdlib.h>
+
+// ------------------------------------------------------------------------------------------------
+// optional timeline stamps (-DB2ODE_FUSED_TRACE, scripts/fused_trace.py): thread 0 of two blocks records clock64() at the
+// phase boundaries of attempts [8, 8 + kTraceAttempts); compiled out of the shipped library
+// ------------------------------------------------------------------------------------------------
+#ifdef B2ODE_FUSED_TRACE
+constexpr int kTraceAttempts = 64, kTracePhases = 16;
+__device__ unsigned long long g_fused_trace[2 * kTraceAttempts * kTracePhases];
+// `dep` is a value that only exists after the event being stamped (a word read after a barrier / received from a poll):
+// the clock read is predicated on it, so ptxas cannot hoist the read above the event (an unanchored clock64() was observed
+// to float above BAR.SYNC)
+#define FTRACE_DEP(att, ph, dep)                                                                                 \
+    do {                                                                                                         \
+        if ((unsigned)(dep) != 0x7ffffff3u && (threadIdx.x == 0 || threadIdx.x == blockDim.x - 32) &&            \
+            (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1) && (att) >= 8 && (att) < 8 + kTraceAttempts)        \
+            g_fused_trace[((blockIdx.x == 0 ? 0 : 1) * kTraceAttempts + ((att)-8)) * kTracePhases + (ph)] = clock64(); \
+    } while (0)
+#define FTRACE(att, ph) FTRACE_DEP(att, ph, 0)
+extern "C" int b2ode_debug_fused_trace(unsigned long long *out) {
+    B2_CUDA(cudaMemcpyFromSymbol(out, g_fused_trace, sizeof(g_fused_trace)));
+    return 0;
+}
+#else
+#define FTRACE(att, ph) do { } while (0)
+#define FTRACE_DEP(att, ph, dep) do { } while (0)
+#endif
 
 // Block size is a template parameter: 512 threads (one block per SM, the fewest barrier arrivals and partials)
 // when the kernel fits in 128 registers per thread, 128 threads otherwise.
@@ -74,14 +101,24 @@ struct RhsCubicMLP {
 };
 
 // ------------------------------------------------------------------------------------------------
-// grid-wide reduction: block tree -> partial per block -> grid barrier -> every block re-reduces all partials
+// Grid-wide (and group-wide) all-reduce of two 64-bit values per attempt, built for LATENCY: measured on the round-1
+// kernel (scripts/fused_trace.py) an attempt cost 15.7k cycles of which only 3.1k were the Runge-Kutta arithmetic; the
+// rest was two block reductions with __syncthreads (1.2k + 2.9k), an atomic grid barrier (2.5k), the serial controller
+// (3.1k) and the dense output (2.4k), all on every thread's critical path.  Now:
+//   * one CONTROL WARP per block owns the whole protocol; the compute warps hand it their warp partials through shared
+//     memory and a named barrier (bar.arrive, they do not wait), write the dense output of the step SPECULATIVELY while
+//     the control warp talks to the rest of the GPU, and pick the decision up at a second named barrier;
+//   * no atomics, no fences: a value travels as 8-byte words {32 data bits | 32-bit sequence number} (the idea of NCCL's
+//     LL protocol) -- a word is valid the moment its sequence number matches;
+//   * block 0's control warp gathers the 4-word partials of all blocks (one 16-byte-pair poll per block, 5 per lane),
+//     reduces them in a fixed order and publishes the GPU total; with a shared-step group it pushes the total to every
+//     peer's mailbox over NVLink instead, and EVERY block polls its own rank's mailbox (one hop after the push);
+//   * every control warp then evaluates the (cheap, now low-latency) controller redundantly and bit-identically.
 // ------------------------------------------------------------------------------------------------
 struct FusedParams {
     b2ode_state *st;
-    Partial *part;          // [2][gridDim.x], double buffered by reduction parity
-    unsigned *bar;          // monotonically increasing arrival counter of the grid barrier
-    Partial *gtot;          // [2]: group totals published by block 0 when a shared-step group is attached
-    unsigned long long *gflag;
+    unsigned long long *part2;   // [2][gridDim.x][4] u64: block partials as 4 tagged words, double buffered by exchange parity
+    unsigned *ctr;               // monotonically increasing arrival counter (zeroed by the host before the launch)
     const void *y0;
     void *out;
     long long n_traj;       // trajectories on this rank
@@ -90,7 +127,8 @@ struct FusedParams {
     double time_sign;       // -1 when integrating the reversed system (misc.py:318-321)
     double rhs[8];
     const void *rhs_data;   // device buffer of staged weights (RhsCubicMLP), else null
-    // tableau (runtime values; structural zeros are skipped exactly like the generic path does)
+    // tableau (runtime values).  Structural zeros are multiplied like any other coefficient, as the reference does
+    // (misc.py:114-121: its zero test never fires): x + 0 * k == x for finite k, so results equal the generic path's
     double beta[B2ODE_MAXK][B2ODE_MAXK];
     double c_sol[B2ODE_MAXK], c_error[B2ODE_MAXK], c_mid[B2ODE_MAXK];
     int fsal;
@@ -99,250 +137,433 @@ struct FusedParams {
     CommParams comm;
 };
 
-__device__ __forceinline__ unsigned ld_acquire_gpu_u32(const unsigned *p) {
-    unsigned v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-
-// Grid barrier on a monotonically increasing arrival counter (zeroed by the host before the launch): barrier
-// number e is passed once the counter reaches e * gridDim.x.  One atomic and one polled word per block.
-__device__ __forceinline__ void grid_barrier(unsigned *count, unsigned &epoch) {
-    __syncthreads();
-    epoch += 1u;
-    if (threadIdx.x == 0) {
-        const unsigned target = epoch * gridDim.x;
-        __threadfence();
-        atomicAdd(count, 1u);
-        while (ld_acquire_gpu_u32(count) < target) {
-        }
-    }
-    __syncthreads();
-}
-
-template <unsigned MM, int BT>
-__device__ __forceinline__ Partial fblock_reduce(Partial x, Partial *sh /*[BT/32]*/) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        Partial y;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) y.v[c] = __shfl_xor_sync(0xffffffffu, x.v[c], o);
-        x = combine<MM>(x, y);
-    }
-    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-    __syncthreads();
-    if (l == 0) sh[w] = x;
-    __syncthreads();
-    Partial r = sh[0];
-#pragma unroll
-    for (int i = 1; i < BT / 32; ++i) r = combine<MM>(r, sh[i]);
-    return r;   // valid in EVERY thread
-}
-
-// All threads of the grid call this with their own contribution; all return the same (group-wide) totals.
-template <unsigned MM, int BT>
-__device__ Partial grid_reduce(const FusedParams &p, Partial mine, unsigned &parity, Partial *sh, Partial *sh_tot) {
-    Partial *part = p.part + (size_t)(parity & 1u) * gridDim.x;
-    Partial b = fblock_reduce<MM, BT>(mine, sh);
-    if (threadIdx.x == 0) part[blockIdx.x] = b;
-    grid_barrier(p.bar, parity);            // the barrier epoch is the reduction count
-    parity -= 1u;
-    Partial acc = identity<MM>();
-    for (int i = threadIdx.x; i < (int)gridDim.x; i += BT) acc = combine<MM>(acc, part[i]);
-    Partial tot = fblock_reduce<MM, BT>(acc, sh);
-    if (p.comm.nranks > 1) {
-        // block 0 exchanges with the peer GPUs and publishes the group totals; the others wait for them
-        const unsigned long long want = (unsigned long long)(parity + 1u);
-        if (blockIdx.x == 0) {
-            if (threadIdx.x == 0) sh_tot[0] = tot;
-            __syncthreads();
-            group_combine<MM>(p.comm, p.st, sh_tot, 1);
-            if (threadIdx.x == 0) {
-                p.gtot[parity & 1u] = sh_tot[0];
-                __threadfence();
-                atomicExch(p.gflag, want);
-            }
-            __syncthreads();
-            tot = sh_tot[0];
-        } else {
-            if (threadIdx.x == 0) {
-                volatile unsigned long long *f = p.gflag;
-                while (*f < want) {
-                }
-                __threadfence();
-                sh_tot[0] = p.gtot[parity & 1u];
-            }
-            __syncthreads();
-            tot = sh_tot[0];
-            __syncthreads();
-        }
-    }
-    parity += 1u;
-    return tot;
-}
-
-// ------------------------------------------------------------------------------------------------
-// per-attempt reduction: {sum err^2, max|y0|, max|y1|}.  For non-negative doubles the IEEE order is the order
-// of the bit patterns read as unsigned integers, and every NaN pattern sorts above +inf, so an integer max is a
-// NaN-propagating max for free; "y0 is non-finite" is simply max|y0| >= +inf (no fourth column).
-// ------------------------------------------------------------------------------------------------
-struct FRed {
-    double sum;
-    unsigned long long m0, m1;
-};
-
 __device__ __forceinline__ unsigned long long umax64(unsigned long long a, unsigned long long b) { return a > b ? a : b; }
 
-__device__ __forceinline__ FRed fred_combine(const FRed &a, const FRed &b) {
-    FRed r;
-    r.sum = a.sum + b.sum;
-    r.m0 = umax64(a.m0, b.m0);
-    r.m1 = umax64(a.m1, b.m1);
+// two 64-bit lanes of payload + one flag bit.  MODE 0: (a: sum >= 0, b: bit pattern of a non-negative double, combined
+// with an unsigned max -- NaN patterns sort above +inf, so it is a NaN-propagating max for free); MODE 1: (a, b: sums)
+struct Pay {
+    double a;
+    unsigned long long b;
+    unsigned flag;
+};
+
+template <int MODE>
+__device__ __forceinline__ Pay pay_identity() {
+    Pay r;
+    r.a = 0.0;
+    r.b = 0ull;       // +0.0 as a double, 0 as a max identity
+    r.flag = 0u;
     return r;
 }
 
-template <int BT>
-__device__ __forceinline__ FRed fred_block(FRed x, FRed *sh /*[BT/32]*/) {
+template <int MODE>
+__device__ __forceinline__ Pay pay_combine(const Pay &x, const Pay &y) {
+    Pay r;
+    r.a = x.a + y.a;
+    if (MODE == 0) r.b = x.b > y.b ? x.b : y.b;
+    else r.b = (unsigned long long)__double_as_longlong(__longlong_as_double((long long)x.b) + __longlong_as_double((long long)y.b));
+    r.flag = x.flag | y.flag;
+    return r;
+}
+
+template <int MODE>
+__device__ __forceinline__ Pay pay_warp_reduce(Pay x) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-        FRed y;
-        y.sum = __shfl_xor_sync(0xffffffffu, x.sum, o);
-        y.m0 = __shfl_xor_sync(0xffffffffu, x.m0, o);
-        y.m1 = __shfl_xor_sync(0xffffffffu, x.m1, o);
-        x = fred_combine(x, y);
+        Pay y;
+        y.a = __shfl_xor_sync(0xffffffffu, x.a, o);
+        y.b = __shfl_xor_sync(0xffffffffu, x.b, o);
+        y.flag = __shfl_xor_sync(0xffffffffu, x.flag, o);
+        x = pay_combine<MODE>(x, y);
     }
-    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-    __syncthreads();
-    if (l == 0) sh[w] = x;
-    __syncthreads();
-    FRed r = sh[0];
-#pragma unroll
-    for (int i = 1; i < BT / 32; ++i) r = fred_combine(r, sh[i]);
-    return r;   // valid in EVERY thread
+    return x;       // every lane holds the warp total (a + b == b + a bitwise, so all lanes agree)
 }
 
-// Grid-wide version; returns the totals as a Partial (columns as in the generic finalize kernel) in every thread.
-__device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long *p, unsigned long long v) {
-    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long *p) {
-    unsigned long long v;
-    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
+// transport form: 4 words, the flag rides in the sign bit of `a` (a is a sum of squares: never negative; a NaN is made
+// canonical first so that its sign bit is free too)
+__device__ __forceinline__ void pay_pack(const Pay &x, unsigned seq, unsigned long long (&w)[4]) {
+    unsigned long long ab = (unsigned long long)__double_as_longlong(x.a);
+    if (x.a != x.a) ab = 0x7ff8000000000000ull;
+    ab = (ab & 0x7fffffffffffffffull) | ((unsigned long long)(x.flag & 1u) << 63);
+    const unsigned long long s = (unsigned long long)seq << 32;
+    w[0] = s | (ab & 0xffffffffull);
+    w[1] = s | (ab >> 32);
+    w[2] = s | (x.b & 0xffffffffull);
+    w[3] = s | (x.b >> 32);
 }
 
-template <int BT>
-__device__ Partial fred_grid(const FusedParams &p, FRed mine, unsigned &parity, unsigned ll_base, FRed *shf) {
-    FRed *part = reinterpret_cast<FRed *>(p.part) + (size_t)(parity & 1u) * gridDim.x;
-    FRed b = fred_block<BT>(mine, shf);
-    if (threadIdx.x == 0) part[blockIdx.x] = b;
-    grid_barrier(p.bar, parity);
-    parity -= 1u;
-    FRed acc;
-    acc.sum = 0.0;
-    acc.m0 = acc.m1 = 0ull;
-    // gridDim.x <= 148 * blocks/SM: the first warps hold everything, the rest contribute the identity
-    for (int i = threadIdx.x; i < (int)gridDim.x; i += BT) acc = fred_combine(acc, part[i]);
-    FRed t = fred_block<BT>(acc, shf);
-    Partial tot;
-    tot.v[0] = t.sum;
-    tot.v[1] = __longlong_as_double((long long)t.m0);
-    tot.v[2] = __longlong_as_double((long long)t.m1);
-    tot.v[3] = (t.m0 >= 0x7ff0000000000000ull) ? 1.0 : 0.0;     // inf or NaN somewhere in y0
-    if (p.comm.nranks > 1) {
-        // Cross-GPU combine, low-latency protocol: block 0 pushes this rank's 3 totals to every peer as six
-        // {32 data bits | 32-bit sequence} words over NVLink; EVERY block polls its own rank's mailbox directly
-        // (no second hop through a local flag) and combines the ranks in rank order.
-        const unsigned seq = ll_base + parity + 1u;
-        const int par = (int)(seq & 1u);
-        __shared__ unsigned long long peer_bits[B2ODE_MAXPEERS][3];
-        if (threadIdx.x < p.comm.nranks) {
-            const int q = threadIdx.x;
-            if (blockIdx.x == 0) {
-                unsigned long long *dst = p.comm.box[q]->ll[par][p.comm.rank];
-                const unsigned long long bits[3] = {(unsigned long long)__double_as_longlong(t.sum), t.m0, t.m1};
+__device__ __forceinline__ Pay pay_unpack(const unsigned long long (&w)[4]) {
+    const unsigned long long ab = (w[0] & 0xffffffffull) | (w[1] << 32);
+    Pay r;
+    r.flag = (unsigned)(ab >> 63);
+    r.a = __longlong_as_double((long long)(ab & 0x7fffffffffffffffull));
+    r.b = (w[2] & 0xffffffffull) | (w[3] << 32);
+    return r;
+}
+
+template <bool SYS>
+__device__ __forceinline__ void ll_store4(unsigned long long *dst, const unsigned long long (&w)[4]) {
+    if (SYS) {
+        asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(dst), "l"(w[0]), "l"(w[1]) : "memory");
+        asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(dst + 2), "l"(w[2]), "l"(w[3]) : "memory");
+    } else {
+        asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(dst), "l"(w[0]), "l"(w[1]) : "memory");
+        asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(dst + 2), "l"(w[2]), "l"(w[3]) : "memory");
+    }
+}
+
+// spin until all four words carry `seq`; every 8-byte word is written atomically, so each is checked on its own
+template <bool SYS>
+__device__ __forceinline__ Pay ll_wait4(const unsigned long long *src, unsigned seq) {
+    unsigned long long w[4];
+    for (;;) {
+        if (SYS) {
+            asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(w[0]), "=l"(w[1]) : "l"(src) : "memory");
+            asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(w[2]), "=l"(w[3]) : "l"(src + 2) : "memory");
+        } else {
+            asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(w[0]), "=l"(w[1]) : "l"(src) : "memory");
+            asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(w[2]), "=l"(w[3]) : "l"(src + 2) : "memory");
+        }
+        if ((unsigned)(w[0] >> 32) == seq && (unsigned)(w[1] >> 32) == seq && (unsigned)(w[2] >> 32) == seq &&
+            (unsigned)(w[3] >> 32) == seq)
+            break;
+    }
+    return pay_unpack(w);
+}
+
+__device__ __forceinline__ void named_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void named_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
+constexpr int kGatherPerLane = 5;        // 160 blocks gathered with every poll in flight (148 SMs x 1 block)
+constexpr int kBarPartials = 1, kBarDecision = 2, kBarRows = 3, kBarRowsReady = 4;
+
+// Called by the CONTROL warp (all 32 lanes, convergent) once the compute warps' partials are in sh_part[0 .. ncw).
+// `epoch` counts the exchanges of this launch (1, 2, ...); ll_base is the persistent sequence base of the cross-GPU
+// mailbox.  Returns the group-wide totals in every lane.
+//
+// What the microbenchmark (scripts/micro/grid_barrier.cu, profiles/r02_fused_exchange_ab.md) showed on B200: a gpu-scope
+// STRONG load (ld.relaxed/acquire.gpu, ld.volatile, atomic read) costs 500-700 cycles and the strong loads of one warp do
+// not overlap -- a flag protocol that polls k words per message pays k round trips per poll, and a leader that gathers
+// 147 messages with 5 polls per lane pays ~10 serialised round trips (7.3k cycles per all-reduce, 9.2k with 4 loads per
+// poll, 13.4k two-level), against 1.9k for one atomic arrival counter + one acquire poll.  So: partials are published with
+// ordinary stores, ONE red.release.gpu on an arrival counter orders them, lane 0 spins on ONE ld.acquire.gpu of that
+// counter, and the partials are then fetched by all lanes with weak L2 loads (ld.global.cg), which pipeline.  Every block
+// reduces the same partials in the same fixed order, so all blocks hold bit-identical totals one hop after the last arrival.
+template <int MODE>
+__device__ __forceinline__ Pay control_allreduce(const FusedParams &p, const Pay *sh_part, int ncw, unsigned epoch, unsigned ll_base,
+                                                 int att = -1) {
+    const int lane = threadIdx.x & 31;
+    Pay x = (lane < ncw) ? sh_part[lane] : pay_identity<MODE>();
+    x = pay_warp_reduce<MODE>(x);                                         // block total, all lanes
+    FTRACE_DEP(att, 2, __double_as_longlong(x.a));
+    const unsigned par = epoch & 1u;
+    const int G = (int)gridDim.x;
+    if (G > 1) {
+        // Publish: the partial goes out as 4 tagged words {32 data bits | 32-bit epoch} (two 16-byte stores) followed by a
+        // RELAXED arrival on the counter -- no fence on the critical path (red.release costs a MEMBAR.GPU that waits for the
+        // store's round trip).  A reader that finds a stale tag (the arrival overtook the data) re-reads that partial with
+        // strong loads; in practice the data is there.
+        unsigned long long *slots = p.part2 + (size_t)par * G * 4;
+        if (lane == 0) {
+            unsigned long long w[4];
+            pay_pack(x, epoch, w);
+            unsigned long long *mine = slots + (size_t)blockIdx.x * 4;
+            asm volatile("st.global.v2.u64 [%0], {%1, %2};" ::"l"(mine), "l"(w[0]), "l"(w[1]) : "memory");
+            asm volatile("st.global.v2.u64 [%0], {%1, %2};" ::"l"(mine + 2), "l"(w[2]), "l"(w[3]) : "memory");
+            asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(p.ctr) : "memory");
+            const unsigned target = epoch * (unsigned)G;
+            unsigned v;
+            do {
+                asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p.ctr) : "memory");
+            } while ((int)(v - target) < 0);
+        }
+        __syncwarp();
+        FTRACE(att, 3);
+        // weak .cg loads bypass L1 and overlap (strong loads of one warp are serialised, ~600 cycles each)
+        unsigned long long gw[kGatherPerLane][4];
 #pragma unroll
-                for (int w = 0; w < 3; ++w) {
-                    st_relaxed_sys_u64(dst + 2 * w, ((unsigned long long)seq << 32) | (bits[w] & 0xffffffffull));
-                    st_relaxed_sys_u64(dst + 2 * w + 1, ((unsigned long long)seq << 32) | (bits[w] >> 32));
+        for (int q = 0; q < kGatherPerLane; ++q) {
+            const int b = lane + 32 * q;
+            const unsigned long long *src = slots + (size_t)(b < G ? b : 0) * 4;
+            asm volatile("ld.global.cg.v2.u64 {%0, %1}, [%2];" : "=l"(gw[q][0]), "=l"(gw[q][1]) : "l"(src) : "memory");
+            asm volatile("ld.global.cg.v2.u64 {%0, %1}, [%2];" : "=l"(gw[q][2]), "=l"(gw[q][3]) : "l"(src + 2) : "memory");
+        }
+        Pay acc = pay_identity<MODE>();
+#pragma unroll
+        for (int q = 0; q < kGatherPerLane; ++q) {
+            const int b = lane + 32 * q;
+            if (b < G) {
+                if ((unsigned)(gw[q][0] >> 32) != epoch || (unsigned)(gw[q][1] >> 32) != epoch ||
+                    (unsigned)(gw[q][2] >> 32) != epoch || (unsigned)(gw[q][3] >> 32) != epoch) {
+                    const Pay v = ll_wait4<false>(slots + (size_t)b * 4, epoch);          // rare: data behind its arrival
+                    acc = pay_combine<MODE>(acc, v);
+                } else {
+                    acc = pay_combine<MODE>(acc, pay_unpack(gw[q]));                       // fixed order -> deterministic
                 }
             }
-            const unsigned long long *src = p.comm.box[p.comm.rank]->ll[par][q];
-#pragma unroll
-            for (int w = 0; w < 3; ++w) {
-                unsigned long long lo, hi;
-                do {
-                    lo = ld_relaxed_sys_u64(src + 2 * w);
-                } while ((unsigned)(lo >> 32) != seq);
-                do {
-                    hi = ld_relaxed_sys_u64(src + 2 * w + 1);
-                } while ((unsigned)(hi >> 32) != seq);
-                peer_bits[q][w] = (lo & 0xffffffffull) | (hi << 32);
-            }
         }
-        __syncthreads();
-        FRed g;
-        g.sum = __longlong_as_double((long long)peer_bits[0][0]);
-        g.m0 = peer_bits[0][1];
-        g.m1 = peer_bits[0][2];
-        for (int q = 1; q < p.comm.nranks; ++q) {
-            g.sum += __longlong_as_double((long long)peer_bits[q][0]);
-            g.m0 = umax64(g.m0, peer_bits[q][1]);
-            g.m1 = umax64(g.m1, peer_bits[q][2]);
-        }
-        tot.v[0] = g.sum;
-        tot.v[1] = __longlong_as_double((long long)g.m0);
-        tot.v[2] = __longlong_as_double((long long)g.m1);
-        tot.v[3] = (g.m0 >= 0x7ff0000000000000ull) ? 1.0 : 0.0;
-        __syncthreads();
+        for (int b = lane + 32 * kGatherPerLane; b < G; b += 32)                            // grids beyond 32 * kGatherPerLane blocks
+            acc = pay_combine<MODE>(acc, ll_wait4<false>(slots + (size_t)b * 4, epoch));
+        x = pay_warp_reduce<MODE>(acc);                                   // this GPU's total, all lanes, all blocks alike
     }
-    parity += 1u;
+    if (p.comm.nranks <= 1) return x;
+    // ---- shared-step group: block 0 pushes this GPU's total into every rank's mailbox over NVLink (4 words
+    // {32 data bits | 32-bit sequence}: valid the moment the sequence matches, no fence); EVERY block polls its own
+    // rank's mailbox, lane q waiting for rank q with ONE strong load per poll (the second half first; the first half
+    // once that is in), and the ranks are combined in rank order -> bit-identical totals on all GPUs
+    const unsigned seq = ll_base + epoch;
+    if (blockIdx.x == 0 && lane < p.comm.nranks) {
+        unsigned long long w[4];
+        pay_pack(x, seq, w);
+        ll_store4<true>(p.comm.box[lane]->ll[par][p.comm.rank], w);      // own mailbox included
+    }
+    Pay mine = pay_identity<MODE>();
+    if (lane < p.comm.nranks) {
+        const unsigned long long *src = p.comm.box[p.comm.rank]->ll[par][lane];
+        unsigned long long w[4];
+        do {
+            asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(w[2]), "=l"(w[3]) : "l"(src + 2) : "memory");
+        } while ((unsigned)(w[2] >> 32) != seq || (unsigned)(w[3] >> 32) != seq);
+        do {
+            asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(w[0]), "=l"(w[1]) : "l"(src) : "memory");
+        } while ((unsigned)(w[0] >> 32) != seq || (unsigned)(w[1] >> 32) != seq);
+        mine = pay_unpack(w);
+    }
+    Pay tot;
+    tot.a = __shfl_sync(0xffffffffu, mine.a, 0);
+    tot.b = __shfl_sync(0xffffffffu, mine.b, 0);
+    tot.flag = __shfl_sync(0xffffffffu, mine.flag, 0);
+    for (int q = 1; q < p.comm.nranks; ++q) {
+        Pay v;
+        v.a = __shfl_sync(0xffffffffu, mine.a, q);
+        v.b = __shfl_sync(0xffffffffu, mine.b, q);
+        v.flag = __shfl_sync(0xffffffffu, mine.flag, q);
+        tot = pay_combine<MODE>(tot, v);
+    }
     return tot;
 }
 
-// what the controller (thread 0 of each block, identical everywhere) hands to the other threads of the block
+// The controller of the persistent kernel (one segment, the reference's controller: misc.py:250-287), written for the
+// shortest dependent chain -- it sits on the critical path of every attempt with the whole GPU waiting:
+//   accept  <=>  mean((err/tol)^2) <= 1  <=>  sum err^2 <= tol^2 * n         (no division; fp32 states compare in fp32,
+//                                                                             i.e. against the largest double that rounds to 1.0f)
+//   dt_next = dt / clamp(sqrt(m)^e / safety, 1/ifactor, 1/dfactor) = dt * clamp(safety * 2^(-e/2 * log2 m), dfactor', ifactor)
+//   with log2 m = log2(sum err^2) - log2(tol^2 n): two independent logarithms, one exp2, no division, no sqrt.
+// dt_next differs from the oracle's expression in the last ulps (an fp32 state: ~1e-7 relative, the oracle rounds sqrt(m)
+// to fp32) -- dt is a free parameter of the method; the parity bars are on the solution (1e-6 / 1e-3).
+// Called by all 32 lanes of the control warp, convergent (it shuffles).
+template <typename T>
+__device__ __forceinline__ CtrlDecision ctrl_fast(const CtrlParams &c, double ssq, double mm, bool bad0, double dt) {
+    const T tol = Ar<T>::add((T)c.atol[0], Ar<T>::mul((T)c.rtol[0], (T)mm));
+    const double tol2n = (double)tol * (double)tol * (double)c.n_global[0];
+    const double bound = std::is_same<T, float>::value ? tol2n * (1.0 + 5.9604644775390625e-08) : tol2n;
+    CtrlDecision d;
+    d.bad0 = bad0;
+    d.accept = ssq <= bound;
+    {
+        // the two logarithms are independent: lane 0 takes log2(ssq), the other lanes log2(tol2n) (one log2 on the chain)
+        const double lg = log2(((threadIdx.x & 31) == 0) ? ssq : tol2n);
+        const double L = __shfl_sync(0xffffffffu, lg, 0) - __shfl_sync(0xffffffffu, lg, 1);
+        const double df = (ssq < tol2n) ? 1.0 : c.dfactor;
+        const double rf = c.safety * exp2(-0.5 * c.exponent * L);
+        d.dt_next = (ssq == 0.0) ? dt * c.ifactor : dt * nan_min(c.ifactor, nan_max(df, rf));
+    }
+    d.m = 0.0;       // filled in off the critical path
+    return d;
+}
+
+// what the control warp hands to the compute warps of its block
 struct CtlOut {
-    double dt_next, t1_new;
-    int accept, cur, done;
+    double dt_next;
+    int accept, done;
     unsigned status;
-    // bookkeeping only thread 0 touches (kept out of everybody's registers)
-    double m, t_prev, dt_last;
-    unsigned long long n_acc, n_rej, attempts;
-    long long nadv;
+};
+
+// shared scratch of one block
+struct FusedShared {
+    Pay part[16];          // compute-warp partials
+    Pay tot;               // totals of the initial-step reductions (read by every thread)
+    CtlOut ctl;
 };
 
 // ------------------------------------------------------------------------------------------------
-// the persistent solve
+// the persistent solve.  Block = NCW compute warps (one trajectory per thread) + 1 control warp (the last one).
 // ------------------------------------------------------------------------------------------------
-template <typename T, typename RHS, int S, int BT>
-__global__ void __launch_bounds__(BT) k_fused_adaptive(const __grid_constant__ FusedParams p) {
+template <typename T, typename RHS, int S, int MAXT>
+__global__ void __launch_bounds__(MAXT) k_fused_adaptive(const __grid_constant__ FusedParams p) {
     using A = Ar<T>;
     constexpr int D = RHS::D;
-    __shared__ Partial sh[BT / 32];
-    __shared__ Partial sh_tot[1];
-    const long long i = (long long)blockIdx.x * BT + threadIdx.x;
+    __shared__ FusedShared sh;
+    __shared__ T sw[RHS::kSmem];
+    constexpr int kDenseRows = 3;
+    __shared__ __align__(16) T s_rows[kDenseRows][(MAXT - 32) * D];     // dense-output rows of the step, waiting for the decision
+    const int nthreads = blockDim.x;
+    const int ncw = (nthreads >> 5) - 1;                 // compute warps
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool is_control = warp == ncw;
+    const unsigned ll_base = (p.comm.nranks > 1) ? (unsigned)p.comm.box[p.comm.rank]->ll_seq : 0u;
+    if (RHS::kSmem > 1) {
+        const int nw = (int)p.rhs[0] * 5 + 2;
+        for (int q = threadIdx.x; q < nw && q < RHS::kSmem; q += nthreads) sw[q] = ((const T *)p.rhs_data)[q];
+        __syncthreads();
+    }
+    const int n_out = p.c.n_out;
+    const double *__restrict__ t_out = p.c.t_out;
+
+    if (is_control) {
+        // ================================ control warp =================================================
+        unsigned epoch = 0;
+        double t_cur = p.t_start, dt;
+        unsigned status = 0;
+        if (p.have_first_step) {
+            dt = p.first_step;
+        } else {
+            // misc.py:226-247 with the two reductions of _select_initial_step
+            named_sync(kBarPartials, nthreads);
+            Pay r = control_allreduce<1>(p, sh.part, ncw, ++epoch, ll_base);
+            if (lane == 0) sh.tot = r;
+            named_arrive(kBarDecision, nthreads);
+            Partial tot;
+            tot.v[0] = r.a;
+            tot.v[1] = __longlong_as_double((long long)r.b);
+            tot.v[2] = tot.v[3] = 0.0;
+            T d1max;
+            const T h0 = init_h0<T>(p.c, &tot, 1, &d1max);
+            named_sync(kBarPartials, nthreads);
+            r = control_allreduce<1>(p, sh.part, ncw, ++epoch, ll_base);
+            if (lane == 0) sh.tot = r;
+            named_arrive(kBarDecision, nthreads);
+            tot.v[0] = r.a;
+            dt = (double)init_dt<T>(p.c, &tot, 1, h0, d1max);
+        }
+        int cur = 1;
+        int done = (n_out <= 1) ? 1 : 0;
+        if (!done && !(t_cur + dt > t_cur)) {
+            status |= B2ODE_ST_UNDERFLOW;
+            done = 1;
+        }
+        // bookkeeping for the final state
+        double m_last = 0.0, t_prev = t_cur, dt_last = 0.0;
+        unsigned long long n_acc = 0, n_rej = 0;
+        long long nadv = 0;
+        int att = 0;
+        while (!done) {
+            FTRACE(att, 0);
+            // everything that does not depend on the reduction, computed while the compute warps work
+            const double t1_acc = t_cur + dt;
+            int c2 = cur;
+            while (c2 < n_out && __ldg(t_out + c2) <= t1_acc) ++c2;             // advance(): `while next_t > t1`
+            if (c2 > cur) named_arrive(kBarRows, nthreads);                    // the previous step's rows have been copied out
+            named_sync(kBarPartials, nthreads);                                // the compute warps' partials are in
+            FTRACE_DEP(att, 1, sh.part[0].flag);
+            const Pay r = control_allreduce<0>(p, sh.part, ncw, ++epoch, ll_base, att);
+            FTRACE_DEP(att, 4, __double_as_longlong(r.a));
+            Partial tot;
+            tot.v[0] = r.a;
+            tot.v[1] = tot.v[2] = __longlong_as_double((long long)r.b);        // max(max|y0|, max|y1|)
+            tot.v[3] = r.flag ? 1.0 : 0.0;                                      // inf or NaN somewhere in y0
+            CtrlDecision dec = ctrl_fast<T>(p.c, tot.v[0], tot.v[1], r.flag != 0u, dt);
+            unsigned st_bits = status;
+            if (dec.bad0) st_bits |= B2ODE_ST_NONFINITE;
+            const bool adv = dec.accept && !dec.bad0;
+            const double t1n = dec.accept ? t1_acc : t_cur;
+            const int c_new = adv ? c2 : cur;
+            const long long nadv2 = (c_new > cur) ? 0 : nadv + 1;
+            int dn = (c_new >= n_out) ? 1 : 0;
+            if (!dn) {
+                if (nadv2 >= p.c.max_num_steps) st_bits |= B2ODE_ST_MAXSTEPS;
+                if (!(t1n + dec.dt_next > t1n)) st_bits |= B2ODE_ST_UNDERFLOW;
+            }
+            if (st_bits) dn = 1;
+            if (lane == 0) {
+                sh.ctl.dt_next = dec.dt_next;
+                sh.ctl.accept = dec.accept ? 1 : 0;
+                sh.ctl.done = dn;
+                sh.ctl.status = st_bits;
+            }
+            named_arrive(kBarDecision, nthreads);
+            FTRACE_DEP(att, 5, __double_as_longlong(dec.dt_next));
+            if (c2 > cur) named_sync(kBarRowsReady, nthreads);                  // the compute warps' rows are in shared memory
+            if (adv && c2 > cur) {
+                // The accepted step's dense-output rows wait in shared memory (written by the compute warps before the
+                // decision barrier): this otherwise idle warp streams them to the solution slab with 16-byte stores while
+                // the compute warps are already in the next attempt's stages.  The block's part of an output row is one
+                // contiguous run of nblk * D elements.
+                const long long first = (long long)blockIdx.x * (ncw * 32);
+                long long nblk = p.n_traj - first;
+                if (nblk > ncw * 32) nblk = ncw * 32;
+                const int nel = (int)(nblk > 0 ? nblk * D : 0);
+                const long long Nrow = p.n_traj * D;
+                const int nrows = (c2 - cur) < kDenseRows ? (c2 - cur) : kDenseRows;
+                for (int q = 0; q < nrows; ++q) {
+                    T *row = (T *)p.out + (long long)(cur + q) * Nrow + first * D;
+                    const T *src = s_rows[q];
+                    constexpr int V = 16 / sizeof(T);
+                    if ((reinterpret_cast<uintptr_t>(row) & 15u) == 0) {
+                        const int nv = nel / V;
+                        for (int e = lane; e < nv; e += 32)
+                            reinterpret_cast<int4 *>(row)[e] = reinterpret_cast<const int4 *>(src)[e];
+                        for (int e = nv * V + lane; e < nel; e += 32) row[e] = src[e];
+                    } else {
+                        for (int e = lane; e < nel; e += 32) row[e] = src[e];
+                    }
+                }
+            }
+            {   // the reported error ratio (b2ode_state.msr_max), off the critical path
+                const T tol = Ar<T>::add((T)p.c.atol[0], Ar<T>::mul((T)p.c.rtol[0], (T)tot.v[1]));
+                dec.m = (double)(T)(tot.v[0] / ((double)tol * (double)tol * (double)p.c.n_global[0]));
+            }
+            m_last = dec.m;
+            dt_last = dt;
+            if (dec.accept) {
+                n_acc += 1;
+                t_prev = t_cur;
+                t_cur = t1n;
+            } else {
+                n_rej += 1;
+            }
+            cur = c_new;
+            nadv = nadv2;
+            dt = dec.dt_next;
+            status = st_bits;
+            done = dn;
+            ++att;
+        }
+        if (blockIdx.x == 0 && lane == 0) {
+            b2ode_state z;
+            memset(&z, 0, sizeof(z));
+            z.t0 = t_prev;
+            z.t1 = t_cur;
+            z.dt = dt;
+            z.dt_last = dt_last;
+            z.msr_max = m_last;
+            z.n_acc = n_acc;
+            z.n_rej = n_rej;
+            z.attempt = n_acc + n_rej;
+            z.n_steps_adv = nadv;
+            z.done = 1;
+            z.status = status;
+            z.cursor = cur;
+            z.xseq = p.st->xseq;
+            *p.st = z;
+            if (p.comm.nranks > 1) p.comm.box[p.comm.rank]->ll_seq = (unsigned long long)(ll_base + epoch);
+        }
+        return;
+    }
+
+    // ================================ compute warps ====================================================
+    const long long i = (long long)blockIdx.x * (ncw * 32) + threadIdx.x;
     const bool live = i < p.n_traj;
     const long long N = p.n_traj * D;
     const T *y0g = (const T *)p.y0;
     T *out = (T *)p.out;
     const T tsign = (T)p.time_sign;
-    unsigned parity = 0;
-    // sequence base of the low-latency exchange (persists in this rank's mailbox across solves); the two grid
-    // reductions of the initial-step heuristic use the generic mailbox protocol, the attempts use this one
-    const unsigned ll_base = (p.comm.nranks > 1) ? (unsigned)p.comm.box[p.comm.rank]->ll_seq : 0u;
-
     T y[D], f0[D];
 #pragma unroll
     for (int d = 0; d < D; ++d) y[d] = live ? y0g[i * D + d] : T(0);
     if (live) {
 #pragma unroll
         for (int d = 0; d < D; ++d) out[i * D + d] = y[d];                 // solution[0] = y0 (solvers.py:29)
-    }
-    __shared__ T sw[RHS::kSmem];
-    if (RHS::kSmem > 1) {
-        const int nw = (int)p.rhs[0] * 5 + 2;
-        for (int q = threadIdx.x; q < nw && q < RHS::kSmem; q += BT) sw[q] = ((const T *)p.rhs_data)[q];
-        __syncthreads();
     }
     auto rhs = [&](T t, const T(&yy)[D], T(&dy)[D]) {
         // reverse-time wrapper of misc.py:318-321: f'(t, y) = -f(-t, y)
@@ -354,67 +575,69 @@ __global__ void __launch_bounds__(BT) k_fused_adaptive(const __grid_constant__ F
             RHS::eval(p.rhs, sw, t, yy, dy);
         }
     };
+    // hand this warp's share to the control warp; do not wait
+    auto contribute = [&](const Pay &mine, auto mode) {
+        constexpr int MODE = decltype(mode)::value;
+        const Pay w = pay_warp_reduce<MODE>(mine);
+        if (lane == 0) sh.part[warp] = w;
+        named_arrive(kBarPartials, nthreads);
+    };
     double t_cur = p.t_start;
     rhs((T)t_cur, y, f0);                                                    // dopri5.py:71
 
     // ---- first step: given (dopri5.py:76) or _select_initial_step (misc.py:183-247) ----------------------
     double dt;
-    unsigned status = 0;
-    int cur = 1;
     if (p.have_first_step) {
         dt = p.first_step;
     } else {
         const T rtol = (T)p.rtol0, atol = (T)p.atol0;
         T scale[D];
-        Partial mine = identity<0u>();
+        Pay mine = pay_identity<1>();
+        double s0 = 0.0, s1 = 0.0;
 #pragma unroll
         for (int d = 0; d < D; ++d) {
             scale[d] = A::add(atol, A::mul(A::abs(y[d]), rtol));
             if (live) {
                 const double q0 = (double)A::div(y[d], scale[d]), q1 = (double)A::div(f0[d], scale[d]);
-                mine.v[0] += q0 * q0;
-                mine.v[1] += q1 * q1;
+                s0 += q0 * q0;
+                s1 += q1 * q1;
             }
         }
-        Partial tot = grid_reduce<0u, BT>(p, mine, parity, sh, sh_tot);
+        mine.a = s0;
+        mine.b = (unsigned long long)__double_as_longlong(s1);
+        contribute(mine, IC<1>{});
+        named_sync(kBarDecision, nthreads);
+        Partial tot;
+        tot.v[0] = sh.tot.a;
+        tot.v[1] = __longlong_as_double((long long)sh.tot.b);
+        tot.v[2] = tot.v[3] = 0.0;
         T d1max;
         const T h0 = init_h0<T>(p.c, &tot, 1, &d1max);
         T y1[D], f1[D];
 #pragma unroll
         for (int d = 0; d < D; ++d) y1[d] = A::add(y[d], A::mul(h0, f0[d]));
         rhs(A::add((T)t_cur, h0), y1, f1);
-        mine = identity<0u>();
+        double s2 = 0.0;
         if (live) {
 #pragma unroll
             for (int d = 0; d < D; ++d) {
                 const double q = (double)A::div(A::sub(f1[d], f0[d]), scale[d]);
-                mine.v[0] += q * q;
+                s2 += q * q;
             }
         }
-        tot = grid_reduce<0u, BT>(p, mine, parity, sh, sh_tot);
+        mine.a = s2;
+        mine.b = 0ull;
+        contribute(mine, IC<1>{});
+        named_sync(kBarDecision, nthreads);
+        tot.v[0] = sh.tot.a;
         dt = (double)init_dt<T>(p.c, &tot, 1, h0, d1max);
     }
-    int done = (p.c.n_out <= 1) ? 1 : 0;
-    if (!done && !(t_cur + dt > t_cur)) {
-        status |= B2ODE_ST_UNDERFLOW;
-        done = 1;
-    }
+    int cur = 1;
+    int done = (n_out <= 1) ? 1 : 0;
+    if (!done && !(t_cur + dt > t_cur)) done = 1;
 
     // ---- attempts -------------------------------------------------------------------------------------
-    __shared__ FRed shf[BT / 32];
-    __shared__ CtlOut ctl;
-    if (threadIdx.x == 0) {
-        ctl.m = 0.0;
-        ctl.t_prev = t_cur;
-        ctl.dt_last = 0.0;
-        ctl.n_acc = ctl.n_rej = ctl.attempts = 0ull;
-        ctl.nadv = 0;
-        ctl.cur = cur;
-        ctl.status = status;
-        ctl.dt_next = dt;
-        ctl.t1_new = t_cur;
-    }
-    __syncthreads();
+    int att = 0;
     while (!done) {
         const T t0c = (T)t_cur, dtc = (T)dt;                               // rk_common.py:45-46
         T k[S][D];
@@ -425,140 +648,90 @@ __global__ void __launch_bounds__(BT) k_fused_adaptive(const __grid_constant__ F
         for (int s = 0; s < S - 1; ++s) {
             const T ti = A::add(t0c, A::mul((T)p.c.alpha[s], dtc));
             T acc[D];
-            bool first = true;
 #pragma unroll
             for (int j = 0; j <= s; ++j) {
-                const double bj = p.beta[s][j];
-                if (bj != 0.0) {                                           // uniform: the tableau's structural zeros
-                    const T c = A::mul(dtc, (T)bj);                        // (scale * x), misc.py:121
+                const T c = A::mul(dtc, (T)p.beta[s][j]);                  // (scale * x), misc.py:121
 #pragma unroll
-                    for (int d = 0; d < D; ++d) {
-                        const T term = A::mul(c, k[j][d]);
-                        acc[d] = first ? term : A::add(acc[d], term);
-                    }
-                    first = false;
+                for (int d = 0; d < D; ++d) {
+                    const T term = A::mul(c, k[j][d]);
+                    acc[d] = (j == 0) ? term : A::add(acc[d], term);
                 }
             }
 #pragma unroll
-            for (int d = 0; d < D; ++d) yi[d] = first ? y[d] : A::add(y[d], acc[d]);
+            for (int d = 0; d < D; ++d) yi[d] = A::add(y[d], acc[d]);
             rhs(ti, yi, k[s + 1]);
         }
         if (!p.fsal) {                                                     // rk_common.py:54-56
             T acc[D];
-            bool first = true;
 #pragma unroll
             for (int j = 0; j < S; ++j) {
-                const double cj = p.c_sol[j];
-                if (cj != 0.0) {
-                    const T c = A::mul(dtc, (T)cj);
+                const T c = A::mul(dtc, (T)p.c_sol[j]);
 #pragma unroll
-                    for (int d = 0; d < D; ++d) {
-                        const T term = A::mul(c, k[j][d]);
-                        acc[d] = first ? term : A::add(acc[d], term);
-                    }
-                    first = false;
+                for (int d = 0; d < D; ++d) {
+                    const T term = A::mul(c, k[j][d]);
+                    acc[d] = (j == 0) ? term : A::add(acc[d], term);
                 }
             }
 #pragma unroll
-            for (int d = 0; d < D; ++d) yi[d] = first ? y[d] : A::add(y[d], acc[d]);
+            for (int d = 0; d < D; ++d) yi[d] = A::add(y[d], acc[d]);
         }
         // error estimate + this thread's share of the reduction (rk_common.py:60, misc.py:256-263)
-        FRed mine;
-        mine.sum = 0.0;
-        mine.m0 = mine.m1 = 0ull;
         {
+            Pay mine = pay_identity<0>();
             T err[D];
-            bool first = true;
 #pragma unroll
             for (int j = 0; j < S; ++j) {
-                const double cj = p.c_error[j];
-                if (cj != 0.0) {
-                    const T c = A::mul(dtc, (T)cj);
+                const T c = A::mul(dtc, (T)p.c_error[j]);
 #pragma unroll
-                    for (int d = 0; d < D; ++d) {
-                        const T term = A::mul(c, k[j][d]);
-                        err[d] = first ? term : A::add(err[d], term);
-                    }
-                    first = false;
+                for (int d = 0; d < D; ++d) {
+                    const T term = A::mul(c, k[j][d]);
+                    err[d] = (j == 0) ? term : A::add(err[d], term);
                 }
             }
             if (live) {
+                double sum = 0.0;
+                unsigned long long m0 = 0ull, m1 = 0ull;
 #pragma unroll
                 for (int d = 0; d < D; ++d) {
-                    const double ed = first ? 0.0 : (double)err[d];
-                    mine.sum += ed * ed;
-                    mine.m0 = umax64(mine.m0, (unsigned long long)__double_as_longlong(fabs((double)y[d])));
-                    mine.m1 = umax64(mine.m1, (unsigned long long)__double_as_longlong(fabs((double)yi[d])));
+                    const double ed = (double)err[d];
+                    sum += ed * ed;
+                    m0 = umax64(m0, (unsigned long long)__double_as_longlong(fabs((double)y[d])));
+                    m1 = umax64(m1, (unsigned long long)__double_as_longlong(fabs((double)yi[d])));
                 }
+                mine.a = sum;
+                mine.b = umax64(m0, m1);
+                mine.flag = (m0 >= 0x7ff0000000000000ull) ? 1u : 0u;     // inf or NaN in y0 (dopri5.py:100)
             }
+            contribute(mine, IC<0>{});
         }
-        const Partial tot = fred_grid<BT>(p, mine, parity, ll_base, shf);
-        // controller: once per block (thread 0), identical in every block; broadcast through shared memory
-        if (threadIdx.x == 0) {
-            const CtrlDecision dec = ctrl_decide<T>(p.c, &tot, 1, dt);
-            unsigned st_bits = status;
-            if (dec.bad0) st_bits |= B2ODE_ST_NONFINITE;
-            const double t1n = dec.accept ? t_cur + dt : t_cur;
-            int c2 = cur;
-            if (dec.accept && !dec.bad0) {
-                while (c2 < p.c.n_out && p.c.t_out[c2] <= t1n) ++c2;        // advance(): `while next_t > t1`
-            }
-            const long long nadv2 = (c2 > cur) ? 0 : ctl.nadv + 1;
-            int dn = (c2 >= p.c.n_out) ? 1 : 0;
-            if (!dn) {
-                if (nadv2 >= p.c.max_num_steps) st_bits |= B2ODE_ST_MAXSTEPS;
-                if (!(t1n + dec.dt_next > t1n)) st_bits |= B2ODE_ST_UNDERFLOW;
-            }
-            if (st_bits) dn = 1;
-            ctl.dt_next = dec.dt_next;
-            ctl.t1_new = t1n;
-            ctl.m = dec.m;
-            ctl.accept = dec.accept ? 1 : 0;
-            ctl.cur = c2;
-            ctl.done = dn;
-            ctl.status = st_bits;
-            ctl.nadv = nadv2;
-            ctl.dt_last = dt;
-            ctl.attempts += 1;
-            if (dec.accept) {
-                ctl.n_acc += 1;
-                ctl.t_prev = t_cur;
-            } else {
-                ctl.n_rej += 1;
-            }
-        }
-        __syncthreads();
-        const bool accept = ctl.accept != 0;
-        const double t1_new = ctl.t1_new;
-        const int j0 = cur;
-        cur = ctl.cur;
-        if (accept && cur > j0 && live) {
-            // dense output for every output time inside the step (dopri5.py:39-45, interp.py:22-67)
-            const T t0s = t0c, t1s = (T)t1_new;
-            const T den = A::sub(t1s, t0s);
+        FTRACE(att, 8);
+        // ---- dense output (dopri5.py:39-45, interp.py:22-67): the VALUES of the first kDenseRows output rows of the step are
+        // computed now, while the control warp runs the reduction (the arithmetic overlaps the exchange latency); they are
+        // STORED only once the step is known to be accepted -- the stores then drain under the next attempt's stages instead
+        // of queueing in front of the control warp's loads (measured: speculative stores tripled the exchange time)
+        const double t1_acc = t_cur + dt;
+        int c2 = cur;
+        while (c2 < n_out && __ldg(t_out + c2) <= t1_acc) ++c2;                 // advance(): `while next_t > t1`
+        const T t0s = t0c, t1s = (T)t1_acc;
+        const T den = A::sub(t1s, t0s);
+        auto fit = [&](T(&ca)[D], T(&cb)[D], T(&cc)[D], T(&cd)[D]) {
             const T m2dt = A::mul(T(-2), dtc), p2dt = A::mul(T(2), dtc), p5dt = A::mul(T(5), dtc);
             const T m3dt = A::mul(T(-3), dtc), m4dt = A::mul(T(-4), dtc);
             T ymid[D];
             {
                 T acc[D];
-                bool first = true;
 #pragma unroll
                 for (int j = 0; j < S; ++j) {
-                    const double cj = p.c_mid[j];
-                    if (cj != 0.0) {
-                        const T c = A::mul(dtc, (T)cj);
+                    const T c = A::mul(dtc, (T)p.c_mid[j]);
 #pragma unroll
-                        for (int d = 0; d < D; ++d) {
-                            const T term = A::mul(c, k[j][d]);
-                            acc[d] = first ? term : A::add(acc[d], term);
-                        }
-                        first = false;
+                    for (int d = 0; d < D; ++d) {
+                        const T term = A::mul(c, k[j][d]);
+                        acc[d] = (j == 0) ? term : A::add(acc[d], term);
                     }
                 }
 #pragma unroll
-                for (int d = 0; d < D; ++d) ymid[d] = first ? y[d] : A::add(y[d], acc[d]);
+                for (int d = 0; d < D; ++d) ymid[d] = A::add(y[d], acc[d]);
             }
-            T ca[D], cb[D], cc[D], cd[D];
 #pragma unroll
             for (int d = 0; d < D; ++d) {
                 const T f0e = k[0][d], f1e = k[S - 1][d], y0e = y[d], y1e = yi[d];
@@ -582,78 +755,113 @@ __global__ void __launch_bounds__(BT) k_fused_adaptive(const __grid_constant__ F
                 cc[d] = cq;
                 cd[d] = A::mul(dtc, f0e);
             }
-            for (int j = j0; j < cur; ++j) {
-                const T x = A::div(A::sub((T)p.c.t_out[j], t0s), den);
-                const T x2 = A::mul(x, x), x3 = A::mul(x2, x), x4 = A::mul(x3, x);
-                T *row = out + (long long)j * N + i * D;
+        };
+        auto eval_row = [&](int j, const T(&ca)[D], const T(&cb)[D], const T(&cc)[D], const T(&cd)[D], T(&r)[D]) {
+            const T x = A::div(A::sub((T)__ldg(t_out + j), t0s), den);
+            const T x2 = A::mul(x, x), x3 = A::mul(x2, x), x4 = A::mul(x3, x);
 #pragma unroll
-                for (int d = 0; d < D; ++d) {
-                    T r = A::mul(ca[d], x4);
-                    r = A::add(r, A::mul(cb[d], x3));
-                    r = A::add(r, A::mul(cc[d], x2));
-                    r = A::add(r, A::mul(cd[d], x));
-                    r = A::add(r, y[d]);
-                    row[d] = r;
+            for (int d = 0; d < D; ++d) {
+                T v = A::mul(ca[d], x4);
+                v = A::add(v, A::mul(cb[d], x3));
+                v = A::add(v, A::mul(cc[d], x2));
+                v = A::add(v, A::mul(cd[d], x));
+                r[d] = A::add(v, y[d]);
+            }
+        };
+        // the rows wait in shared memory, laid out exactly like the block's contiguous chunk of an output row
+        const bool blk_out = c2 > cur;                                        // uniform over the grid
+        if (blk_out) {
+            named_sync(kBarRows, nthreads);                                   // the control warp has copied the previous step's rows out
+            if (live) {
+                T ca[D], cb[D], cc[D], cd[D];
+                fit(ca, cb, cc, cd);
+#pragma unroll
+                for (int q = 0; q < kDenseRows; ++q) {
+                    if (cur + q < c2) {
+                        T r[D];
+                        eval_row(cur + q, ca, cb, cc, cd, r);
+#pragma unroll
+                        for (int d = 0; d < D; ++d) s_rows[q][threadIdx.x * D + d] = r[d];
+                    }
                 }
             }
         }
+        if (blk_out) named_arrive(kBarRowsReady, nthreads);                   // rows handed to the control warp
+        FTRACE(att, 9);
+        named_sync(kBarDecision, nthreads);                                 // the control warp's decision
+        const bool accept = sh.ctl.accept != 0;
+        FTRACE_DEP(att, 10, sh.ctl.accept);
         // state update (dopri5.py:113-120)
         if (accept) {
-            t_cur = t1_new;
+            if (blk_out) {
+                if (cur + kDenseRows < c2 && live) {                         // long steps: the remaining rows, after the fact
+                    T ca[D], cb[D], cc[D], cd[D];
+                    fit(ca, cb, cc, cd);                                     // (recomputed: not kept live over the barrier)
+                    for (int j = cur + kDenseRows; j < c2; ++j) {
+                        T r[D];
+                        eval_row(j, ca, cb, cc, cd, r);
+                        T *row = out + (long long)j * N + i * D;
+#pragma unroll
+                        for (int d = 0; d < D; ++d) row[d] = r[d];
+                    }
+                }
+            }
+            t_cur = t1_acc;
+            cur = c2;                     // (a non-finite y0 also sets `done`, so the cursor is moot in that case)
 #pragma unroll
             for (int d = 0; d < D; ++d) {
                 y[d] = yi[d];
                 f0[d] = k[S - 1][d];
             }
         }
-        dt = ctl.dt_next;
-        status = ctl.status;
-        done = ctl.done;
-        __syncthreads();     // ctl is rewritten by thread 0 in the next attempt
-    }
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        b2ode_state z;
-        memset(&z, 0, sizeof(z));
-        z.t0 = ctl.t_prev;
-        z.t1 = t_cur;
-        z.dt = dt;
-        z.dt_last = ctl.dt_last;
-        z.msr_max = ctl.m;
-        z.n_acc = ctl.n_acc;
-        z.n_rej = ctl.n_rej;
-        z.attempt = ctl.attempts;
-        z.n_steps_adv = ctl.nadv;
-        z.done = 1;
-        z.status = status;
-        z.cursor = cur;
-        z.xseq = p.st->xseq;
-        *p.st = z;
-        if (p.comm.nranks > 1) p.comm.box[p.comm.rank]->ll_seq = (unsigned long long)(ll_base + parity);
+        dt = sh.ctl.dt_next;
+        done = sh.ctl.done;
+        ++att;
     }
 }
 
 // ================================================================================================
 // host side
 // ================================================================================================
-// `capacity` != null: only report how many trajectories this instantiation can keep co-resident on the current device
-template <typename T, typename RHS, int S, int BT>
+// Block geometry: NCW compute warps + 1 control warp.  One block per SM when the batch allows it (fewest partials to
+// gather, all 148 SMs busy): NCW = ceil(ceil(n / SMs) / 32), capped by the register budget of the instantiation.
+// `capacity` != null: only report how many trajectories this instantiation can keep co-resident on the current device.
+template <typename T, typename RHS, int S, int MAXT>
 static int fused_launch(const FusedParams &p, long long n_traj, cudaStream_t st, long long *capacity = nullptr) {
     void *args[] = {(void *)&p};
     int dev = 0, coop = 0, nsm = 0, per_sm = 0;
     B2_CUDA(cudaGetDevice(&dev));
     B2_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
     B2_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
-    B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused_adaptive<T, RHS, S, BT>, BT, 0));
+    constexpr int kMaxNcw = MAXT / 32 - 1;
     if (capacity) {
-        *capacity = coop ? (long long)per_sm * nsm * BT : 0;
+        long long best = 0;
+        for (int ncw = kMaxNcw; ncw >= 1 && coop; --ncw) {
+            B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused_adaptive<T, RHS, S, MAXT>, 32 * (ncw + 1), 0));
+            const long long cap = (long long)per_sm * nsm * ncw * 32;
+            if (cap > best) best = cap;
+        }
+        *capacity = best;
         return 0;
     }
     if (!coop) return b2_fail(B2ODE_ESTATE, "device does not support cooperative launch");
-    const int grid = (int)((n_traj + BT - 1) / BT);
-    if (grid > per_sm * nsm)
-        return b2_fail(B2ODE_ENOMEM, "batch needs %d co-resident blocks of %d threads, device holds %d", grid, BT, per_sm * nsm);
+    long long per_block = (n_traj + nsm - 1) / nsm;
+    int ncw = (int)((per_block + 31) / 32);
+    if (ncw < 1) ncw = 1;
+    if (ncw > kMaxNcw) ncw = kMaxNcw;
+    int threads = 0, grid = 0;
+    // the largest block that keeps the whole batch co-resident (smaller blocks can pack more warps per SM when the
+    // register file, not the block size, is the limit)
+    for (; ncw >= 1; --ncw) {
+        threads = 32 * (ncw + 1);
+        grid = (int)((n_traj + (long long)ncw * 32 - 1) / ((long long)ncw * 32));
+        B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused_adaptive<T, RHS, S, MAXT>, threads, 0));
+        if (grid <= per_sm * nsm) break;
+    }
+    if (ncw < 1)
+        return b2_fail(B2ODE_ENOMEM, "batch of %lld trajectories cannot stay co-resident on %d SMs", n_traj, nsm);
     const int slot = b2_timing_begin(6 /* B2_FAM_FUSED */, st);
-    B2_CUDA(cudaLaunchCooperativeKernel((const void *)k_fused_adaptive<T, RHS, S, BT>, dim3(grid), dim3(BT), args, 0, st));
+    B2_CUDA(cudaLaunchCooperativeKernel((const void *)k_fused_adaptive<T, RHS, S, MAXT>, dim3(grid), dim3(threads), args, 0, st));
     b2_timing_end(6, slot, st);
     b2_count_launch();
     return 0;
@@ -661,12 +869,12 @@ static int fused_launch(const FusedParams &p, long long n_traj, cudaStream_t st,
 
 template <typename T, typename RHS>
 static int fused_dispatch_s(const FusedParams &p, int n_k, long long n_traj, cudaStream_t st, long long *capacity) {
-    // 512-thread blocks (<= 128 registers per thread) for the tableaus whose k-set fits; 128 otherwise
+    // up to 512 threads per block (<= 128 registers per thread) for the tableaus whose k-set fits; 256 otherwise
     switch (n_k) {
         case 2: return fused_launch<T, RHS, 2, 512>(p, n_traj, st, capacity);
         case 4: return fused_launch<T, RHS, 4, 512>(p, n_traj, st, capacity);
         case 7: return fused_launch<T, RHS, 7, 512>(p, n_traj, st, capacity);
-        case 14: return fused_launch<T, RHS, 14, 128>(p, n_traj, st, capacity);
+        case 14: return fused_launch<T, RHS, 14, 256>(p, n_traj, st, capacity);
     }
     return b2_fail(B2ODE_EINVAL, "fused solve supports tableaus with 2, 4, 7 or 14 k's (got %d)", n_k);
 }
@@ -710,9 +918,9 @@ static int rhs_check(int kind, const double *prm, int n_prm, const void *rhs_dat
 }
 
 extern "C" size_t b2ode_fused_workspace_bytes(int64_t n_traj) {
-    const long long grid = (n_traj + 127) / 128;      // the smallest block size used is 128
-    // [2][grid] partials + 2 group totals + barrier words + flag, 256-byte aligned pieces
-    return (size_t)(2 * grid + 2) * sizeof(Partial) + 256;
+    const long long grid_max = (n_traj + 31) / 32;       // the smallest block has one compute warp
+    // [arrival counter, 128 B][partials 2 x grid x 32 B]
+    return (size_t)128 + (size_t)grid_max * 64;
 }
 
 extern "C" int b2ode_fused_solve(const b2ode_adaptive_desc *desc, int rhs_kind, const double *rhs_params, int n_rhs_params,
@@ -729,16 +937,15 @@ extern "C" int b2ode_fused_solve(const b2ode_adaptive_desc *desc, int rhs_kind, 
     if (n_traj < 1) return b2_fail(B2ODE_EINVAL, "empty batch");
     if (workspace_bytes < b2ode_fused_workspace_bytes(n_traj)) return b2_fail(B2ODE_ENOMEM, "workspace too small");
     cudaStream_t st = (cudaStream_t)cuda_stream;
-    // workspace layout: [barrier 2 x u32 | pad to 64][flag u64 | pad to 128][gtot x2][partials 2 x grid]
+    // workspace layout: [arrival counter | pad to 128 B][partials 2 x grid x 16 B]; the counter starts at 0 every launch
     unsigned char *w = (unsigned char *)workspace;
-    B2_CUDA(cudaMemsetAsync(w, 0, 256, st));
+    if ((uintptr_t)w & 15u) return b2_fail(B2ODE_EINVAL, "workspace must be 16-byte aligned");
+    B2_CUDA(cudaMemsetAsync(w, 0, b2ode_fused_workspace_bytes(n_traj), st));      // epoch tags start at 1
     FusedParams p;
     memset(&p, 0, sizeof(p));
     p.st = (b2ode_state *)state;
-    p.bar = (unsigned *)w;
-    p.gflag = (unsigned long long *)(w + 64);
-    p.gtot = (Partial *)(w + 128);
-    p.part = (Partial *)(w + 256);
+    p.ctr = (unsigned *)w;
+    p.part2 = (unsigned long long *)(w + 128);
     p.y0 = y0;
     p.out = out;
     p.n_traj = n_traj;
@@ -771,6 +978,9 @@ extern "C" int b2ode_fused_solve(const b2ode_adaptive_desc *desc, int rhs_kind, 
     p.c.ifactor = desc->ifactor;
     p.c.dfactor = desc->dfactor;
     p.c.exponent = desc->exponent;
+    p.c.inv_safety = 1.0 / desc->safety;
+    p.c.inv_ifactor = 1.0 / desc->ifactor;
+    p.c.inv_dfactor = 1.0 / desc->dfactor;
     p.c.max_num_steps = desc->max_num_steps;
     p.c.init_order = desc->init_order;
     p.c.n_out = n_out;
