@@ -446,7 +446,10 @@ def timed(ctx, step_fn, steps, warmup):
     ctx.barrier()
     wall = time.perf_counter() - w0
     launches = int(_lib.lib.b2ode_launch_count()) - l0 + extra_launches
-    ms = sum(a.elapsed_time(b) for a, b in ev)
+    per_step = [a.elapsed_time(b) for a, b in ev]
+    if os.environ.get("B2ODE_BENCH_DEBUG"):
+        sys.stderr.write("rank %d per-step ms: %s\n" % (ctx.rank, " ".join("%.3f" % v for v in per_step)))
+    ms = sum(per_step)
     ms, (work, launches) = ctx.reduce(ms, (work, launches))
     return dict(value=work / (ms * 1e-3), ms_per_step=ms / steps, launches=int(launches), wall=wall)
 

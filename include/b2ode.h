@@ -211,10 +211,27 @@ size_t b2ode_fused_workspace_bytes(int64_t n_trajectories);
 /* Largest per-device batch b2ode_fused_solve keeps co-resident for this tableau / dtype / right-hand side on the
  * current device (< 0: error).  Asked before launching so that all shards of a shared-step group take the same path. */
 int64_t b2ode_fused_capacity(const b2ode_adaptive_desc *desc, int rhs_kind);
-int b2ode_fused_solve(const b2ode_adaptive_desc *desc, int rhs_kind, const double *rhs_params, int n_rhs_params,
-                      const void *rhs_data, double time_sign, const void *y0, void *out, const double *t_out, int n_out, double t_start,
-                      double first_step, void *state, void *workspace, size_t workspace_bytes, int rank, int nranks,
-                      void *const *mailboxes, int64_t n_traj_global, void *cuda_stream);
+/* Everything b2ode_fused_solve needs besides the tableau / tolerances of `b2ode_adaptive_desc`. */
+typedef struct b2ode_fused_desc {
+    int32_t rhs_kind;                   /* B2ODE_RHS_*                                                            */
+    int32_t n_rhs_params;
+    double rhs_params[8];
+    const void *rhs_data;               /* staged weights (B2ODE_RHS_CUBIC_MLP), else NULL                        */
+    double time_sign;                   /* -1 integrates the reversed system of tfdiffeq/misc.py:318-321          */
+    const void *y0;                     /* (B, D) initial state                                                   */
+    void *out;                          /* (n_out, B, D) solution slab                                            */
+    const double *t_out;                /* n_out output times (device memory, float64, increasing)                */
+    int32_t n_out;
+    double t_start, first_step;         /* first_step NaN -> _select_initial_step (misc.py:183-247)               */
+    void *state;                        /* receives the final b2ode_state                                         */
+    void *workspace;                    /* b2ode_fused_workspace_bytes(B) bytes, 16-byte aligned                  */
+    size_t workspace_bytes;
+    int32_t rank, nranks;               /* shared-step group (nranks <= 1: none)                                  */
+    void *const *mailboxes;             /* nranks mailbox addresses in this process (b2ode_mailbox_create/open)   */
+    int64_t n_traj_rank[B2ODE_MAXPEERS];/* trajectories of every rank: each rank derives every rank's kernel grid */
+    void *cuda_stream;
+} b2ode_fused_desc;
+int b2ode_fused_solve(const b2ode_adaptive_desc *desc, const b2ode_fused_desc *fused);
 
 /* Fixed-grid methods (0 euler, 1 midpoint, 2 heun, 3 rk4 3/8 rule) with a built-in right-hand side: replaces the
  * whole of FixedGridODESolver.integrate (tfdiffeq/solvers.py:82-104); no reductions, one launch.  The host

@@ -51,6 +51,37 @@ def _worker(rank, world, port, q):
     assert s_full["fused_rhs"] and s_part["fused_rhs"]
     res["fused_dopri5"] = (float((part - full[:, lo:hi]).abs().max()), s_full["n_accepted"], s_full["n_rejected"],
                            s_part["n_accepted"], s_part["n_rejected"])
+    # sharded odeint_adjoint: y / adj_y sharded like the batch, adj_t / adj_params replicated (all-reduced derivatives);
+    # the returned parameter gradient is the gradient of the WHOLE batch's loss on every rank
+    import torch.nn as nn
+
+    class Net(nn.Module):
+        def __init__(self):
+            super().__init__()
+            g = torch.Generator().manual_seed(3)
+            self.W1 = nn.Parameter(0.5 * torch.randn(3, 8, generator=g, dtype=torch.float64))
+            self.W2 = nn.Parameter(0.5 * torch.randn(8, 3, generator=g, dtype=torch.float64))
+
+        def forward(self, t, y):
+            return torch.tanh(y @ self.W1) @ self.W2 - 0.1 * y
+    net = Net().to(dev)
+    ya = torch.tensor(y0[:1001], device=dev)
+    ta = torch.tensor([0.0, 0.5, 1.0], dtype=torch.float64)
+    kwa = dict(rtol=1e-8, atol=1e-10, method="dopri5")
+    yw = ya.clone().requires_grad_(True)
+    out = tfd.odeint_adjoint(net, yw, ta, **kwa)
+    (out[-1] ** 2).sum().backward()
+    g_full = torch.cat([p.grad.reshape(-1) for p in net.parameters()]).clone()
+    gy_full = yw.grad.clone()
+    for p_ in net.parameters():
+        p_.grad = None
+    lo2, hi2 = shard_bounds(ya.shape[0], world, rank)
+    ys = ya[lo2:hi2].clone().requires_grad_(True)
+    out = tfd.odeint_adjoint(net, ys, ta, options={"shared_step_group": group}, **kwa)
+    (out[-1] ** 2).sum().backward()
+    g_part = torch.cat([p.grad.reshape(-1) for p in net.parameters()])
+    res["adjoint_param_grad"] = (float((g_part - g_full).abs().max() / g_full.abs().max()), 0, 0, 0, 0)
+    res["adjoint_input_grad"] = (float((ys.grad - gy_full[lo2:hi2]).abs().max() / gy_full.abs().max()), 0, 0, 0, 0)
     group.close()
     q.put((rank, res))
     dist.destroy_process_group()

@@ -124,10 +124,20 @@ class SharedStepGroup(object):
         return self._sum_cached("count", (n,))[0]
 
     def agree_fused(self, n_traj, fits):
-        """(group-wide trajectory count, every shard fits the persistent fused kernel): all shards must take the same
-        path, because the fused kernel and the generic kernels use different exchange protocols."""
-        n_glob, unfit = self._sum_cached("fused", (n_traj, 0 if fits else 1))
-        return n_glob, unfit == 0
+        """(trajectories of every rank, every shard fits the persistent fused kernel): all shards must take the same path
+        -- the fused kernel and the generic kernels use different exchange protocols -- and each rank derives every
+        other rank's kernel grid from its shard size.  One all-gather per distinct local (n_traj, fits), cached."""
+        key = ("fused", int(n_traj), bool(fits))
+        hit = self._sums.get(key)
+        if hit is None:
+            v = torch.tensor([int(n_traj), 1 if fits else 0], dtype=torch.int64)
+            if dist.get_backend(self.group) == "nccl":
+                v = v.to(self.device)
+            out = [torch.empty_like(v) for _ in range(self.world)]
+            dist.all_gather(out, v, group=self.group)
+            rows = [o.cpu().tolist() for o in out]
+            hit = self._sums[key] = ([int(r[0]) for r in rows], all(int(r[1]) == 1 for r in rows))
+        return hit
 
     def close(self):
         lib = _lib.lib

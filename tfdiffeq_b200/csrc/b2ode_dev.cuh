@@ -211,14 +211,22 @@ struct MailSlot {
     unsigned long long seq;
     unsigned long long pad[7];
 };
+constexpr int kMaxFusedBlocks = 320;     // blocks of one rank's persistent fused kernel (148 SMs x 2 blocks, rounded up)
 struct Mailbox {
     MailSlot slot[2][B2ODE_MAXPEERS];
     unsigned long long local_seq;   // exchanges completed by the owning rank; persists across solves
-    unsigned long long ll_seq;      // same, for the low-latency protocol of the persistent fused kernel
+    unsigned long long ll_seq;      // exchanges of the persistent fused kernel so far; persists across solves
     unsigned long long pad[6];
-    // low-latency slots (the protocol of NCCL's "LL": every 8-byte word = {32 data bits, 32-bit sequence flag},
-    // so a word is valid as soon as its flag matches -- no fence, no separate flag store): 3 doubles = 6 words
-    unsigned long long ll[2][B2ODE_MAXPEERS][8];
+    // ---- receive area of the persistent fused kernel (b2ode_fused.cu): every block of every rank writes its 16-byte
+    // tagged partial into fused_part[parity][source rank][block] of EVERY rank's mailbox and bumps fused_ctr[source rank]
+    // there (a remote atomic over NVLink) -- one hop, no relay through a leader block
+    unsigned fused_base[B2ODE_MAXPEERS];                 // arrivals from source rank s before the current launch (local bookkeeping)
+    unsigned long long pad2[4];
+    struct alignas(128) Ctr {
+        unsigned v;
+        unsigned pad[31];
+    } fused_ctr[B2ODE_MAXPEERS];                          // one 128-byte line per source rank
+    unsigned long long fused_part[2][B2ODE_MAXPEERS][kMaxFusedBlocks][2];
 };
 
 struct CommParams {
@@ -226,6 +234,7 @@ struct CommParams {
     int nranks;  // 0 or 1: no exchange
     unsigned repl_mask;   // bit s: segment s is replicated (bit-identical on every rank): its totals are NOT combined
     Mailbox *box[B2ODE_MAXPEERS];
+    int grid_of[B2ODE_MAXPEERS];   // blocks of rank r's persistent fused kernel (fused path only)
 };
 
 __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {

@@ -117,8 +117,13 @@ struct RhsCubicMLP {
 // ------------------------------------------------------------------------------------------------
 struct FusedParams {
     b2ode_state *st;
-    unsigned long long *part2;   // [2][gridDim.x][4] u64: block partials as 4 tagged words, double buffered by exchange parity
-    unsigned *ctr;               // monotonically increasing arrival counter (zeroed by the host before the launch)
+    // exchange plumbing (see control_allreduce).  Without a shared-step group: one "rank" whose receive area is the
+    // caller's workspace.  With a group: the receive areas live in the peer-mapped mailboxes.
+    int xnranks, xrank;
+    int xpeers, xstride;                          // dimensions of the partial arrays: [2][xpeers][xstride][2]
+    int xgrid[B2ODE_MAXPEERS];                    // grid size of every rank's kernel
+    unsigned *xctr[B2ODE_MAXPEERS];               // rank r's counters (32 unsigned = 128 bytes apart, one per source rank)
+    unsigned long long *xpart[B2ODE_MAXPEERS];    // rank r's partial arrays
     const void *y0;
     void *out;
     long long n_traj;       // trajectories on this rank
@@ -237,110 +242,108 @@ __device__ __forceinline__ void named_sync(int id, int count) { asm volatile("ba
 constexpr int kGatherPerLane = 5;        // 160 blocks gathered with every poll in flight (148 SMs x 1 block)
 constexpr int kBarPartials = 1, kBarDecision = 2, kBarRows = 3, kBarRowsReady = 4;
 
+// 16-byte message: {a | tag, b | tag}.  The 4-bit tag (exchange number mod 16) replaces the four lowest mantissa bits of
+// both words (2^-48 relative: below the rounding noise of the sums it carries) so that ONE 16-byte load both fetches and
+// validates a partial; the flag rides in the sign bit of `a` (a sum of squares; a NaN is made canonical first).  A buffer
+// is reused every second exchange, so a stale message always carries a different tag.
+__device__ __forceinline__ void pay_pack16(const Pay &x, unsigned seq, unsigned long long &w0, unsigned long long &w1) {
+    unsigned long long ab = (unsigned long long)__double_as_longlong(x.a);
+    if (x.a != x.a) ab = 0x7ff8000000000000ull;
+    ab = (ab & 0x7ffffffffffffff0ull) | ((unsigned long long)(x.flag & 1u) << 63) | (unsigned long long)(seq & 15u);
+    w0 = ab;
+    w1 = (x.b & ~0xfull) | (unsigned long long)(seq & 15u);
+}
+__device__ __forceinline__ bool pay_valid16(unsigned long long w0, unsigned long long w1, unsigned seq) {
+    return (unsigned)(w0 & 15ull) == (seq & 15u) && (unsigned)(w1 & 15ull) == (seq & 15u);
+}
+__device__ __forceinline__ Pay pay_unpack16(unsigned long long w0, unsigned long long w1) {
+    Pay r;
+    r.flag = (unsigned)(w0 >> 63);
+    r.a = __longlong_as_double((long long)(w0 & 0x7ffffffffffffff0ull));
+    r.b = w1 & ~0xfull;
+    return r;
+}
+
 // Called by the CONTROL warp (all 32 lanes, convergent) once the compute warps' partials are in sh_part[0 .. ncw).
-// `epoch` counts the exchanges of this launch (1, 2, ...); ll_base is the persistent sequence base of the cross-GPU
-// mailbox.  Returns the group-wide totals in every lane.
+// `epoch` counts the exchanges of this launch (1, 2, ...).  Returns the group-wide totals in every lane of every block of
+// every rank, bit-identical everywhere.
 //
-// What the microbenchmark (scripts/micro/grid_barrier.cu, profiles/r02_fused_exchange_ab.md) showed on B200: a gpu-scope
-// STRONG load (ld.relaxed/acquire.gpu, ld.volatile, atomic read) costs 500-700 cycles and the strong loads of one warp do
-// not overlap -- a flag protocol that polls k words per message pays k round trips per poll, and a leader that gathers
-// 147 messages with 5 polls per lane pays ~10 serialised round trips (7.3k cycles per all-reduce, 9.2k with 4 loads per
-// poll, 13.4k two-level), against 1.9k for one atomic arrival counter + one acquire poll.  So: partials are published with
-// ordinary stores, ONE red.release.gpu on an arrival counter orders them, lane 0 spins on ONE ld.acquire.gpu of that
-// counter, and the partials are then fetched by all lanes with weak L2 loads (ld.global.cg), which pipeline.  Every block
-// reduces the same partials in the same fixed order, so all blocks hold bit-identical totals one hop after the last arrival.
+// What the microbenchmarks showed on B200 (scripts/micro/grid_barrier.cu, nvlink_pingpong.cu; profiles/r02_fused_exchange_ab.md):
+//   * a gpu- or sys-scope STRONG load (ld.relaxed / acquire / volatile, atomic read) costs 500-700 cycles and the strong loads
+//     of one warp do not overlap: a flag protocol that polls k words pays k round trips per poll; a leader gathering 147
+//     messages with 5 polls per lane pays ~10 serialised round trips (7.3k cycles per all-reduce; two-level 13.4k);
+//   * one atomic arrival counter + one polled word: 1.9k; weak ld.global.cg loads pipeline;
+//   * a fence (red.release) in front of the arrival costs a MEMBAR.GPU = the store's round trip;
+//   * one NVLink hop (remote write -> visible to a poll of local memory) is ~2070 cycles whatever the instructions, plus ~520
+//     per extra polled word.
+//   * weak ld.global.cg loads always read the L2 and overlap, but POLLING the data itself with them (no counter) measured
+//     slower than counter + one fetch (3.7k vs 3.5k cycles on one GPU): every retry round is a full L2 round trip.
+// Hence a FLAT, one-hop exchange: every block stores its 16-byte tagged partial into part[parity][my rank][my block] of
+// EVERY rank (its own included; remote ones over NVLink) and bumps that rank's arrival counter for my rank with a RELAXED
+// atomic (no fence: a reader that finds a stale tag re-reads that one partial with strong loads); every block then spins
+// on the arrival counters of its own rank (lane q: source rank q, ONE strong load per poll) and fetches all partials of
+// all ranks from LOCAL memory with weak L2 loads that overlap, reducing them in one fixed (rank, block) order.
 template <int MODE>
-__device__ __forceinline__ Pay control_allreduce(const FusedParams &p, const Pay *sh_part, int ncw, unsigned epoch, unsigned ll_base,
-                                                 int att = -1) {
+__device__ __forceinline__ Pay control_allreduce(const FusedParams &p, const Pay *sh_part, int ncw, unsigned epoch, unsigned seq0,
+                                                 unsigned base_q /* lane q: arrivals from rank q before this launch */, int att = -1) {
     const int lane = threadIdx.x & 31;
     Pay x = (lane < ncw) ? sh_part[lane] : pay_identity<MODE>();
     x = pay_warp_reduce<MODE>(x);                                         // block total, all lanes
     FTRACE_DEP(att, 2, __double_as_longlong(x.a));
-    const unsigned par = epoch & 1u;
-    const int G = (int)gridDim.x;
-    if (G > 1) {
-        // Publish: the partial goes out as 4 tagged words {32 data bits | 32-bit epoch} (two 16-byte stores) followed by a
-        // RELAXED arrival on the counter -- no fence on the critical path (red.release costs a MEMBAR.GPU that waits for the
-        // store's round trip).  A reader that finds a stale tag (the arrival overtook the data) re-reads that partial with
-        // strong loads; in practice the data is there.
-        unsigned long long *slots = p.part2 + (size_t)par * G * 4;
-        if (lane == 0) {
-            unsigned long long w[4];
-            pay_pack(x, epoch, w);
-            unsigned long long *mine = slots + (size_t)blockIdx.x * 4;
-            asm volatile("st.global.v2.u64 [%0], {%1, %2};" ::"l"(mine), "l"(w[0]), "l"(w[1]) : "memory");
-            asm volatile("st.global.v2.u64 [%0], {%1, %2};" ::"l"(mine + 2), "l"(w[2]), "l"(w[3]) : "memory");
-            asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(p.ctr) : "memory");
-            const unsigned target = epoch * (unsigned)G;
-            unsigned v;
-            do {
-                asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p.ctr) : "memory");
-            } while ((int)(v - target) < 0);
-        }
-        __syncwarp();
-        FTRACE(att, 3);
-        // weak .cg loads bypass L1 and overlap (strong loads of one warp are serialised, ~600 cycles each)
-        unsigned long long gw[kGatherPerLane][4];
+    const int nranks = p.xnranks, rank = p.xrank;
+    if (nranks == 1 && gridDim.x == 1) return x;
+    // buffer parity follows the PERSISTENT sequence number, so the alternation continues across launches: a rank that has
+    // already started the next solve cannot overwrite a partial a slower rank has not read yet
+    const unsigned seq = seq0 + epoch, par = seq & 1u;
+    unsigned long long w0, w1;
+    pay_pack16(x, seq, w0, w1);
+    if (lane < nranks) {                                                  // lane q publishes to rank q
+        unsigned long long *dst = p.xpart[lane] + (((size_t)par * p.xpeers + rank) * p.xstride + blockIdx.x) * 2;
+        asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(dst), "l"(w0), "l"(w1) : "memory");
+        asm volatile("red.relaxed.sys.global.add.u32 [%0], 1;" ::"l"(p.xctr[lane] + 32 * rank) : "memory");
+    }
+    // arrivals of source rank q at MY counters: lane q polls one word
+    if (lane < nranks) {
+        const unsigned target = base_q + epoch * (unsigned)p.xgrid[lane];
+        const unsigned *c = p.xctr[rank] + 32 * lane;
+        unsigned v;
+        do {
+            asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(c) : "memory");
+        } while ((int)(v - target) < 0);
+    }
+    __syncwarp();
+    FTRACE(att, 3);
+    // every partial of every rank now sits in local memory: weak .cg loads (they overlap), fixed (rank, block) order
+    const unsigned long long *mine = p.xpart[rank] + (size_t)par * p.xpeers * p.xstride * 2;
+    Pay acc = pay_identity<MODE>();
+    for (int s = 0; s < nranks; ++s) {
+        const unsigned long long *src = mine + (size_t)s * p.xstride * 2;
+        const int G = p.xgrid[s];
+        unsigned long long g0[kGatherPerLane], g1[kGatherPerLane];
 #pragma unroll
         for (int q = 0; q < kGatherPerLane; ++q) {
             const int b = lane + 32 * q;
-            const unsigned long long *src = slots + (size_t)(b < G ? b : 0) * 4;
-            asm volatile("ld.global.cg.v2.u64 {%0, %1}, [%2];" : "=l"(gw[q][0]), "=l"(gw[q][1]) : "l"(src) : "memory");
-            asm volatile("ld.global.cg.v2.u64 {%0, %1}, [%2];" : "=l"(gw[q][2]), "=l"(gw[q][3]) : "l"(src + 2) : "memory");
+            const unsigned long long *a = src + (size_t)(b < G ? b : 0) * 2;
+            asm volatile("ld.global.cg.v2.u64 {%0, %1}, [%2];" : "=l"(g0[q]), "=l"(g1[q]) : "l"(a) : "memory");
         }
-        Pay acc = pay_identity<MODE>();
 #pragma unroll
         for (int q = 0; q < kGatherPerLane; ++q) {
             const int b = lane + 32 * q;
             if (b < G) {
-                if ((unsigned)(gw[q][0] >> 32) != epoch || (unsigned)(gw[q][1] >> 32) != epoch ||
-                    (unsigned)(gw[q][2] >> 32) != epoch || (unsigned)(gw[q][3] >> 32) != epoch) {
-                    const Pay v = ll_wait4<false>(slots + (size_t)b * 4, epoch);          // rare: data behind its arrival
-                    acc = pay_combine<MODE>(acc, v);
-                } else {
-                    acc = pay_combine<MODE>(acc, pay_unpack(gw[q]));                       // fixed order -> deterministic
-                }
+                while (!pay_valid16(g0[q], g1[q], seq))                   // rare: the arrival overtook the data
+                    asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(g0[q]), "=l"(g1[q]) : "l"(src + (size_t)b * 2) : "memory");
+                acc = pay_combine<MODE>(acc, pay_unpack16(g0[q], g1[q]));
             }
         }
-        for (int b = lane + 32 * kGatherPerLane; b < G; b += 32)                            // grids beyond 32 * kGatherPerLane blocks
-            acc = pay_combine<MODE>(acc, ll_wait4<false>(slots + (size_t)b * 4, epoch));
-        x = pay_warp_reduce<MODE>(acc);                                   // this GPU's total, all lanes, all blocks alike
+        for (int b = lane + 32 * kGatherPerLane; b < G; b += 32) {         // grids beyond 32 * kGatherPerLane blocks
+            unsigned long long a0, a1;
+            do {
+                asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(a0), "=l"(a1) : "l"(src + (size_t)b * 2) : "memory");
+            } while (!pay_valid16(a0, a1, seq));
+            acc = pay_combine<MODE>(acc, pay_unpack16(a0, a1));
+        }
     }
-    if (p.comm.nranks <= 1) return x;
-    // ---- shared-step group: block 0 pushes this GPU's total into every rank's mailbox over NVLink (4 words
-    // {32 data bits | 32-bit sequence}: valid the moment the sequence matches, no fence); EVERY block polls its own
-    // rank's mailbox, lane q waiting for rank q with ONE strong load per poll (the second half first; the first half
-    // once that is in), and the ranks are combined in rank order -> bit-identical totals on all GPUs
-    const unsigned seq = ll_base + epoch;
-    if (blockIdx.x == 0 && lane < p.comm.nranks) {
-        unsigned long long w[4];
-        pay_pack(x, seq, w);
-        ll_store4<true>(p.comm.box[lane]->ll[par][p.comm.rank], w);      // own mailbox included
-    }
-    Pay mine = pay_identity<MODE>();
-    if (lane < p.comm.nranks) {
-        const unsigned long long *src = p.comm.box[p.comm.rank]->ll[par][lane];
-        unsigned long long w[4];
-        do {
-            asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(w[2]), "=l"(w[3]) : "l"(src + 2) : "memory");
-        } while ((unsigned)(w[2] >> 32) != seq || (unsigned)(w[3] >> 32) != seq);
-        do {
-            asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(w[0]), "=l"(w[1]) : "l"(src) : "memory");
-        } while ((unsigned)(w[0] >> 32) != seq || (unsigned)(w[1] >> 32) != seq);
-        mine = pay_unpack(w);
-    }
-    Pay tot;
-    tot.a = __shfl_sync(0xffffffffu, mine.a, 0);
-    tot.b = __shfl_sync(0xffffffffu, mine.b, 0);
-    tot.flag = __shfl_sync(0xffffffffu, mine.flag, 0);
-    for (int q = 1; q < p.comm.nranks; ++q) {
-        Pay v;
-        v.a = __shfl_sync(0xffffffffu, mine.a, q);
-        v.b = __shfl_sync(0xffffffffu, mine.b, q);
-        v.flag = __shfl_sync(0xffffffffu, mine.flag, q);
-        tot = pay_combine<MODE>(tot, v);
-    }
-    return tot;
+    return pay_warp_reduce<MODE>(acc);
 }
 
 // The controller of the persistent kernel (one segment, the reference's controller: misc.py:250-287), written for the
@@ -401,7 +404,10 @@ __global__ void __launch_bounds__(MAXT) k_fused_adaptive(const __grid_constant__
     const int ncw = (nthreads >> 5) - 1;                 // compute warps
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool is_control = warp == ncw;
-    const unsigned ll_base = (p.comm.nranks > 1) ? (unsigned)p.comm.box[p.comm.rank]->ll_seq : 0u;
+    // persistent sequence / arrival bases of the cross-GPU receive area (they survive across solves in the mailbox)
+    const bool grouped = p.comm.nranks > 1;
+    const unsigned ll_base = grouped ? (unsigned)p.comm.box[p.comm.rank]->ll_seq : 0u;
+    const unsigned base_q = (grouped && lane < p.comm.nranks) ? p.comm.box[p.comm.rank]->fused_base[lane] : 0u;
     if (RHS::kSmem > 1) {
         const int nw = (int)p.rhs[0] * 5 + 2;
         for (int q = threadIdx.x; q < nw && q < RHS::kSmem; q += nthreads) sw[q] = ((const T *)p.rhs_data)[q];
@@ -420,7 +426,7 @@ __global__ void __launch_bounds__(MAXT) k_fused_adaptive(const __grid_constant__
         } else {
             // misc.py:226-247 with the two reductions of _select_initial_step
             named_sync(kBarPartials, nthreads);
-            Pay r = control_allreduce<1>(p, sh.part, ncw, ++epoch, ll_base);
+            Pay r = control_allreduce<1>(p, sh.part, ncw, ++epoch, ll_base, base_q);
             if (lane == 0) sh.tot = r;
             named_arrive(kBarDecision, nthreads);
             Partial tot;
@@ -430,7 +436,7 @@ __global__ void __launch_bounds__(MAXT) k_fused_adaptive(const __grid_constant__
             T d1max;
             const T h0 = init_h0<T>(p.c, &tot, 1, &d1max);
             named_sync(kBarPartials, nthreads);
-            r = control_allreduce<1>(p, sh.part, ncw, ++epoch, ll_base);
+            r = control_allreduce<1>(p, sh.part, ncw, ++epoch, ll_base, base_q);
             if (lane == 0) sh.tot = r;
             named_arrive(kBarDecision, nthreads);
             tot.v[0] = r.a;
@@ -456,7 +462,7 @@ __global__ void __launch_bounds__(MAXT) k_fused_adaptive(const __grid_constant__
             if (c2 > cur) named_arrive(kBarRows, nthreads);                    // the previous step's rows have been copied out
             named_sync(kBarPartials, nthreads);                                // the compute warps' partials are in
             FTRACE_DEP(att, 1, sh.part[0].flag);
-            const Pay r = control_allreduce<0>(p, sh.part, ncw, ++epoch, ll_base, att);
+            const Pay r = control_allreduce<0>(p, sh.part, ncw, ++epoch, ll_base, base_q, att);
             FTRACE_DEP(att, 4, __double_as_longlong(r.a));
             Partial tot;
             tot.v[0] = r.a;
@@ -546,7 +552,11 @@ __global__ void __launch_bounds__(MAXT) k_fused_adaptive(const __grid_constant__
             z.cursor = cur;
             z.xseq = p.st->xseq;
             *p.st = z;
-            if (p.comm.nranks > 1) p.comm.box[p.comm.rank]->ll_seq = (unsigned long long)(ll_base + epoch);
+        }
+        if (blockIdx.x == 0 && grouped) {
+            Mailbox *mb = p.comm.box[p.comm.rank];
+            if (lane == 0) mb->ll_seq = (unsigned long long)(ll_base + epoch);
+            if (lane < p.comm.nranks) mb->fused_base[lane] = base_q + epoch * (unsigned)p.xgrid[lane];
         }
         return;
     }
@@ -824,11 +834,34 @@ __global__ void __launch_bounds__(MAXT) k_fused_adaptive(const __grid_constant__
 // host side
 // ================================================================================================
 // Block geometry: NCW compute warps + 1 control warp.  One block per SM when the batch allows it (fewest partials to
-// gather, all 148 SMs busy): NCW = ceil(ceil(n / SMs) / 32), capped by the register budget of the instantiation.
-// `capacity` != null: only report how many trajectories this instantiation can keep co-resident on the current device.
+// gather, all 148 SMs busy): NCW = ceil(ceil(n / SMs) / 32), capped by the register budget of the instantiation; if
+// that does not keep the batch co-resident, the largest block that does (smaller blocks can pack more warps per SM when
+// the register file, not the block size, is the limit).  A pure function of (n, device, instantiation): every rank of a
+// shared-step group computes the same geometry for every other rank's shard.
 template <typename T, typename RHS, int S, int MAXT>
-static int fused_launch(const FusedParams &p, long long n_traj, cudaStream_t st, long long *capacity = nullptr) {
-    void *args[] = {(void *)&p};
+static int fused_geometry(long long n_traj, int nsm, int *ncw_out, int *grid_out) {
+    constexpr int kMaxNcw = MAXT / 32 - 1;
+    long long per_block = (n_traj + nsm - 1) / nsm;
+    int ncw = (int)((per_block + 31) / 32);
+    if (ncw < 1) ncw = 1;
+    if (ncw > kMaxNcw) ncw = kMaxNcw;
+    for (; ncw >= 1; --ncw) {
+        int per_sm = 0;
+        const int grid = (int)((n_traj + (long long)ncw * 32 - 1) / ((long long)ncw * 32));
+        B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused_adaptive<T, RHS, S, MAXT>, 32 * (ncw + 1), 0));
+        if (grid <= per_sm * nsm) {
+            *ncw_out = ncw;
+            *grid_out = grid;
+            return 0;
+        }
+    }
+    return b2_fail(B2ODE_ENOMEM, "batch of %lld trajectories cannot stay co-resident on %d SMs", n_traj, nsm);
+}
+
+// `capacity` != null: only report how many trajectories this instantiation can keep co-resident on the current device.
+// n_traj_rank: trajectories of every rank of the group (null / ignored without a group).
+template <typename T, typename RHS, int S, int MAXT>
+static int fused_launch(const FusedParams &p_in, long long n_traj, cudaStream_t st, long long *capacity, const int64_t *n_traj_rank) {
     int dev = 0, coop = 0, nsm = 0, per_sm = 0;
     B2_CUDA(cudaGetDevice(&dev));
     B2_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
@@ -845,47 +878,54 @@ static int fused_launch(const FusedParams &p, long long n_traj, cudaStream_t st,
         return 0;
     }
     if (!coop) return b2_fail(B2ODE_ESTATE, "device does not support cooperative launch");
-    long long per_block = (n_traj + nsm - 1) / nsm;
-    int ncw = (int)((per_block + 31) / 32);
-    if (ncw < 1) ncw = 1;
-    if (ncw > kMaxNcw) ncw = kMaxNcw;
-    int threads = 0, grid = 0;
-    // the largest block that keeps the whole batch co-resident (smaller blocks can pack more warps per SM when the
-    // register file, not the block size, is the limit)
-    for (; ncw >= 1; --ncw) {
-        threads = 32 * (ncw + 1);
-        grid = (int)((n_traj + (long long)ncw * 32 - 1) / ((long long)ncw * 32));
-        B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused_adaptive<T, RHS, S, MAXT>, threads, 0));
-        if (grid <= per_sm * nsm) break;
+    FusedParams p = p_in;
+    int ncw = 0, grid = 0;
+    {
+        const int rc = fused_geometry<T, RHS, S, MAXT>(n_traj, nsm, &ncw, &grid);
+        if (rc) return rc;
     }
-    if (ncw < 1)
-        return b2_fail(B2ODE_ENOMEM, "batch of %lld trajectories cannot stay co-resident on %d SMs", n_traj, nsm);
+    if (p.comm.nranks > 1) {
+        for (int r = 0; r < p.comm.nranks; ++r) {
+            int ncw_r = 0, grid_r = 0;
+            const int rc = fused_geometry<T, RHS, S, MAXT>(n_traj_rank[r], nsm, &ncw_r, &grid_r);
+            if (rc) return rc;
+            if (grid_r > kMaxFusedBlocks)
+                return b2_fail(B2ODE_ENOMEM, "rank %d needs %d blocks, the group mailbox holds %d", r, grid_r, kMaxFusedBlocks);
+            p.xgrid[r] = grid_r;
+        }
+        if (p.xgrid[p.comm.rank] != grid) return b2_fail(B2ODE_ESTATE, "inconsistent shard size for this rank");
+    } else {
+        p.xgrid[0] = grid;
+        p.xstride = grid;
+    }
+    void *args[] = {(void *)&p};
     const int slot = b2_timing_begin(6 /* B2_FAM_FUSED */, st);
-    B2_CUDA(cudaLaunchCooperativeKernel((const void *)k_fused_adaptive<T, RHS, S, MAXT>, dim3(grid), dim3(threads), args, 0, st));
+    B2_CUDA(cudaLaunchCooperativeKernel((const void *)k_fused_adaptive<T, RHS, S, MAXT>, dim3(grid), dim3(32 * (ncw + 1)), args, 0, st));
     b2_timing_end(6, slot, st);
     b2_count_launch();
     return 0;
 }
 
 template <typename T, typename RHS>
-static int fused_dispatch_s(const FusedParams &p, int n_k, long long n_traj, cudaStream_t st, long long *capacity) {
+static int fused_dispatch_s(const FusedParams &p, int n_k, long long n_traj, cudaStream_t st, long long *capacity,
+                            const int64_t *ntr) {
     // up to 512 threads per block (<= 128 registers per thread) for the tableaus whose k-set fits; 256 otherwise
     switch (n_k) {
-        case 2: return fused_launch<T, RHS, 2, 512>(p, n_traj, st, capacity);
-        case 4: return fused_launch<T, RHS, 4, 512>(p, n_traj, st, capacity);
-        case 7: return fused_launch<T, RHS, 7, 512>(p, n_traj, st, capacity);
-        case 14: return fused_launch<T, RHS, 14, 256>(p, n_traj, st, capacity);
+        case 2: return fused_launch<T, RHS, 2, 512>(p, n_traj, st, capacity, ntr);
+        case 4: return fused_launch<T, RHS, 4, 512>(p, n_traj, st, capacity, ntr);
+        case 7: return fused_launch<T, RHS, 7, 512>(p, n_traj, st, capacity, ntr);
+        case 14: return fused_launch<T, RHS, 14, 256>(p, n_traj, st, capacity, ntr);
     }
     return b2_fail(B2ODE_EINVAL, "fused solve supports tableaus with 2, 4, 7 or 14 k's (got %d)", n_k);
 }
 
 template <typename T>
 static int fused_dispatch_rhs(const FusedParams &p, int rhs_kind, int n_k, long long n_traj, cudaStream_t st,
-                              long long *capacity = nullptr) {
+                              long long *capacity = nullptr, const int64_t *ntr = nullptr) {
     switch (rhs_kind) {
-        case B2ODE_RHS_LORENZ: return fused_dispatch_s<T, RhsLorenz<T>>(p, n_k, n_traj, st, capacity);
-        case B2ODE_RHS_LOTKA_VOLTERRA: return fused_dispatch_s<T, RhsLotkaVolterra<T>>(p, n_k, n_traj, st, capacity);
-        case B2ODE_RHS_CUBIC_MLP: return fused_dispatch_s<T, RhsCubicMLP<T>>(p, n_k, n_traj, st, capacity);
+        case B2ODE_RHS_LORENZ: return fused_dispatch_s<T, RhsLorenz<T>>(p, n_k, n_traj, st, capacity, ntr);
+        case B2ODE_RHS_LOTKA_VOLTERRA: return fused_dispatch_s<T, RhsLotkaVolterra<T>>(p, n_k, n_traj, st, capacity, ntr);
+        case B2ODE_RHS_CUBIC_MLP: return fused_dispatch_s<T, RhsCubicMLP<T>>(p, n_k, n_traj, st, capacity, ntr);
     }
     return b2_fail(B2ODE_EINVAL, "unknown built-in right-hand side %d", rhs_kind);
 }
@@ -919,44 +959,40 @@ static int rhs_check(int kind, const double *prm, int n_prm, const void *rhs_dat
 
 extern "C" size_t b2ode_fused_workspace_bytes(int64_t n_traj) {
     const long long grid_max = (n_traj + 31) / 32;       // the smallest block has one compute warp
-    // [arrival counter, 128 B][partials 2 x grid x 32 B]
-    return (size_t)128 + (size_t)grid_max * 64;
+    // [arrival counter, 128 B][partials 2 x grid x 16 B] -- used when no shared-step group is attached
+    return (size_t)128 + (size_t)grid_max * 32;
 }
 
-extern "C" int b2ode_fused_solve(const b2ode_adaptive_desc *desc, int rhs_kind, const double *rhs_params, int n_rhs_params,
-                                 const void *rhs_data, double time_sign, const void *y0, void *out, const double *t_out, int n_out, double t_start,
-                                 double first_step, void *state, void *workspace, size_t workspace_bytes, int rank, int nranks,
-                                 void *const *mailboxes, int64_t n_traj_global, void *cuda_stream) {
-    if (!desc || !y0 || !out || !t_out || !state || !workspace) return b2_fail(B2ODE_EINVAL, "null argument");
+extern "C" int b2ode_fused_solve(const b2ode_adaptive_desc *desc, const b2ode_fused_desc *f) {
+    if (!desc || !f) return b2_fail(B2ODE_EINVAL, "null argument");
+    if (!f->y0 || !f->out || !f->t_out || !f->state || !f->workspace) return b2_fail(B2ODE_EINVAL, "null buffer");
+    const int rhs_kind = f->rhs_kind;
     const int D = rhs_dim(rhs_kind);
     if (D < 0) return b2_fail(B2ODE_EINVAL, "unknown built-in right-hand side %d", rhs_kind);
     if (desc->nseg != 1 || desc->seg_len[0] % D != 0) return b2_fail(B2ODE_EINVAL, "state must be one (B, %d) tensor", D);
     if (desc->dense_kind != 0) return b2_fail(B2ODE_EINVAL, "fused solve supports the quartic dense output only");
-    if (n_rhs_params < 0 || n_rhs_params > 8 || (n_rhs_params && !rhs_params)) return b2_fail(B2ODE_EINVAL, "bad rhs params");
+    if (f->n_rhs_params < 0 || f->n_rhs_params > 8) return b2_fail(B2ODE_EINVAL, "bad rhs params");
     const long long n_traj = desc->seg_len[0] / D;
     if (n_traj < 1) return b2_fail(B2ODE_EINVAL, "empty batch");
-    if (workspace_bytes < b2ode_fused_workspace_bytes(n_traj)) return b2_fail(B2ODE_ENOMEM, "workspace too small");
-    cudaStream_t st = (cudaStream_t)cuda_stream;
-    // workspace layout: [arrival counter | pad to 128 B][partials 2 x grid x 16 B]; the counter starts at 0 every launch
-    unsigned char *w = (unsigned char *)workspace;
+    if (f->workspace_bytes < b2ode_fused_workspace_bytes(n_traj)) return b2_fail(B2ODE_ENOMEM, "workspace too small");
+    cudaStream_t st = (cudaStream_t)f->cuda_stream;
+    unsigned char *w = (unsigned char *)f->workspace;
     if ((uintptr_t)w & 15u) return b2_fail(B2ODE_EINVAL, "workspace must be 16-byte aligned");
-    B2_CUDA(cudaMemsetAsync(w, 0, b2ode_fused_workspace_bytes(n_traj), st));      // epoch tags start at 1
+    const int nranks = f->nranks > 1 ? f->nranks : 1;
     FusedParams p;
     memset(&p, 0, sizeof(p));
-    p.st = (b2ode_state *)state;
-    p.ctr = (unsigned *)w;
-    p.part2 = (unsigned long long *)(w + 128);
-    p.y0 = y0;
-    p.out = out;
+    p.st = (b2ode_state *)f->state;
+    p.y0 = f->y0;
+    p.out = f->out;
     p.n_traj = n_traj;
-    p.have_first_step = (first_step == first_step) ? 1 : 0;
-    p.t_start = t_start;
-    p.first_step = first_step;
-    p.time_sign = time_sign;
-    for (int i = 0; i < n_rhs_params; ++i) p.rhs[i] = rhs_params[i];
-    p.rhs_data = rhs_data;
+    p.have_first_step = (f->first_step == f->first_step) ? 1 : 0;
+    p.t_start = f->t_start;
+    p.first_step = f->first_step;
+    p.time_sign = f->time_sign;
+    for (int i = 0; i < f->n_rhs_params; ++i) p.rhs[i] = f->rhs_params[i];
+    p.rhs_data = f->rhs_data;
     {
-        const int rc_ = rhs_check(rhs_kind, rhs_params, n_rhs_params, rhs_data);
+        const int rc_ = rhs_check(rhs_kind, f->rhs_params, f->n_rhs_params, f->rhs_data);
         if (rc_) return rc_;
     }
     const int nk = desc->n_k;
@@ -983,18 +1019,42 @@ extern "C" int b2ode_fused_solve(const b2ode_adaptive_desc *desc, int rhs_kind, 
     p.c.inv_dfactor = 1.0 / desc->dfactor;
     p.c.max_num_steps = desc->max_num_steps;
     p.c.init_order = desc->init_order;
-    p.c.n_out = n_out;
-    p.c.t_out = t_out;
+    p.c.n_out = f->n_out;
+    p.c.t_out = f->t_out;
     p.c.tstage = nullptr;
-    p.c.n_global[0] = (nranks > 1 ? n_traj_global : n_traj) * D;
-    p.comm.rank = rank;
-    p.comm.nranks = nranks > 1 ? nranks : 0;
+    long long n_glob = n_traj;
+    p.comm.rank = 0;
+    p.comm.nranks = 0;
+    p.xnranks = 1;
+    p.xrank = 0;
     if (nranks > 1) {
-        if (!mailboxes || nranks > B2ODE_MAXPEERS) return b2_fail(B2ODE_EINVAL, "bad mailboxes");
-        for (int r = 0; r < nranks; ++r) p.comm.box[r] = (Mailbox *)mailboxes[r];
+        if (!f->mailboxes || nranks > B2ODE_MAXPEERS || f->rank < 0 || f->rank >= nranks) return b2_fail(B2ODE_EINVAL, "bad group arguments");
+        n_glob = 0;
+        for (int r = 0; r < nranks; ++r) {
+            if (!f->mailboxes[r] || f->n_traj_rank[r] < 1) return b2_fail(B2ODE_EINVAL, "bad mailbox / shard size of rank %d", r);
+            n_glob += f->n_traj_rank[r];
+            Mailbox *mb = (Mailbox *)f->mailboxes[r];
+            p.comm.box[r] = mb;
+            p.xctr[r] = &mb->fused_ctr[0].v;
+            p.xpart[r] = &mb->fused_part[0][0][0][0];
+        }
+        if (f->n_traj_rank[f->rank] != n_traj) return b2_fail(B2ODE_EINVAL, "n_traj_rank[rank] does not match the state");
+        p.comm.rank = f->rank;
+        p.comm.nranks = nranks;
+        p.xnranks = nranks;
+        p.xrank = f->rank;
+        p.xpeers = B2ODE_MAXPEERS;
+        p.xstride = kMaxFusedBlocks;
+    } else {
+        // receive area = the caller's workspace: [arrival counter | pad to 128 B][partials 2 x grid x 16 B], zeroed per launch
+        B2_CUDA(cudaMemsetAsync(w, 0, b2ode_fused_workspace_bytes(n_traj), st));
+        p.xctr[0] = (unsigned *)w;
+        p.xpart[0] = (unsigned long long *)(w + 128);
+        p.xpeers = 1;          // xstride / xgrid[0] = the grid, filled in by the launcher
     }
-    if (desc->dtype == B2ODE_F64) return fused_dispatch_rhs<double>(p, rhs_kind, nk, n_traj, st);
-    if (desc->dtype == B2ODE_F32) return fused_dispatch_rhs<float>(p, rhs_kind, nk, n_traj, st);
+    p.c.n_global[0] = n_glob * D;
+    if (desc->dtype == B2ODE_F64) return fused_dispatch_rhs<double>(p, rhs_kind, nk, n_traj, st, nullptr, f->n_traj_rank);
+    if (desc->dtype == B2ODE_F32) return fused_dispatch_rhs<float>(p, rhs_kind, nk, n_traj, st, nullptr, f->n_traj_rank);
     return b2_fail(B2ODE_EINVAL, "dtype must be 0 or 1");
 }
 

@@ -253,16 +253,20 @@ class AdaptiveStepsizeODESolver(object):
         workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         desc = self._describe(seg)
         prm = base.rhs_params()
-        prm_arr = (C.c_double * 8)(*(prm + [0.0] * (8 - len(prm))))
         weights = base.rhs_data(dtype, dev)
         first = float("nan") if self.first_step is None else _tf_f64(self.first_step)
-        rank, world, boxes, n_glob = 0, 1, None, n_traj
         fits = int(lib.b2ode_fused_capacity(C.byref(desc), base.kind)) >= n_traj
+        fd = _lib.FusedDesc()
+        fd.rank, fd.nranks = 0, 1
         if self.comm is not None:
-            rank, world, boxes = self.comm.rank, self.comm.world, self.comm._ptrs
             # the shards of a group must take the same path (the fused kernel and the generic kernels speak different
-            # exchange protocols): agree on "every shard fits" and on the group-wide trajectory count in one cached call
-            n_glob, fits = self.comm.agree_fused(n_traj, fits)
+            # exchange protocols) and every rank derives every other rank's kernel grid from its shard size: agree on
+            # "every shard fits" and learn all shard sizes in one cached collective
+            sizes, fits = self.comm.agree_fused(n_traj, fits)
+            fd.rank, fd.nranks = self.comm.rank, self.comm.world
+            fd.mailboxes = C.cast(self.comm._ptrs, C.c_void_p)
+            for r, n_r in enumerate(sizes):
+                fd.n_traj_rank[r] = n_r
         if not fits:
             import warnings
             warnings.warn("tfdiffeq_b200: batch of %d trajectories per GPU exceeds what the persistent fused kernel can keep "
@@ -270,13 +274,16 @@ class AdaptiveStepsizeODESolver(object):
                           "right-hand side)" % n_traj, RuntimeWarning)
             return None
         stream = torch.cuda.current_stream(dev)
-        rc = lib.b2ode_fused_solve(C.byref(desc), base.kind, prm_arr, len(prm),
-                                   C.c_void_p(weights.data_ptr()) if weights is not None else None,
-                                   float(self.func._b2ode_sign),
-                                   C.c_void_p(y0.data_ptr()), C.c_void_p(out.data_ptr()), C.c_void_p(t_dev.data_ptr()),
-                                   n_out, float(t_host[0]), first, C.c_void_p(state_dev.data_ptr()),
-                                   C.c_void_p(workspace.data_ptr()), ws_bytes, rank, world, boxes, n_glob,
-                                   C.c_void_p(stream.cuda_stream))
+        fd.rhs_kind, fd.n_rhs_params = base.kind, len(prm)
+        for k_, v_ in enumerate(prm):
+            fd.rhs_params[k_] = v_
+        fd.rhs_data = weights.data_ptr() if weights is not None else None
+        fd.time_sign = float(self.func._b2ode_sign)
+        fd.y0, fd.out, fd.t_out, fd.n_out = y0.data_ptr(), out.data_ptr(), t_dev.data_ptr(), n_out
+        fd.t_start, fd.first_step = float(t_host[0]), first
+        fd.state, fd.workspace, fd.workspace_bytes = state_dev.data_ptr(), workspace.data_ptr(), ws_bytes
+        fd.cuda_stream = stream.cuda_stream
+        rc = lib.b2ode_fused_solve(C.byref(desc), C.byref(fd))
         check(rc)
         host, hkey = _pinned_acquire(dev)
         try:
