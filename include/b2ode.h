@@ -230,6 +230,10 @@ typedef struct b2ode_fused_desc {
     void *const *mailboxes;             /* nranks mailbox addresses in this process (b2ode_mailbox_create/open)   */
     int64_t n_traj_rank[B2ODE_MAXPEERS];/* trajectories of every rank: each rank derives every rank's kernel grid */
     void *cuda_stream;
+    int32_t *host_mark;                 /* optional: page-locked, device-mapped int.  While the solve runs the kernel keeps
+                                           it at the number of leading rows of `out` that are complete on the device, so
+                                           the caller can stream the solution to the host behind the solve (the value only
+                                           grows; rows [0, *host_mark) may be copied without further synchronisation)      */
 } b2ode_fused_desc;
 int b2ode_fused_solve(const b2ode_adaptive_desc *desc, const b2ode_fused_desc *fused);
 

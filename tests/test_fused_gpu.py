@@ -177,3 +177,31 @@ def test_config3_full_size_fused_mlp_rk4():
     ref = np_ref.odeint(f_np, y0[idx], t, method="rk4")
     got = sol[:, torch.tensor(idx, device=DEV)].cpu().numpy()
     assert max_rel_err(got, ref) <= 1e-3
+
+
+@pytest.mark.parametrize("batch", [300, 65536])
+def test_host_output_streams_the_solution_behind_the_solve(batch):
+    """options={'host_output': pinned}: the solution is delivered into the caller's page-locked buffer; with a built-in
+    right-hand side the device-to-host copies are issued while the persistent kernel is still running, gated by the row
+    watermark the kernel publishes (rows [0, mark) complete on every block).  Values must equal the ordinary result."""
+    import tfdiffeq_b200 as tfd
+    rng = np.random.default_rng(11)
+    y0 = torch.tensor(np.array([1., 1., 1.]) + 0.1 * rng.standard_normal((batch, 3)), device=DEV)
+    t = torch.arange(400, dtype=torch.float64) * 0.01
+    f = tfd.rhs.Lorenz()
+    want = tfd.odeint(f, y0, t, method="dopri5")
+    host = torch.empty((400, batch, 3), dtype=torch.float64).pin_memory()
+    for rep in range(3):
+        host.fill_(float("nan"))
+        got = tfd.odeint(f, y0, t, method="dopri5", options={"host_output": host})
+        assert got.data_ptr() == host.data_ptr() and tfd.last_stats["fused_rhs"]
+        assert torch.equal(got, want.cpu())
+    # generic path and fixed grid: delivered with one copy at the end
+    g = PROBLEMS["lorenz"](backend="torch", device=DEV)
+    host.fill_(float("nan"))
+    got = tfd.odeint(g, y0, t, method="dopri5", options={"host_output": host})
+    assert float((got - want.cpu()).abs().max()) < 1e-9
+    got = tfd.odeint(g, y0, t, method="rk4", options={"host_output": host})
+    assert torch.equal(got, tfd.odeint(g, y0, t, method="rk4").cpu())
+    with pytest.raises(ValueError):
+        tfd.odeint(f, y0, t, method="dopri5", options={"host_output": torch.empty((400, batch, 3), dtype=torch.float64)})

@@ -55,7 +55,7 @@ class FusedDesc(C.Structure):
                 ("time_sign", C.c_double), ("y0", C.c_void_p), ("out", C.c_void_p), ("t_out", C.c_void_p), ("n_out", C.c_int32),
                 ("t_start", C.c_double), ("first_step", C.c_double), ("state", C.c_void_p), ("workspace", C.c_void_p),
                 ("workspace_bytes", C.c_size_t), ("rank", C.c_int32), ("nranks", C.c_int32), ("mailboxes", C.c_void_p),
-                ("n_traj_rank", C.c_int64 * MAXPEERS), ("cuda_stream", C.c_void_p)]
+                ("n_traj_rank", C.c_int64 * MAXPEERS), ("cuda_stream", C.c_void_p), ("host_mark", C.c_void_p)]
 
 
 assert C.sizeof(State) == 256

@@ -24,6 +24,38 @@ import torch.distributed as dist
 from . import _lib
 
 
+def bind_to_gpu_numa(device=None):
+    """Pin the calling process (and therefore the page-locked buffers it allocates from now on: first touch) to the NUMA
+    node the GPU hangs off.  On an 8-GPU box GPUs 4-7 sit on the second socket; a rank whose pinned staging buffers live on
+    the other socket pushes every host<->device byte across the inter-socket link (round 1: end-to-end time per solve went
+    from 34 ms at 1-4 GPUs to 108 ms at 8).  Returns the node number, or None when the topology cannot be read (no
+    /sys entry, container without the PCI tree): the caller carries on unbound."""
+    import os
+    try:
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        props = torch.cuda.get_device_properties(dev)
+        bus = "%04x:%02x:%02x.0" % (getattr(props, "pci_domain_id", 0), props.pci_bus_id, props.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/numa_node" % bus) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                if "-" in part:
+                    lo, hi = part.split("-")
+                    cpus.update(range(int(lo), int(hi) + 1))
+                elif part:
+                    cpus.add(int(part))
+        allowed = os.sched_getaffinity(0) & cpus
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except (OSError, ValueError, AttributeError, RuntimeError):
+        return None
+
+
 def shard_bounds(n, world_size, rank):
     """Contiguous, balanced split of ``n`` items: the first ``n % world_size`` ranks get one extra."""
     base, extra = divmod(n, world_size)

@@ -126,6 +126,11 @@ struct FusedParams {
     unsigned long long *xpart[B2ODE_MAXPEERS];    // rank r's partial arrays
     const void *y0;
     void *out;
+    // optional streaming of the solution to the host: `progress` counts output rows completed over all blocks, `host_mark`
+    // (page-locked host memory, mapped) receives the number of leading rows that are complete on EVERY block, so that the
+    // host can issue device-to-host copies behind the solve (b2ode_fused_desc.host_mark)
+    unsigned *progress;
+    int *host_mark;
     long long n_traj;       // trajectories on this rank
     int have_first_step;
     double t_start, first_step;
@@ -449,6 +454,7 @@ __global__ void __launch_bounds__(MAXT) k_fused_adaptive(const __grid_constant__
             done = 1;
         }
         // bookkeeping for the final state
+        int late_rows = 0;     // host streaming: rows of a long step whose completion is accounted one barrier later
         double m_last = 0.0, t_prev = t_cur, dt_last = 0.0;
         unsigned long long n_acc = 0, n_rej = 0;
         long long nadv = 0;
@@ -461,6 +467,18 @@ __global__ void __launch_bounds__(MAXT) k_fused_adaptive(const __grid_constant__
             while (c2 < n_out && __ldg(t_out + c2) <= t1_acc) ++c2;             // advance(): `while next_t > t1`
             if (c2 > cur) named_arrive(kBarRows, nthreads);                    // the previous step's rows have been copied out
             named_sync(kBarPartials, nthreads);                                // the compute warps' partials are in
+            if (late_rows) {
+                // a long step's extra rows were stored by the compute warps themselves, before this barrier
+                __threadfence();
+                if (lane == 0) {
+                    const unsigned old = atomicAdd(p.progress, (unsigned)late_rows);
+                    if (old + (unsigned)late_rows == (unsigned)(cur - 1) * gridDim.x) {
+                        __threadfence_system();
+                        *(volatile int *)p.host_mark = cur;
+                    }
+                }
+                late_rows = 0;
+            }
             FTRACE_DEP(att, 1, sh.part[0].flag);
             const Pay r = control_allreduce<0>(p, sh.part, ncw, ++epoch, ll_base, base_q, att);
             FTRACE_DEP(att, 4, __double_as_longlong(r.a));
@@ -512,6 +530,21 @@ __global__ void __launch_bounds__(MAXT) k_fused_adaptive(const __grid_constant__
                         for (int e = nv * V + lane; e < nel; e += 32) row[e] = src[e];
                     } else {
                         for (int e = lane; e < nel; e += 32) row[e] = src[e];
+                    }
+                }
+                if (p.host_mark) {
+                    if (c2 - cur > kDenseRows) {
+                        late_rows = c2 - cur;                       // compute warps are still writing rows: account later
+                    } else {
+                        __threadfence();                            // my rows are visible device-wide before the count moves
+                        if (lane == 0) {
+                            const unsigned old = atomicAdd(p.progress, (unsigned)(c2 - cur));
+                            // rows 1 .. c2-1 complete on every block  <=>  the count reached (c2 - 1) * blocks
+                            if (old + (unsigned)(c2 - cur) == (unsigned)(c2 - 1) * gridDim.x) {
+                                __threadfence_system();
+                                *(volatile int *)p.host_mark = c2;
+                            }
+                        }
                     }
                 }
             }
@@ -959,8 +992,8 @@ static int rhs_check(int kind, const double *prm, int n_prm, const void *rhs_dat
 
 extern "C" size_t b2ode_fused_workspace_bytes(int64_t n_traj) {
     const long long grid_max = (n_traj + 31) / 32;       // the smallest block has one compute warp
-    // [arrival counter, 128 B][partials 2 x grid x 16 B] -- used when no shared-step group is attached
-    return (size_t)128 + (size_t)grid_max * 32;
+    // [arrival counter, 128 B][row progress counter, 128 B][partials 2 x grid x 16 B (no shared-step group)]
+    return (size_t)256 + (size_t)grid_max * 32;
 }
 
 extern "C" int b2ode_fused_solve(const b2ode_adaptive_desc *desc, const b2ode_fused_desc *f) {
@@ -981,6 +1014,9 @@ extern "C" int b2ode_fused_solve(const b2ode_adaptive_desc *desc, const b2ode_fu
     const int nranks = f->nranks > 1 ? f->nranks : 1;
     FusedParams p;
     memset(&p, 0, sizeof(p));
+    B2_CUDA(cudaMemsetAsync(w, 0, 256, st));
+    p.progress = (unsigned *)(w + 128);
+    p.host_mark = (int *)f->host_mark;
     p.st = (b2ode_state *)f->state;
     p.y0 = f->y0;
     p.out = f->out;
@@ -1046,10 +1082,10 @@ extern "C" int b2ode_fused_solve(const b2ode_adaptive_desc *desc, const b2ode_fu
         p.xpeers = B2ODE_MAXPEERS;
         p.xstride = kMaxFusedBlocks;
     } else {
-        // receive area = the caller's workspace: [arrival counter | pad to 128 B][partials 2 x grid x 16 B], zeroed per launch
-        B2_CUDA(cudaMemsetAsync(w, 0, b2ode_fused_workspace_bytes(n_traj), st));
+        // receive area = the caller's workspace: [arrival counter][progress][partials 2 x grid x 16 B], zeroed per launch
+        B2_CUDA(cudaMemsetAsync(w + 256, 0, b2ode_fused_workspace_bytes(n_traj) - 256, st));
         p.xctr[0] = (unsigned *)w;
-        p.xpart[0] = (unsigned long long *)(w + 128);
+        p.xpart[0] = (unsigned long long *)(w + 256);
         p.xpeers = 1;          // xstride / xgrid[0] = the grid, filled in by the launcher
     }
     p.c.n_global[0] = n_glob * D;

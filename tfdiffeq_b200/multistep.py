@@ -300,6 +300,7 @@ class VariableCoefficientAdamsBashforth(object):
                  dfactor=0.2, **unused_kwargs):
         unused_kwargs.pop('shared_step_group', None)
         unused_kwargs.pop('replicated_components', None)
+        unused_kwargs.pop('host_output', None)       # (only the Runge-Kutta drivers deliver to host buffers)
         unused_kwargs.pop('cuda_graph', None)
         unused_kwargs.pop('fused_rhs', None)
         _handle_unused_kwargs(self, unused_kwargs)

@@ -58,6 +58,17 @@ def _pinned_acquire(dev, nbytes=256):
     return buf, key
 
 
+_COPY_STREAMS = {}
+
+
+def _copy_stream(dev):
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    st = _COPY_STREAMS.get(key)
+    if st is None:
+        st = _COPY_STREAMS[key] = torch.cuda.Stream(dev)
+    return st
+
+
 def _pinned_release(key):
     if key is not None:
         _PINNED_BUSY.discard(key)
@@ -169,6 +180,9 @@ class AdaptiveStepsizeODESolver(object):
         self.cuda_graph = bool(unused_kwargs.pop("cuda_graph", False))
         # extension: a built-in right-hand side (tfdiffeq_b200/rhs.py) runs in one persistent kernel unless disabled
         self.fused_rhs = bool(unused_kwargs.pop("fused_rhs", True))
+        # extension: a page-locked host tensor of the solution's shape.  The solution is delivered THERE (and returned as
+        # that tensor); with a built-in right-hand side the device-to-host copies are issued behind the running solve
+        self.host_output = unused_kwargs.pop("host_output", None)
         _handle_unused_kwargs(self, unused_kwargs)
         del unused_kwargs
         self.func = func
@@ -229,7 +243,24 @@ class AdaptiveStepsizeODESolver(object):
             fused = self._integrate_fused(t, seg, dev, dtype) if self.fused_rhs else None
             if fused is not None:
                 return fused
-            return self._integrate(t, seg, dev, dtype)
+            res = self._integrate(t, seg, dev, dtype)
+            if self.host_output is not None:
+                ho = self._check_host_output(res)
+                for h, r in zip(ho, res):
+                    h.copy_(r, non_blocking=True)
+                torch.cuda.current_stream(dev).synchronize()
+                return tuple(ho)
+            return res
+
+    def _check_host_output(self, outs):
+        ho = self.host_output
+        ho = (ho,) if isinstance(ho, torch.Tensor) else tuple(ho)
+        if len(ho) != len(outs):
+            raise ValueError("host_output must hold one tensor per state component")
+        for h, o in zip(ho, outs):
+            if h.device.type != "cpu" or not h.is_pinned() or h.shape != o.shape or h.dtype != o.dtype or not h.is_contiguous():
+                raise ValueError("host_output must be page-locked, contiguous CPU tensors of the solution's shape and dtype")
+        return ho
 
     def _integrate_fused(self, t, seg, dev, dtype):
         """Whole solve in one persistent kernel when func is a built-in right-hand side (rhs.py)."""
@@ -283,8 +314,32 @@ class AdaptiveStepsizeODESolver(object):
         fd.t_start, fd.first_step = float(t_host[0]), first
         fd.state, fd.workspace, fd.workspace_bytes = state_dev.data_ptr(), workspace.data_ptr(), ws_bytes
         fd.cuda_stream = stream.cuda_stream
+        host_out = mark = mkey = None
+        if self.host_output is not None:
+            host_out = self._check_host_output((out,))[0]
+            mark, mkey = _pinned_acquire(dev, 64)
+            mark = mark[:4].view(torch.int32)
+            mark.zero_()
+            fd.host_mark = mark.data_ptr()      # page-locked memory is device-addressable at its host address (UVA)
         rc = lib.b2ode_fused_solve(C.byref(desc), C.byref(fd))
         check(rc)
+        if host_out is not None:
+            # stream the slab out behind the solve: the kernel keeps `mark` at the number of leading rows that are complete
+            done = torch.cuda.Event()
+            done.record(stream)
+            cs = _copy_stream(dev)
+            out.record_stream(cs)
+            mark_np = mark.numpy()
+            copied, chunk = 0, max(8, n_out // 64)
+            while copied < n_out:
+                fin = done.query()
+                m = n_out if fin else min(int(mark_np[0]), n_out)
+                if m - copied >= chunk or (fin and m > copied):
+                    if fin:
+                        cs.wait_event(done)
+                    with torch.cuda.stream(cs):
+                        host_out[copied:m].copy_(out[copied:m], non_blocking=True)
+                    copied = m
         host, hkey = _pinned_acquire(dev)
         try:
             host.copy_(state_dev, non_blocking=True)
@@ -292,6 +347,10 @@ class AdaptiveStepsizeODESolver(object):
             final = _lib.State.from_buffer_copy(host.numpy().tobytes())
         finally:
             _pinned_release(hkey)
+        if host_out is not None:
+            cs.synchronize()
+            _pinned_release(mkey)
+            out = host_out
         attempts = int(final.n_acc + final.n_rej)
         nfe = 1 + (1 if self.first_step is None else 0) + (tab.n_k - 1) * attempts
         self.stats = dict(n_accepted=int(final.n_acc), n_rejected=int(final.n_rej), nfe=nfe, attempts_enqueued=attempts,
@@ -547,6 +606,7 @@ class FixedGridODESolver(object):
         unused_kwargs.pop('replicated_components', None)
         unused_kwargs.pop('cuda_graph', None)
         self.fused_rhs = bool(unused_kwargs.pop("fused_rhs", True))
+        self.host_output = unused_kwargs.pop("host_output", None)
         _handle_unused_kwargs(self, unused_kwargs)
         del unused_kwargs
         self.func = func
@@ -582,7 +642,14 @@ class FixedGridODESolver(object):
         _assert_increasing(t)
         seg = _Segments(self.y0)
         with torch.cuda.device(seg.device), torch.no_grad():
-            return self._integrate(t, seg)
+            res = self._integrate(t, seg)
+            if self.host_output is not None:
+                ho = AdaptiveStepsizeODESolver._check_host_output(self, res)
+                for h, r in zip(ho, res):
+                    h.copy_(r, non_blocking=True)
+                torch.cuda.current_stream(seg.device).synchronize()
+                return tuple(ho)
+            return res
 
     def _integrate(self, t, seg):
         lib, check = _lib.lib, _lib.check
