@@ -1,6 +1,7 @@
 """Short, deterministic kernel sequence for ncu (never a bench number).
 
-  --workload lorenz    : BASELINE config 2 shape (65 536 x 3 fp64 dopri5), first --npts output points
+  --workload lorenz    : BASELINE config 2 shape (65 536 x 3 fp64 dopri5), first --npts output points, external func
+  --workload fused     : the same system with the library's own right-hand side: the persistent kernel, all 1 000 points
   --workload headline  : north-star kernel size (65 536 x 128 fp64 dopri5, linear func), 3 output points
   --workload mlp       : ODENet func rhs.DenseMLP(64, 256) on 131 072 rows (fp32 / TF32 tcgen05), one dopri5 solve
 """
@@ -28,6 +29,12 @@ if a.workload == "lorenz":
     y0 = torch.tensor(np.array([1., 1., 1.]) + 0.1 * rng.standard_normal((65536, 3)), device=dev)
     f = PROBLEMS["lorenz"](backend="torch", device=dev)
     t = torch.arange(a.npts, dtype=torch.float64) * 0.01
+    kw = dict(method="dopri5")
+elif a.workload == "fused":
+    rng = np.random.default_rng(0)
+    y0 = torch.tensor(np.array([1., 1., 1.]) + 0.1 * rng.standard_normal((65536, 3)), device=dev)
+    f = tfd.rhs.Lorenz()
+    t = torch.arange(1000, dtype=torch.float64) * 0.01
     kw = dict(method="dopri5")
 elif a.workload == "mlp":
     torch.manual_seed(0)

@@ -62,5 +62,33 @@ def full(src, dst):
             f.write("\n")
 
 
+def traffic(src, key, match):
+    """Record dram bytes per launch of the first kernel whose name contains `match` in profiles/ncu_traffic.json under
+    `key` (read by bench.py's roofline.traffic, with the report it came from)."""
+    import json
+    import os
+    raw = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, units = rows[0], rows[1]
+    scale = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}
+    for row in rows[2:]:
+        d = dict(zip(hdr, row))
+        u = dict(zip(hdr, units))
+        if match in d.get("Kernel Name", ""):
+            tb = float(d["dram__bytes_read.sum"]) * scale[u["dram__bytes_read.sum"]] + \
+                float(d["dram__bytes_write.sum"]) * scale[u["dram__bytes_write.sum"]]
+            path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "ncu_traffic.json")
+            db = json.load(open(path)) if os.path.exists(path) else {}
+            db[key] = {"dram_bytes": tb, "kernel": d["Kernel Name"][:120], "source": "ncu --set full --clock-control none: " + os.path.basename(src),
+                       "duration_us_under_ncu": float(d["gpu__time_duration.sum"]) * {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(u["gpu__time_duration.sum"], 1.0)}
+            json.dump(db, open(path, "w"), indent=1, sort_keys=True)
+            print(key, db[key])
+            return
+    raise SystemExit("no kernel matching %r in %s" % (match, src))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    if sys.argv[1] == "traffic":
+        traffic(sys.argv[2], sys.argv[3], sys.argv[4])
+    else:
+        {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])

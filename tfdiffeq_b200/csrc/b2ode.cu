@@ -18,6 +18,7 @@
 //    quartic's coefficients are never written to HBM.
 
 #include "b2ode_dev.cuh"
+#include <stdlib.h>
 
 static thread_local char g_err[512] = "";
 
@@ -241,6 +242,131 @@ __global__ void __launch_bounds__(kThreads, B2_MINB_FINALIZE) k_rk_finalize(cons
         }
     });
     // columns: 0 = sum err^2, 1 = max|y0|, 2 = max|y1| (NaN poisons the tolerance like reduce_max), 3 = non-finite y0
+    constexpr unsigned MM = 0xEu;
+    Partial mine;
+    mine.v[0] = sum;
+    mine.v[1] = m0.value();
+    mine.v[2] = m1.value();
+    mine.v[3] = bad ? 1.0 : 0.0;
+    Partial r = block_reduce<MM>(mine);
+    if (threadIdx.x == 0) p.part[blockIdx.x] = r;
+    if (!last_block_arrives(&p.st->ticket)) return;
+    __shared__ Partial tot[B2ODE_MAXSEG];
+    reduce_partials<MM>(p.g, p.part, tot);
+    group_combine<MM>(p.comm, p.st, tot, p.g.nseg);
+    if (threadIdx.x < 32) {
+        control_step<T>(p.st, p.c, tot, p.g.nseg, p.klast);
+        if (threadIdx.x == 0) p.st->ticket = 0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2+K3, bulk-copy variant (A/B, B2ODE_FINALIZE_BULK=1): the same pass with its (NK + 2) read streams staged through
+// shared memory by the TMA engine in linear mode -- one thread issues cp.async.bulk copies of kBulkTile elements per
+// stream into a kBulkStages-deep ring, an mbarrier transaction count tells the block when a stage has landed.  north_star
+// asks for "TMA-staged shared-memory tiles for the k-stage buffer"; there is no reuse and no tile structure in this pass,
+// so the question is only whether the copy engine feeds HBM better than 16-byte LDGs with eight streams in flight per
+// thread.  Measured at 65 536 x 128 fp64: profiles/r02_finalize_bulk_ab.md.  One segment, 16-byte aligned pointers.
+// ------------------------------------------------------------------------------------------------
+constexpr int kBulkTile = 512;       // elements per stream per stage (4 KB fp64, 2 KB fp32)
+constexpr int kBulkStages = 3;
+
+__device__ __forceinline__ unsigned smem_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_parity(unsigned long long *bar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t}" ::"r"(smem_addr(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_addr(bar))
+                 : "memory");
+}
+
+template <typename T, int NK>
+__global__ void __launch_bounds__(kThreads) k_rk_finalize_bulk(const __grid_constant__ FinalizeParams<NK> p) {
+    extern __shared__ __align__(128) unsigned char bulk_smem[];
+    __shared__ __align__(8) unsigned long long full[kBulkStages];
+    constexpr int NS = NK + 2;                                   // streams: y0, y1, k...
+    T *ring = reinterpret_cast<T *>(bulk_smem);                  // [stage][stream][kBulkTile]
+    const long long n = p.g.n[0];
+    const long long ntiles = n / kBulkTile;                      // full tiles; the remainder is read directly
+    const T dt = (T)p.st->dt;
+    T c[NK];
+#pragma unroll
+    for (int j = 0; j < NK; ++j) c[j] = Ar<T>::mul(dt, (T)p.coef[j]);
+    const T *src[NS];
+    src[0] = (const T *)p.y0[0];
+    src[1] = (const T *)p.y1[0];
+#pragma unroll
+    for (int j = 0; j < NK; ++j) src[2 + j] = (const T *)p.k[j][0];
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kBulkStages; ++s) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](long long tile, int stage) {
+        mbar_expect_tx(&full[stage], (unsigned)(NS * kBulkTile * sizeof(T)));
+#pragma unroll
+        for (int q = 0; q < NS; ++q)
+            bulk_g2s(ring + ((size_t)stage * NS + q) * kBulkTile, src[q] + tile * kBulkTile, (unsigned)(kBulkTile * sizeof(T)), &full[stage]);
+    };
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kBulkStages; ++s) {
+            const long long tile = (long long)blockIdx.x + (long long)s * gridDim.x;
+            if (tile < ntiles) issue(tile, s);
+        }
+    }
+    double sum = 0.0;
+    AbsMax<T> m0, m1;
+    bool bad = false;
+    auto one = [&](T a, T b, const T(&kk)[NK]) {
+        T err = Ar<T>::mul(c[0], kk[0]);
+#pragma unroll
+        for (int j = 1; j < NK; ++j) err = Ar<T>::add(err, Ar<T>::mul(c[j], kk[j]));
+        const double ed = (double)err;
+        sum += ed * ed;
+        m0.see(a);
+        m1.see(b);
+        bad |= !isfinite((double)a);
+    };
+    int it = 0;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const int stage = it % kBulkStages;
+        mbar_wait_parity(&full[stage], (unsigned)((it / kBulkStages) & 1));
+        const T *base = ring + (size_t)stage * NS * kBulkTile;
+#pragma unroll
+        for (int e = threadIdx.x; e < kBulkTile; e += kThreads) {
+            T kk[NK];
+#pragma unroll
+            for (int j = 0; j < NK; ++j) kk[j] = base[(2 + j) * kBulkTile + e];
+            one(base[e], base[kBulkTile + e], kk);
+        }
+        __syncthreads();                                         // everyone has read the stage: it may be refilled
+        const long long next = tile + (long long)kBulkStages * gridDim.x;
+        if (threadIdx.x == 0 && next < ntiles) issue(next, stage);
+    }
+    // remainder (n not a multiple of the tile): plain loads, one block
+    if (blockIdx.x == 0) {
+        for (long long i = ntiles * kBulkTile + threadIdx.x; i < n; i += kThreads) {
+            T kk[NK];
+#pragma unroll
+            for (int j = 0; j < NK; ++j) kk[j] = src[2 + j][i];
+            one(src[0][i], src[1][i], kk);
+        }
+    }
     constexpr unsigned MM = 0xEu;
     Partial mine;
     mine.v[0] = sum;
@@ -868,7 +994,7 @@ struct Timing {
 static Timing *g_timing = nullptr;
 
 template <typename K, typename P>
-static int launch(K kernel, int grid, cudaStream_t st, const P &p, int fam = -1) {
+static int launch(K kernel, int grid, cudaStream_t st, const P &p, int fam = -1, size_t dyn_smem = 0) {
     if (grid <= 0) return 0;
     Timing *tm = g_timing;
     bool timed = tm && fam >= 0 && ((tm->mask >> fam) & 1u) && tm->n[fam] < kMaxTimed;
@@ -877,7 +1003,7 @@ static int launch(K kernel, int grid, cudaStream_t st, const P &p, int fam = -1)
         if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) timed = false;
     }
     if (timed) B2_CUDA(cudaEventRecord(tm->ev[fam][tm->n[fam]][0], st));
-    kernel<<<grid, kThreads, 0, st>>>(p);
+    kernel<<<grid, kThreads, dyn_smem, st>>>(p);
     B2_CUDA(cudaGetLastError());
     if (timed) {
         B2_CUDA(cudaEventRecord(tm->ev[fam][tm->n[fam]][1], st));
@@ -1147,6 +1273,31 @@ static int launch_finalize(b2ode_solver *s) {
     p.c = s->ctrl;
     p.comm = s->comm;
     p.g.vec_mask = vec_mask_of(s, lists, NK + 2);
+    static int bulk = -1;            // A/B switch (profiles/r02_finalize_bulk_ab.md); default = the LDG kernel
+    if (bulk < 0) {
+        const char *e = getenv("B2ODE_FINALIZE_BULK");
+        bulk = (e && e[0] == '1') ? 1 : 0;
+    }
+    if (bulk && s->d.nseg == 1 && (p.g.vec_mask & 1u) && s->d.seg_len[0] >= (long long)kBulkTile * 4) {
+        const size_t smem = (size_t)kBulkStages * (NK + 2) * kBulkTile * sizeof(T);
+        if (smem <= 200 * 1024) {
+            static bool configured[64][15] = {};
+            int dev = 0;
+            B2_CUDA(cudaGetDevice(&dev));
+            if (dev >= 0 && dev < 64 && !configured[dev][NK]) {
+                B2_CUDA(cudaFuncSetAttribute(k_rk_finalize_bulk<T, NK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                configured[dev][NK] = true;
+            }
+            const long long ntiles = s->d.seg_len[0] / kBulkTile;
+            const int sms = s->d.sm_count > 0 ? s->d.sm_count : 148;
+            const int per_sm = (int)((220 * 1024) / (smem + 1024)) < 1 ? 1 : (int)((220 * 1024) / (smem + 1024));
+            long long grid = (long long)sms * per_sm;
+            if (grid > ntiles) grid = ntiles;
+            if (grid > s->grid) grid = s->grid;          // the partial array was sized for s->grid blocks
+            p.g.blk_begin[1] = (int)grid;                 // reduce_partials walks [blk_begin[0], blk_begin[1])
+            return launch(k_rk_finalize_bulk<T, NK>, (int)grid, s->stream, p, B2_FAM_FINALIZE, smem);
+        }
+    }
     return launch(k_rk_finalize<T, NK>, s->grid, s->stream, p, B2_FAM_FINALIZE);
 }
 
