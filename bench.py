@@ -252,7 +252,13 @@ class Cfg3(Workload):
 class Cfg5(Workload):
     name, tag = "cfg5", "kepler32_b4096x128_f64_dopri8_rtol1e-9_101pts"
     method, rtol, atol = "dopri8", 1e-9, 1e-9
-    paths = ("external_func_cuda_graph", "external_func_eager")
+    paths = ("builtin_rhs_stage_kernels_cuda_graph", "builtin_rhs_stage_kernels", "external_func_cuda_graph", "external_func_eager")
+
+    def func(self, path, dev):
+        if path.startswith("builtin_rhs"):
+            import tfdiffeq_b200 as tfd
+            return tfd.rhs.Kepler(), ({"cuda_graph": True} if path.endswith("cuda_graph") else {})
+        return Workload.func(self, path, dev)
 
     def shape(self):
         return (4096, 128)

@@ -200,6 +200,29 @@ int b2ode_comm_set_replicated(b2ode_solver *s, unsigned segment_mask);
 #define B2ODE_RHS_CUBIC_MLP 2       /* (B,2): W2 tanh(W1 y^3 + b1) + b2; params {H <= 128, cube}; rhs_data = packed
                                        [W1 (2 x H) | b1 (H) | W2 (H x 2) | b2 (2)] in the state dtype   examples/ode_demo.py:115-129 */
 
+#define B2ODE_RHS_KEPLER 3         /* (B, 4 m): m two-body orbits [x, y, vx, vy] per row; no params   tests/DETEST/detest.py:263-283 */
+
+/* A built-in right-hand side as the kernels see it. */
+typedef struct b2ode_rhs_desc {
+    int32_t kind;                       /* B2ODE_RHS_*                                                   */
+    int32_t n_params;
+    double params[8];
+    const void *data;                   /* staged weights (B2ODE_RHS_CUBIC_MLP), else NULL               */
+    double time_sign;                   /* -1: the reversed system of tfdiffeq/misc.py:318-321           */
+} b2ode_rhs_desc;
+
+/* k_out = f(t, y) for a built-in right-hand side: one elementwise pass over n state elements (rows of the
+ * right-hand side's dimension); `t_scalar` is a device scalar of the state dtype.  Used for the first derivative
+ * (dopri5.py:71), the initial-step probe (misc.py:237) and stage 0. */
+int b2ode_rhs_eval(int dtype, const b2ode_rhs_desc *rhs, const void *t_scalar, const void *y, void *k_out, int64_t n,
+                   int sm_count, void *cuda_stream);
+
+/* b2ode_rk_stage for stage i in [1, n_k - 2] WITH the evaluation of a built-in right-hand side in the same launch
+ * (tfdiffeq/rk_common.py:49-52: y_i = y0 + sum (dt beta_ij) k_j ; k_{i+1} = func(t_i, y_i)): registers k_i = k_new,
+ * writes k_{i+1} to k_out (caller-owned, n elements) and, for the last stage, the stage input to ystage.  For batches
+ * the persistent kernel below cannot keep co-resident.  Single-tensor states. */
+int b2ode_rk_stage_rhs(b2ode_solver *s, int i, const void *const *k_new, const b2ode_rhs_desc *rhs, void *k_out);
+
 /* Replaces the WHOLE of AdaptiveStepsizeODESolver.integrate (tfdiffeq/solvers.py:27-35) for a func the library
  * knows: every trajectory stays in one thread's registers (state + all k's) for the entire solve, one grid-wide
  * reduction per attempt keeps the reference's single shared step / global scalar tolerance; HBM traffic is the

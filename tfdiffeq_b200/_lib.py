@@ -13,7 +13,7 @@ F32, F64 = 0, 1
 ST_UNDERFLOW, ST_NONFINITE, ST_MAXSTEPS = 1, 2, 4
 CTRL_REFERENCE, CTRL_TSIT5 = 0, 1
 FAM_STAGE0, FAM_STAGE, FAM_FINALIZE, FAM_EMIT, FAM_INIT, FAM_FIXED, FAM_FUSED = range(7)
-RHS_LORENZ, RHS_LOTKA_VOLTERRA, RHS_CUBIC_MLP = 0, 1, 2
+RHS_LORENZ, RHS_LOTKA_VOLTERRA, RHS_CUBIC_MLP, RHS_KEPLER = 0, 1, 2, 3
 OP_EULER, OP_HALF_STEP, OP_HEUN_FINAL, OP_RK4_S2, OP_RK4_S3, OP_RK4_S4, OP_RK4_FINAL, OP_LERP = range(8)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -47,6 +47,12 @@ class AdaptiveBuffers(C.Structure):
                 ("y0", C.c_void_p * MAXSEG), ("f0", C.c_void_p * MAXSEG), ("ystage", C.c_void_p * MAXSEG),
                 ("tstage", C.c_void_p), ("t_out", C.c_void_p), ("n_out", C.c_int32),
                 ("out", C.c_void_p * MAXSEG)]
+
+
+class RhsDesc(C.Structure):
+    """mirror of ``b2ode_rhs_desc``"""
+    _fields_ = [("kind", C.c_int32), ("n_params", C.c_int32), ("params", C.c_double * 8), ("data", C.c_void_p),
+                ("time_sign", C.c_double)]
 
 
 class FusedDesc(C.Structure):
@@ -93,6 +99,8 @@ _SIGNATURES = {
                                           C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "b2ode_fused_solve": (C.c_int, [C.POINTER(AdaptiveDesc), C.c_void_p]),
+    "b2ode_rhs_eval": (C.c_int, [C.c_int, C.POINTER(RhsDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
+    "b2ode_rk_stage_rhs": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(RhsDesc), C.c_void_p]),
     "b2ode_set_k": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
     "b2ode_dense_layer": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_double), C.c_int, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p]),

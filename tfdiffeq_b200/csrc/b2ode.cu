@@ -18,6 +18,7 @@
 //    quartic's coefficients are never written to HBM.
 
 #include "b2ode_dev.cuh"
+#include "b2ode_rhs.cuh"
 #include <stdlib.h>
 
 static thread_local char g_err[512] = "";
@@ -72,6 +73,84 @@ __global__ void __launch_bounds__(kThreads, B2_MINB_STAGE) k_rk_stage(const __gr
         }
         st_pack<T, V>(out, i, o);
     });
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1 + func: stage combine with a BUILT-IN right-hand side evaluated in the same pass (SURVEY 8f-2 for batches / tableaus
+// the one-launch persistent kernel cannot hold: BASELINE config 5's 131 072 Kepler orbits under dopri8, Lorenz batches
+// beyond 71 040 trajectories).  One thread per ROW of RHS::D state elements:
+//     y_i = y0 + sum_j (dt * beta_ij) k_j        (rk_common.py:51, same operation order as k_rk_stage)
+//     k_{i+1} = f(t_i, y_i)                      (rk_common.py:52; f = the library's right-hand side, same arithmetic as rhs.py)
+// so a stage is ONE launch that reads (NK + 1) N and writes N, instead of the stage kernel, a 2 N round trip of the stage
+// input and the ~6 elementwise torch kernels of the module's forward.  NK = 0: plain evaluation k = f(t, y) of an
+// existing buffer (first derivative, initial-step probe, stage 0 after the commit kernel).
+// ------------------------------------------------------------------------------------------------
+template <int NK>
+struct StageRhsParams {
+    const b2ode_state *st;
+    const void *y0;
+    const void *k[NK > 0 ? NK : 1];
+    double coef[NK > 0 ? NK : 1];
+    void *ystage;              // optional: also materialise the stage input (the last stage's input is y1)
+    void *k_out;
+    const void *t_scalar;      // device scalar of the state dtype: the stage time
+    long long rows;
+    double time_sign;
+    double rhs[8];
+    const void *rhs_data;
+};
+
+template <typename T, typename RHS, int NK>
+__global__ void __launch_bounds__(kThreads) k_rk_stage_rhs(const __grid_constant__ StageRhsParams<NK> p) {
+    constexpr int D = RHS::D;
+    __shared__ T sw[RHS::kSmem];
+    if (RHS::kSmem > 1) {
+        const int nw = (int)p.rhs[0] * 5 + 2;
+        for (int q = threadIdx.x; q < nw && q < RHS::kSmem; q += kThreads) sw[q] = ((const T *)p.rhs_data)[q];
+        __syncthreads();
+    }
+    T c[NK > 0 ? NK : 1];
+    if (NK > 0) {
+        const T dt = (T)p.st->dt;
+#pragma unroll
+        for (int j = 0; j < NK; ++j) c[j] = Ar<T>::mul(dt, (T)p.coef[j]);
+    }
+    const T ti = *reinterpret_cast<const T *>(p.t_scalar);
+    const T sgn = (T)p.time_sign;
+    const T *y0 = (const T *)p.y0;
+    T *ys = (T *)p.ystage, *ko = (T *)p.k_out;
+    for (long long r = (long long)blockIdx.x * kThreads + threadIdx.x; r < p.rows; r += (long long)gridDim.x * kThreads) {
+        T y[D], kv[NK > 0 ? NK : 1][D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) y[d] = y0[r * D + d];
+#pragma unroll
+        for (int j = 0; j < NK; ++j)
+#pragma unroll
+            for (int d = 0; d < D; ++d) kv[j][d] = ((const T *)p.k[j])[r * D + d];
+        if (NK > 0) {
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+                T acc = Ar<T>::mul(c[0], kv[0][d]);
+#pragma unroll
+                for (int j = 1; j < NK; ++j) acc = Ar<T>::add(acc, Ar<T>::mul(c[j], kv[j][d]));   // add_n, left to right
+                y[d] = Ar<T>::add(y[d], acc);
+            }
+            if (ys) {
+#pragma unroll
+                for (int d = 0; d < D; ++d) ys[r * D + d] = y[d];
+            }
+        }
+        T dy[D];
+        if (sgn < T(0)) {                                              // reverse-time wrapper of misc.py:318-321
+            RHS::eval(p.rhs, sw, -ti, y, dy);
+#pragma unroll
+            for (int d = 0; d < D; ++d) dy[d] = -dy[d];
+        } else {
+            RHS::eval(p.rhs, sw, ti, y, dy);
+        }
+#pragma unroll
+        for (int d = 0; d < D; ++d) ko[r * D + d] = dy[d];
+    }
 }
 
 // Stage 0 with the deferred commit of the previous attempt (dopri5.py:113-114: y_next = y1 if accept ...).
@@ -1248,6 +1327,125 @@ extern "C" int b2ode_rk_stage(b2ode_solver *s, int i, const void *const *k_new) 
     }
     if (s->d.dtype == B2ODE_F64) return dispatch_stage<double>(s, i);
     return dispatch_stage<float>(s, i);
+}
+
+// ---- stage kernels with a built-in right-hand side ------------------------------------------------------------------
+static int rhs_row_dim(int kind) {
+    switch (kind) {
+        case B2ODE_RHS_LORENZ: return 3;
+        case B2ODE_RHS_LOTKA_VOLTERRA:
+        case B2ODE_RHS_CUBIC_MLP: return 2;
+        case B2ODE_RHS_KEPLER: return 4;
+    }
+    return -1;
+}
+
+struct RhsCall {
+    int kind;
+    double prm[8];
+    const void *data;
+    double time_sign;
+};
+
+template <typename T, typename RHS, int NK>
+static int launch_stage_rhs_t(const StageRhsParams<NK> &p, int sm_count, cudaStream_t st) {
+    const long long need = (p.rows + kThreads - 1) / kThreads;
+    const long long cap = (long long)(sm_count > 0 ? sm_count : 148) * 8;
+    const int grid = (int)(need < cap ? (need < 1 ? 1 : need) : cap);
+    return launch(k_rk_stage_rhs<T, RHS, NK>, grid, st, p, B2_FAM_STAGE);
+}
+
+template <typename T, int NK>
+static int launch_stage_rhs_k(int kind, const StageRhsParams<NK> &p, int sm_count, cudaStream_t st) {
+    switch (kind) {
+        case B2ODE_RHS_LORENZ: return launch_stage_rhs_t<T, RhsLorenz<T>, NK>(p, sm_count, st);
+        case B2ODE_RHS_LOTKA_VOLTERRA: return launch_stage_rhs_t<T, RhsLotkaVolterra<T>, NK>(p, sm_count, st);
+        case B2ODE_RHS_CUBIC_MLP: return launch_stage_rhs_t<T, RhsCubicMLP<T>, NK>(p, sm_count, st);
+        case B2ODE_RHS_KEPLER: return launch_stage_rhs_t<T, RhsKepler<T>, NK>(p, sm_count, st);
+    }
+    return b2_fail(B2ODE_EINVAL, "unknown built-in right-hand side %d", kind);
+}
+
+template <int NK>
+static void fill_rhs(StageRhsParams<NK> *p, const b2ode_rhs_desc *r) {
+    for (int i = 0; i < 8; ++i) p->rhs[i] = i < r->n_params ? r->params[i] : 0.0;
+    p->rhs_data = r->data;
+    p->time_sign = r->time_sign;
+}
+
+static int check_rhs(const b2ode_rhs_desc *r, long long seg_len, long long *rows) {
+    if (!r) return b2_fail(B2ODE_EINVAL, "null right-hand side");
+    const int D = rhs_row_dim(r->kind);
+    if (D < 0) return b2_fail(B2ODE_EINVAL, "unknown built-in right-hand side %d", r->kind);
+    if (r->n_params < 0 || r->n_params > 8) return b2_fail(B2ODE_EINVAL, "bad rhs params");
+    if (seg_len % D != 0) return b2_fail(B2ODE_EINVAL, "state length %lld is not a multiple of the row size %d", seg_len, D);
+    if (r->kind == B2ODE_RHS_CUBIC_MLP && (!r->data || r->n_params < 2 || r->params[0] < 1 || r->params[0] > 128))
+        return b2_fail(B2ODE_EINVAL, "cubic-MLP right-hand side needs {H <= 128, cube} and its weights");
+    *rows = seg_len / D;
+    return 0;
+}
+
+extern "C" int b2ode_rhs_eval(int dtype, const b2ode_rhs_desc *rhs, const void *t_scalar, const void *y, void *k_out, int64_t n,
+                              int sm_count, void *cuda_stream) {
+    if (!t_scalar || !y || !k_out || n < 1) return b2_fail(B2ODE_EINVAL, "bad arguments");
+    long long rows = 0;
+    const int rc = check_rhs(rhs, n, &rows);
+    if (rc) return rc;
+    StageRhsParams<0> p;
+    memset(&p, 0, sizeof(p));
+    p.y0 = y;
+    p.k_out = k_out;
+    p.t_scalar = t_scalar;
+    p.rows = rows;
+    fill_rhs(&p, rhs);
+    if (dtype == B2ODE_F64) return launch_stage_rhs_k<double, 0>(rhs->kind, p, sm_count, (cudaStream_t)cuda_stream);
+    if (dtype == B2ODE_F32) return launch_stage_rhs_k<float, 0>(rhs->kind, p, sm_count, (cudaStream_t)cuda_stream);
+    return b2_fail(B2ODE_EINVAL, "dtype must be 0 or 1");
+}
+
+template <typename T, int NK>
+static int launch_stage_rhs(b2ode_solver *s, int row, const b2ode_rhs_desc *rhs, void *k_out, long long rows) {
+    StageRhsParams<NK> p;
+    memset(&p, 0, sizeof(p));
+    p.st = (const b2ode_state *)s->b.state;
+    p.y0 = s->b.y0[0];
+    for (int j = 0; j < NK; ++j) {
+        p.k[j] = s->k[s->st_idx[row][j]][0];
+        p.coef[j] = s->st_coef[row][j];
+    }
+    p.ystage = (row == s->d.n_k - 2) ? s->b.ystage[0] : nullptr;     // the last stage's input is y1 (FSAL) / feeds the commit
+    p.k_out = k_out;
+    p.t_scalar = (const char *)s->b.tstage + (size_t)row * (s->d.dtype == B2ODE_F64 ? 8 : 4);
+    p.rows = rows;
+    fill_rhs(&p, rhs);
+    return launch_stage_rhs_k<T, NK>(rhs->kind, p, s->d.sm_count, s->stream);
+}
+
+template <typename T>
+static int dispatch_stage_rhs(b2ode_solver *s, int row, const b2ode_rhs_desc *rhs, void *k_out, long long rows) {
+    switch (s->st_nk[row]) {
+#define B2_CASE(N) \
+    case N:        \
+        return launch_stage_rhs<T, N>(s, row, rhs, k_out, rows);
+        B2_CASE(1) B2_CASE(2) B2_CASE(3) B2_CASE(4) B2_CASE(5) B2_CASE(6) B2_CASE(7) B2_CASE(8) B2_CASE(9) B2_CASE(10)
+        B2_CASE(11) B2_CASE(12) B2_CASE(13)
+#undef B2_CASE
+    }
+    return b2_fail(B2ODE_EINVAL, "unsupported number of stage terms %d", s->st_nk[row]);
+}
+
+extern "C" int b2ode_rk_stage_rhs(b2ode_solver *s, int i, const void *const *k_new, const b2ode_rhs_desc *rhs, void *k_out) {
+    B2_REQUIRE_BOUND(s);
+    const int nk = s->d.n_k;
+    if (s->d.nseg != 1) return b2_fail(B2ODE_EINVAL, "built-in right-hand sides take a single-tensor state");
+    if (i < 1 || i > nk - 2) return b2_fail(B2ODE_EINVAL, "stage index %d out of range for a fused right-hand side", i);
+    if (!k_new || !k_new[0] || !k_out) return b2_fail(B2ODE_EINVAL, "null k buffer");
+    long long rows = 0;
+    const int rc = check_rhs(rhs, s->d.seg_len[0], &rows);
+    if (rc) return rc;
+    s->k[i][0] = k_new[0];
+    if (s->d.dtype == B2ODE_F64) return dispatch_stage_rhs<double>(s, i, rhs, k_out, rows);
+    return dispatch_stage_rhs<float>(s, i, rhs, k_out, rows);
 }
 
 template <typename T, int NK>

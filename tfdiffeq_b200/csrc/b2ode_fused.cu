@@ -11,6 +11,7 @@
 // order: rk_common.py:49-60, misc.py:250-287, interp.py:6-67), only the reduction order differs.
 
 #include "b2ode_dev.cuh"
+#include "b2ode_rhs.cuh"
 #include <stdlib.h>
 
 // ------------------------------------------------------------------------------------------------
@@ -41,64 +42,6 @@ extern "C" int b2ode_debug_fused_trace(unsigned long long *out) {
 
 // Block size is a template parameter: 512 threads (one block per SM, the fewest barrier arrivals and partials)
 // when the kernel fits in 128 registers per thread, 128 threads otherwise.
-
-// ------------------------------------------------------------------------------------------------
-// built-in right-hand sides: explicit mul/add in the order of the torch expressions in rhs.py
-// ------------------------------------------------------------------------------------------------
-template <typename T>
-struct RhsLorenz {   // examples/lorenz_attractor.py:20-37 ; params {sigma, beta, rho}
-    static constexpr int D = 3;
-    static constexpr int kSmem = 1;      // no staged weights
-    static __device__ __forceinline__ void eval(const double *prm, const T * /*sw*/, T /*t*/, const T (&y)[3], T (&dy)[3]) {
-        using A = Ar<T>;
-        const T sigma = (T)prm[0], beta = (T)prm[1], rho = (T)prm[2];
-        dy[0] = A::mul(sigma, A::sub(y[1], y[0]));                          // sigma * (y - x)
-        dy[1] = A::sub(A::mul(y[0], A::sub(rho, y[2])), y[1]);              // x * (rho - z) - y
-        dy[2] = A::sub(A::mul(y[0], y[1]), A::mul(beta, y[2]));             // x * y - beta * z
-    }
-};
-
-template <typename T>
-struct RhsLotkaVolterra {   // README.md:67-81 ; params {a, b, c, d}
-    static constexpr int D = 2;
-    static constexpr int kSmem = 1;
-    static __device__ __forceinline__ void eval(const double *prm, const T * /*sw*/, T /*t*/, const T (&y)[2], T (&dy)[2]) {
-        using A = Ar<T>;
-        const T a = (T)prm[0], b = (T)prm[1], c = (T)prm[2], d = (T)prm[3];
-        dy[0] = A::sub(A::mul(a, y[0]), A::mul(A::mul(b, y[0]), y[1]));     // a*x - b*x*z
-        dy[1] = A::add(A::mul(-c, y[1]), A::mul(A::mul(d, y[0]), y[1]));    // -c*z + d*x*z
-    }
-};
-
-// examples/ode_demo.py:115-129 (BASELINE config 3): W2 . tanh(W1 . y**3 + b1) + b2, 2 -> H -> 2, H <= 128.
-// params {H, cube}; weights staged in shared memory, packed [W1 (2 x H) | b1 (H) | W2 (H x 2) | b2 (2)].
-// torch evaluates the two products with cuBLAS (its own FMA order), so this right-hand side agrees with the
-// module's forward to rounding, not bit for bit.
-template <typename T>
-struct RhsCubicMLP {
-    static constexpr int D = 2;
-    static constexpr int kMaxH = 128;
-    static constexpr int kSmem = 2 * kMaxH + kMaxH + 2 * kMaxH + 2;
-    static __device__ __forceinline__ void eval(const double *prm, const T *sw, T /*t*/, const T (&y)[2], T (&dy)[2]) {
-        using A = Ar<T>;
-        const int H = (int)prm[0];
-        const bool cube = prm[1] != 0.0;
-        const T u0 = cube ? A::mul(A::mul(y[0], y[0]), y[0]) : y[0];
-        const T u1 = cube ? A::mul(A::mul(y[1], y[1]), y[1]) : y[1];
-        const T *W1 = sw, *b1 = sw + 2 * H, *W2 = sw + 3 * H, *b2 = sw + 5 * H;
-        T o0 = T(0), o1 = T(0);
-        for (int h = 0; h < H; ++h) {
-            const T a = A::add(A::add(A::mul(u0, W1[h]), A::mul(u1, W1[H + h])), b1[h]);
-            const T z = act_dispatch(a);
-            o0 = A::add(o0, A::mul(z, W2[2 * h]));
-            o1 = A::add(o1, A::mul(z, W2[2 * h + 1]));
-        }
-        dy[0] = A::add(o0, b2[0]);
-        dy[1] = A::add(o1, b2[1]);
-    }
-    static __device__ __forceinline__ float act_dispatch(float a) { return tanhf(a); }
-    static __device__ __forceinline__ double act_dispatch(double a) { return tanh(a); }
-};
 
 // ------------------------------------------------------------------------------------------------
 // Grid-wide (and group-wide) all-reduce of two 64-bit values per attempt, built for LATENCY: measured on the round-1
@@ -959,6 +902,7 @@ static int fused_dispatch_rhs(const FusedParams &p, int rhs_kind, int n_k, long 
         case B2ODE_RHS_LORENZ: return fused_dispatch_s<T, RhsLorenz<T>>(p, n_k, n_traj, st, capacity, ntr);
         case B2ODE_RHS_LOTKA_VOLTERRA: return fused_dispatch_s<T, RhsLotkaVolterra<T>>(p, n_k, n_traj, st, capacity, ntr);
         case B2ODE_RHS_CUBIC_MLP: return fused_dispatch_s<T, RhsCubicMLP<T>>(p, n_k, n_traj, st, capacity, ntr);
+        case B2ODE_RHS_KEPLER: return fused_dispatch_s<T, RhsKepler<T>>(p, n_k, n_traj, st, capacity, ntr);
     }
     return b2_fail(B2ODE_EINVAL, "unknown built-in right-hand side %d", rhs_kind);
 }
@@ -979,7 +923,7 @@ extern "C" int64_t b2ode_fused_capacity(const b2ode_adaptive_desc *desc, int rhs
 }
 
 static int rhs_dim(int kind) {
-    return kind == B2ODE_RHS_LORENZ ? 3 : (kind == B2ODE_RHS_LOTKA_VOLTERRA || kind == B2ODE_RHS_CUBIC_MLP) ? 2 : -1;
+    return kind == B2ODE_RHS_LORENZ ? 3 : (kind == B2ODE_RHS_LOTKA_VOLTERRA || kind == B2ODE_RHS_CUBIC_MLP) ? 2 : kind == B2ODE_RHS_KEPLER ? 4 : -1;
 }
 
 static int rhs_check(int kind, const double *prm, int n_prm, const void *rhs_data) {
@@ -1206,6 +1150,7 @@ static int fused_fixed_dispatch(const FusedFixedParams &p, int rhs_kind, int sm_
         case B2ODE_RHS_LORENZ: k_fused_fixed<T, RhsLorenz<T>><<<grid, 256, 0, st>>>(p); break;
         case B2ODE_RHS_LOTKA_VOLTERRA: k_fused_fixed<T, RhsLotkaVolterra<T>><<<grid, 256, 0, st>>>(p); break;
         case B2ODE_RHS_CUBIC_MLP: k_fused_fixed<T, RhsCubicMLP<T>><<<grid, 256, 0, st>>>(p); break;
+        case B2ODE_RHS_KEPLER: k_fused_fixed<T, RhsKepler<T>><<<grid, 256, 0, st>>>(p); break;
         default: return b2_fail(B2ODE_EINVAL, "unknown built-in right-hand side %d", rhs_kind);
     }
     B2_CUDA(cudaGetLastError());

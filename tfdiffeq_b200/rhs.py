@@ -2,9 +2,11 @@
 
 Each class is an ordinary ``nn.Module`` -- ``forward(t, y)`` is written in plain torch ops and works anywhere
 (on the generic path, on CPU, under autograd).  When an instance is handed to ``odeint`` with an adaptive
-Runge-Kutta method and a single ``(..., dim)`` CUDA state, the solver recognises it and runs the WHOLE solve in
+Runge-Kutta method and a single ``(..., k * dim)`` CUDA state, the solver recognises it and runs the WHOLE solve in
 one persistent kernel (``b2ode_fused_solve``): every trajectory lives in one thread's registers, HBM traffic is
-the solution slab only.  The kernel evaluates exactly the same IEEE operations in the same order as
+the solution slab only.  Batches that cannot stay co-resident (and tsit5, whose dense output needs all k's) take the
+per-stage kernels with the right-hand side evaluated inside the stage kernel (``b2ode_rk_stage_rhs``): one launch per
+stage, no ``forward`` call at all.  The kernel evaluates exactly the same IEEE operations in the same order as
 ``forward`` does, so both paths agree to the last bit per stage; ``options={'fused_rhs': False}`` forces the
 generic path.
 """
@@ -56,6 +58,21 @@ class LotkaVolterra(BuiltinRHS):
     def forward(self, t, y):
         x, z = y[..., 0], y[..., 1]
         return torch.stack([self.a * x - self.b * x * z, -self.c * z + self.d * x * z], -1)
+
+
+class Kepler(BuiltinRHS):
+    """DETEST class D (tests/DETEST/detest.py:263-283): two-body orbits, ``[x, y, vx, vy]`` per orbit, any number of orbits
+    stacked along the last state axis (BASELINE config 5: 32 orbits = dim 128).  The kernels see the state as rows of 4."""
+    kind, dim = _lib.RHS_KEPLER, 4
+
+    def rhs_params(self):
+        return []
+
+    def forward(self, t, y):
+        s = y.reshape(y.shape[:-1] + (y.shape[-1] // 4, 4))
+        x, yy, vx, vy = s[..., 0], s[..., 1], s[..., 2], s[..., 3]
+        r3 = (x * x + yy * yy) ** 1.5
+        return torch.stack([vx, vy, -x / r3, -yy / r3], -1).reshape(y.shape)
 
 
 class CubicMLP(BuiltinRHS):

@@ -179,7 +179,10 @@ class AdaptiveStepsizeODESolver(object):
         # because python-side effects of func (e.g. an `nfe` counter on the module) happen once, at capture.
         self.cuda_graph = bool(unused_kwargs.pop("cuda_graph", False))
         # extension: a built-in right-hand side (tfdiffeq_b200/rhs.py) runs in one persistent kernel unless disabled
-        self.fused_rhs = bool(unused_kwargs.pop("fused_rhs", True))
+        # (True: persistent kernel when the batch fits, else the stage kernels with the right-hand side fused in; 'stages':
+        # always the latter; False: call func like any other callable)
+        fr = unused_kwargs.pop("fused_rhs", True)
+        self.fused_rhs = fr if fr == "stages" else bool(fr)
         # extension: a page-locked host tensor of the solution's shape.  The solution is delivered THERE (and returned as
         # that tensor); with a built-in right-hand side the device-to-host copies are issued behind the running solve
         self.host_output = unused_kwargs.pop("host_output", None)
@@ -240,7 +243,7 @@ class AdaptiveStepsizeODESolver(object):
         seg = _Segments(self.y0)
         dev, dtype = seg.device, seg.dtype
         with torch.cuda.device(dev), torch.no_grad():
-            fused = self._integrate_fused(t, seg, dev, dtype) if self.fused_rhs else None
+            fused = self._integrate_fused(t, seg, dev, dtype) if self.fused_rhs is True else None
             if fused is not None:
                 return fused
             res = self._integrate(t, seg, dev, dtype)
@@ -270,7 +273,7 @@ class AdaptiveStepsizeODESolver(object):
         if not isinstance(base, BuiltinRHS) or seg.nseg != 1 or tab.c_mid is None or tab.n_k not in (2, 4, 7, 14):
             return None
         shape = seg.shapes[0]
-        if len(shape) < 1 or shape[-1] != base.dim or seg.lens[0] == 0:
+        if len(shape) < 1 or shape[-1] % base.dim != 0 or seg.lens[0] == 0:
             return None
         lib, check = _lib.lib, _lib.check
         n_traj = seg.lens[0] // base.dim
@@ -301,8 +304,8 @@ class AdaptiveStepsizeODESolver(object):
         if not fits:
             import warnings
             warnings.warn("tfdiffeq_b200: batch of %d trajectories per GPU exceeds what the persistent fused kernel can keep "
-                          "co-resident; using the generic per-stage path (an order of magnitude slower for a built-in "
-                          "right-hand side)" % n_traj, RuntimeWarning)
+                          "co-resident; using the per-stage kernels with the right-hand side fused into them (one launch "
+                          "per stage instead of one per solve)" % n_traj, RuntimeWarning)
             return None
         stream = torch.cuda.current_stream(dev)
         fd.rhs_kind, fd.n_rhs_params = base.kind, len(prm)
@@ -400,26 +403,60 @@ class AdaptiveStepsizeODESolver(object):
             y0_views, s_views = seg.views(Y0), seg.views(S)
             nfe = 0
 
+            # built-in right-hand side on the per-stage path: it is evaluated INSIDE the stage kernels
+            # (b2ode_rk_stage_rhs / b2ode_rhs_eval), func's forward is never called; the k's live in engine buffers
+            from .rhs import BuiltinRHS
+            brhs = getattr(self.func, "_b2ode_base", None)
+            if not (self.fused_rhs and isinstance(brhs, BuiltinRHS) and seg.nseg == 1 and len(seg.shapes[0]) >= 1
+                    and seg.shapes[0][-1] % brhs.dim == 0 and seg.lens[0] > 0):
+                brhs = None
+            if brhs is not None:
+                rd = _lib.RhsDesc()
+                prm = brhs.rhs_params()
+                rd.kind, rd.n_params = brhs.kind, len(prm)
+                for k_, v_ in enumerate(prm):
+                    rd.params[k_] = v_
+                rhs_weights = brhs.rhs_data(dtype, dev)
+                rd.data = rhs_weights.data_ptr() if rhs_weights is not None else None
+                rd.time_sign = float(getattr(self.func, "_b2ode_sign", 1.0))
+                Kb = [seg.new() for _ in range(nk - 1)]
+                Kp = [_ptr_array(seg.ptrs(kb)) for kb in Kb]
+                dcode, n_el, sm_ = _DT[dtype], seg.lens[0], desc.sm_count
+
+                def rhs_eval(t_ptr, y_flat, k_flat):
+                    # on torch's CURRENT stream: inside a CUDA-graph capture that is the capture stream
+                    check(lib.b2ode_rhs_eval(dcode, C.byref(rd), C.c_void_p(t_ptr), C.c_void_p(y_flat.data_ptr()),
+                                             C.c_void_p(k_flat.data_ptr()), n_el, sm_,
+                                             C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+
             # ---- before_integrate (dopri5.py:70-78) ----------------------------------------------
             seg.fill(Y0, self.y0)
             t0_state = t_dev[0].to(dtype)                                    # tf.cast(t[0], y0.dtype)
-            f0 = fo.collect(self.func(t0_state, y0_views), set())
+            if brhs is not None:
+                rhs_eval(t0_state.data_ptr(), Y0, F0)
+            else:
+                f0 = fo.collect(self.func(t0_state, y0_views), set())
+                seg.fill(F0, f0)
             nfe += 1
-            seg.fill(F0, f0)
             if self.first_step is None:
                 check(lib.b2ode_adaptive_init(handle, float(t_host[0]), float("nan")))
                 check(lib.b2ode_initial_step_probe(handle))
-                f1 = fo.collect(self.func(tstage[0], s_views), set())
+                if brhs is not None:
+                    rhs_eval(tstage.data_ptr(), S, Kb[0])
+                    check(lib.b2ode_initial_step_finish(handle, Kp[0]))
+                else:
+                    f1 = fo.collect(self.func(tstage[0], s_views), set())
+                    check(lib.b2ode_initial_step_finish(handle, fo.pointers(f1)))
+                    del f1
                 nfe += 1
-                check(lib.b2ode_initial_step_finish(handle, fo.pointers(f1)))
-                del f1
             else:
                 check(lib.b2ode_adaptive_init(handle, float(t_host[0]), _tf_f64(self.first_step)))
             if tab.controller == "tsit5":
                 # tsit5.py:92-98: _select_initial_step computes its own f0 and the state f0 is evaluated
                 # again (with the float64 t[0]); one redundant evaluation, kept so NFE matches
                 if self.first_step is None:
-                    self.func(t_dev[0], y0_views)
+                    if brhs is None:
+                        self.func(t_dev[0], y0_views)
                     nfe += 1
 
             # ---- pinned ring for asynchronous state polls --------------------------------------------
@@ -454,6 +491,16 @@ class AdaptiveStepsizeODESolver(object):
             def run_attempt():
                 """Enqueue one attempt: stage i -> func -> ... -> finalize (+ dense output).  No kernel argument
                 depends on dt / accept / the output cursor: they live in the device state."""
+                if brhs is not None:
+                    item_ = seg.item
+                    check(rk_stage(handle, 0, None))
+                    rhs_eval(tstage.data_ptr(), S, Kb[0])
+                    for i in range(1, nk - 1):
+                        check(lib.b2ode_rk_stage_rhs(handle, i, Kp[i - 1], C.byref(rd), C.c_void_p(Kb[i].data_ptr())))
+                    if not tab.fsal:
+                        check(rk_stage(handle, nk - 1, Kp[nk - 2]))
+                    check(rk_finalize(handle, Kp[nk - 2]))
+                    return Kb
                 live = set()
                 ks = []           # every k of the attempt stays referenced until its last reader is enqueued
                 check(rk_stage(handle, 0, None))
@@ -529,7 +576,7 @@ class AdaptiveStepsizeODESolver(object):
             final = known
             self.stats = dict(n_accepted=int(final.n_acc), n_rejected=int(final.n_rej), nfe=nfe,
                               attempts_enqueued=n_enq, status=int(final.status), cuda_graph=graph is not None,
-                              fused_rhs=False)
+                              fused_rhs=False, stage_rhs=brhs is not None)
             last_stats.clear()
             last_stats.update(self.stats)
             if final.status:
@@ -692,7 +739,7 @@ class FixedGridODESolver(object):
         from .rhs import BuiltinRHS
         base = getattr(self.func, "_b2ode_base", None)
         if (self.fused_rhs and isinstance(base, BuiltinRHS) and seg.nseg == 1 and len(seg.shapes[0]) >= 1
-                and seg.shapes[0][-1] == base.dim and seg.lens[0] > 0):
+                and seg.shapes[0][-1] % base.dim == 0 and seg.lens[0] > 0):
             n_traj = seg.lens[0] // base.dim
             j0 = np.zeros(n_steps + 1, dtype=np.int32)
             ends = np.zeros(max(n_steps, 1), dtype=np.uint8)
