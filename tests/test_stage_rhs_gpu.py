@@ -19,7 +19,7 @@ def tfd():
 
 
 @pytest.mark.parametrize("method,kw", [("dopri5", {}), ("dopri8", dict(rtol=1e-9, atol=1e-9)), ("bosh3", dict(rtol=1e-5, atol=1e-7)),
-                                       ("tsit5", dict(rtol=1e-3, atol=1e-5)), ("adaptive_heun", dict(rtol=1e-4, atol=1e-6))])
+                                       ("tsit5", dict(rtol=1e-2, atol=1e-2)), ("adaptive_heun", dict(rtol=1e-4, atol=1e-6))])
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
 def test_stage_rhs_lorenz_equals_func_path(method, kw, dtype):
     rng = np.random.default_rng(2)
