@@ -217,15 +217,8 @@ struct Mailbox {
     unsigned long long local_seq;   // exchanges completed by the owning rank; persists across solves
     unsigned long long ll_seq;      // exchanges of the persistent fused kernel so far; persists across solves
     unsigned long long pad[6];
-    // ---- receive area of the persistent fused kernel (b2ode_fused.cu): every block of every rank writes its 16-byte
-    // tagged partial into fused_part[parity][source rank][block] of EVERY rank's mailbox and bumps fused_ctr[source rank]
-    // there (a remote atomic over NVLink) -- one hop, no relay through a leader block
-    unsigned fused_base[B2ODE_MAXPEERS];                 // arrivals from source rank s before the current launch (local bookkeeping)
-    unsigned long long pad2[4];
-    struct alignas(128) Ctr {
-        unsigned v;
-        unsigned pad[31];
-    } fused_ctr[B2ODE_MAXPEERS];                          // one 128-byte line per source rank
+    // receive area of the persistent fused kernel (b2ode_fused.cu): every block of rank s stores its 16-byte tagged partial
+    // of exchange `seq` into fused_part[seq & 1][s][block] of every other rank's mailbox (plain NVLink stores, no atomics)
     unsigned long long fused_part[2][B2ODE_MAXPEERS][kMaxFusedBlocks][2];
 };
 

@@ -26,7 +26,7 @@ __device__ unsigned long long g_fused_trace[2 * kTraceAttempts * kTracePhases];
 // to float above BAR.SYNC)
 #define FTRACE_DEP(att, ph, dep)                                                                                 \
     do {                                                                                                         \
-        if ((unsigned)(dep) != 0x7ffffff3u && (threadIdx.x == 0 || threadIdx.x == blockDim.x - 32) &&            \
+        if ((unsigned)(dep) != 0x7ffffff3u && (threadIdx.x == 0 || threadIdx.x == blockDim.x - 32) /* single-GPU traces: the control warp is the last warp */ &&            \
             (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1) && (att) >= 8 && (att) < 8 + kTraceAttempts)        \
             g_fused_trace[((blockIdx.x == 0 ? 0 : 1) * kTraceAttempts + ((att)-8)) * kTracePhases + (ph)] = clock64(); \
     } while (0)
@@ -60,13 +60,8 @@ extern "C" int b2ode_debug_fused_trace(unsigned long long *out) {
 // ------------------------------------------------------------------------------------------------
 struct FusedParams {
     b2ode_state *st;
-    // exchange plumbing (see control_allreduce).  Without a shared-step group: one "rank" whose receive area is the
-    // caller's workspace.  With a group: the receive areas live in the peer-mapped mailboxes.
-    int xnranks, xrank;
-    int xpeers, xstride;                          // dimensions of the partial arrays: [2][xpeers][xstride][2]
-    int xgrid[B2ODE_MAXPEERS];                    // grid size of every rank's kernel
-    unsigned *xctr[B2ODE_MAXPEERS];               // rank r's counters (32 unsigned = 128 bytes apart, one per source rank)
-    unsigned long long *xpart[B2ODE_MAXPEERS];    // rank r's partial arrays
+    unsigned long long *part2;   // [2][gridDim.x][2] u64: 16-byte tagged block partials, double buffered by exchange parity
+    unsigned *ctr;               // monotonically increasing arrival counter (zeroed by the host before the launch)
     const void *y0;
     void *out;
     // optional streaming of the solution to the host: `progress` counts output rows completed over all blocks, `host_mark`
@@ -187,8 +182,18 @@ __device__ __forceinline__ Pay ll_wait4(const unsigned long long *src, unsigned 
 __device__ __forceinline__ void named_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void named_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
+// The polls below use WEAK loads (ld.global.cg: they overlap; strong loads of one warp do not), and to the PTX memory
+// model a weak load of an unchanged address may be assumed to return the same value again: ptxas is entitled to hoist such
+// a load out of a polling loop, or to drop the loop ("it must terminate, so its condition holds") -- and does, once the loop
+// is simple enough.  Every polling round therefore offsets its addresses by this value, which is always 0 but which ptxas
+// cannot know: the loads are loop-variant and have to be issued again.
+__device__ __forceinline__ unsigned long long opaque_zero() {
+    unsigned long long c;
+    asm volatile("mov.u64 %0, %%clock64;" : "=l"(c));
+    return c >> 63;
+}
+
 constexpr int kGatherPerLane = 5;        // 160 blocks gathered with every poll in flight (148 SMs x 1 block)
-constexpr int kBarPartials = 1, kBarDecision = 2, kBarRows = 3, kBarRowsReady = 4;
 
 // 16-byte message: {a | tag, b | tag}.  The 4-bit tag (exchange number mod 16) replaces the four lowest mantissa bits of
 // both words (2^-48 relative: below the rounding noise of the sums it carries) so that ONE 16-byte load both fetches and
@@ -212,7 +217,142 @@ __device__ __forceinline__ Pay pay_unpack16(unsigned long long w0, unsigned long
     return r;
 }
 
-// Called by the CONTROL warp (all 32 lanes, convergent) once the compute warps' partials are in sh_part[0 .. ncw).
+// Gather the G 16-byte tagged partials in `slots` (local memory; written by this GPU's blocks or, over NVLink, by a peer's)
+// with weak L2 loads, all of a lane's loads in flight together; partials whose tag is not `seq` yet are re-read, round by
+// round, until they are.  Called by a whole warp; returns the total in every lane (fixed order -> deterministic).
+// NPL = loads in flight per lane: 5 for the control warp (147 blocks in one round), 2 for the compute warps' gather of a
+// peer's partials (their registers are full of trajectory state and they are in no hurry).
+template <int MODE, int NPL, bool BUTTERFLY = true>
+__device__ __forceinline__ Pay gather_tagged(const unsigned long long *slots, int G, unsigned seq) {
+    const int lane = threadIdx.x & 31;
+    Pay acc = pay_identity<MODE>();
+    for (int base = 0; base < G; base += 32 * NPL) {
+        unsigned long long g0[NPL], g1[NPL];
+        unsigned pending = 0u;
+#pragma unroll
+        for (int q = 0; q < NPL; ++q) {
+            g0[q] = g1[q] = 0ull;
+            if (base + lane + 32 * q < G) pending |= 1u << q;
+        }
+        const unsigned mine = pending;
+        while (pending) {
+            const unsigned long long *sl = slots + (size_t)(base + lane) * 2 + opaque_zero();
+#pragma unroll
+            for (int q = 0; q < NPL; ++q)
+                if ((pending >> q) & 1u)
+                    asm volatile("ld.global.cg.v2.u64 {%0, %1}, [%2];" : "=l"(g0[q]), "=l"(g1[q]) : "l"(sl + 64 * q) : "memory");
+#pragma unroll
+            for (int q = 0; q < NPL; ++q)
+                if (((pending >> q) & 1u) && pay_valid16(g0[q], g1[q], seq)) pending &= ~(1u << q);
+        }
+#pragma unroll
+        for (int q = 0; q < NPL; ++q)
+            if ((mine >> q) & 1u) acc = pay_combine<MODE>(acc, pay_unpack16(g0[q], g1[q]));      // fixed order
+    }
+    return BUTTERFLY ? pay_warp_reduce<MODE>(acc) : acc;      // (without: this lane's share, blocks lane, lane + 32, ...)
+}
+
+// shared scratch of one block
+struct FusedShared {
+    Pay part[16];                  // compute-warp partials
+    unsigned long long rlane[B2ODE_MAXPEERS][32][2];   // per-lane sums of the OTHER ranks' partials (comm warp -> control warp)
+    Pay tot;                       // totals of the initial-step reductions (read by every thread)
+    struct {
+        double dt_next;
+        int accept, done;
+        unsigned status;
+    } ctl;                         // what the control warp hands to the compute warps
+};
+
+constexpr int kBarPartials = 1, kBarDecision = 2, kBarRows = 3, kBarRowsReady = 4, kBarRemote = 5;
+
+// Called by the COMM warp (blocks of a shared-step group have one: a second service warp without trajectories): fetch the
+// partials every peer wrote into this rank's mailbox over NVLink and leave, per source rank, each LANE's share (blocks
+// lane, lane + 32, ... summed in that order) in shared memory; the control warp folds the ranks in rank order and does the
+// one butterfly.  The comm warp starts polling the moment an exchange begins, so the peers' data is fetched while the
+// control warp is still in the intra-GPU phase: the NVLink hop (~2070 cycles) hides behind it.  Up to four source ranks
+// (20 weak loads per lane) are in flight together; partials whose tag is not `seq` yet are re-read, round by round.
+template <int MODE>
+__device__ __forceinline__ void remote_gather(const FusedParams &p, FusedShared &sh, unsigned seq) {
+    const int nranks = p.comm.nranks, lane = threadIdx.x & 31, rank = p.comm.rank;
+#ifndef B2ODE_COMM_RG
+#define B2ODE_COMM_RG 3
+#endif
+    constexpr int RG = B2ODE_COMM_RG;                       // source ranks per batch
+    constexpr int NL = RG * kGatherPerLane;                 // loads in flight per lane
+    const unsigned long long *base = &p.comm.box[rank]->fused_part[seq & 1u][0][0][0] + (size_t)lane * 2;
+    const unsigned tag = seq & 15u;
+    for (int i0 = 0; i0 < nranks - 1; i0 += RG) {
+        // The poll loop is INSTRUCTION bound (one warp, every load followed by its validation), so it is kept minimal: one
+        // pointer per source rank, loads at immediate offsets and without predicates -- a slot past the source's grid, or
+        // of a rank past the group, is just memory of the mailbox (fused_part has kMaxFusedBlocks >= 32 * kGatherPerLane
+        // slots per rank) whose content is ignored -- and a two-instruction tag test per load.  Slots that were valid a
+        // round ago stay valid (a buffer is rewritten two exchanges later), so every round simply reloads everything.
+        unsigned long long g0[NL], g1[NL];
+        const unsigned long long *ptr[RG];
+        unsigned mine = 0u;
+#pragma unroll
+        for (int r = 0; r < RG; ++r) {
+            const int i = i0 + r;
+            const bool ok = i < nranks - 1;
+            const int src = ok ? (i < rank ? i : i + 1) : rank;
+            const int G = ok ? p.comm.grid_of[src] : 0;
+            ptr[r] = base + (size_t)src * (kMaxFusedBlocks * 2);
+            asm volatile("" : "+l"(ptr[r]));                 // (keep it in a register: do not recompute it per load)
+#pragma unroll
+            for (int q = 0; q < kGatherPerLane; ++q)
+                if (lane + 32 * q < G) mine |= 1u << (r * kGatherPerLane + q);
+        }
+        unsigned got;
+        do {
+            const unsigned long long z = opaque_zero();
+#pragma unroll
+            for (int r = 0; r < RG; ++r)
+#pragma unroll
+                for (int q = 0; q < kGatherPerLane; ++q)
+                    asm volatile("ld.global.cg.v2.u64 {%0, %1}, [%2];"
+                                 : "=l"(g0[r * kGatherPerLane + q]), "=l"(g1[r * kGatherPerLane + q])
+                                 : "l"(ptr[r] + z + 64 * q)
+                                 : "memory");
+            got = 0u;
+#pragma unroll
+            for (int k = 0; k < NL; ++k) {
+                const unsigned t = (((unsigned)g0[k] ^ tag) | ((unsigned)g1[k] ^ tag)) & 15u;
+                got |= (t == 0u) ? (1u << k) : 0u;
+            }
+        } while ((got & mine) != mine);
+#pragma unroll
+        for (int r = 0; r < RG; ++r) {
+            const int i = i0 + r;
+            if (i >= nranks - 1) continue;
+            const int src = i < rank ? i : i + 1;
+            Pay acc = pay_identity<MODE>();
+#pragma unroll
+            for (int q = 0; q < kGatherPerLane; ++q)
+                if ((mine >> (r * kGatherPerLane + q)) & 1u)
+                    acc = pay_combine<MODE>(acc, pay_unpack16(g0[r * kGatherPerLane + q], g1[r * kGatherPerLane + q]));   // fixed order
+            const int G = p.comm.grid_of[src];
+            for (int b = lane + 32 * kGatherPerLane; b < G; b += 32) {       // grids beyond 32 * kGatherPerLane blocks
+                const unsigned long long *sl = base + (size_t)src * (kMaxFusedBlocks * 2) + (size_t)(b - lane) * 2;
+                unsigned long long a0, a1;
+                do {
+                    asm volatile("ld.global.cg.v2.u64 {%0, %1}, [%2];" : "=l"(a0), "=l"(a1) : "l"(sl + opaque_zero()) : "memory");
+                } while (!pay_valid16(a0, a1, seq));
+                acc = pay_combine<MODE>(acc, pay_unpack16(a0, a1));
+            }
+#ifdef B2ODE_COMM_RTOT
+            acc = pay_warp_reduce<MODE>(acc);                // A/B variant: the comm warp does one butterfly per source rank
+#endif
+            unsigned long long ab = (unsigned long long)__double_as_longlong(acc.a);
+            if (acc.a != acc.a) ab = 0x7ff8000000000000ull;
+            sh.rlane[src][lane][0] = (ab & 0x7fffffffffffffffull) | ((unsigned long long)(acc.flag & 1u) << 63);
+            sh.rlane[src][lane][1] = acc.b;
+        }
+    }
+    asm volatile("bar.arrive %0, %1;" ::"r"(kBarRemote), "r"(64) : "memory");
+}
+
+// Called by the CONTROL warp (all 32 lanes, convergent) once the compute warps' partials are in sh.part[0 .. ncw).
 // `epoch` counts the exchanges of this launch (1, 2, ...).  Returns the group-wide totals in every lane of every block of
 // every rank, bit-identical everywhere.
 //
@@ -220,78 +360,73 @@ __device__ __forceinline__ Pay pay_unpack16(unsigned long long w0, unsigned long
 //   * a gpu- or sys-scope STRONG load (ld.relaxed / acquire / volatile, atomic read) costs 500-700 cycles and the strong loads
 //     of one warp do not overlap: a flag protocol that polls k words pays k round trips per poll; a leader gathering 147
 //     messages with 5 polls per lane pays ~10 serialised round trips (7.3k cycles per all-reduce; two-level 13.4k);
-//   * one atomic arrival counter + one polled word: 1.9k; weak ld.global.cg loads pipeline;
+//   * one atomic arrival counter + one polled word: 1.9k; weak ld.global.cg loads always read the L2 and pipeline;
 //   * a fence (red.release) in front of the arrival costs a MEMBAR.GPU = the store's round trip;
-//   * one NVLink hop (remote write -> visible to a poll of local memory) is ~2070 cycles whatever the instructions, plus ~520
-//     per extra polled word.
-//   * weak ld.global.cg loads always read the L2 and overlap, but POLLING the data itself with them (no counter) measured
-//     slower than counter + one fetch (3.7k vs 3.5k cycles on one GPU): every retry round is a full L2 round trip.
-// Hence a FLAT, one-hop exchange: every block stores its 16-byte tagged partial into part[parity][my rank][my block] of
-// EVERY rank (its own included; remote ones over NVLink) and bumps that rank's arrival counter for my rank with a RELAXED
-// atomic (no fence: a reader that finds a stale tag re-reads that one partial with strong loads); every block then spins
-// on the arrival counters of its own rank (lane q: source rank q, ONE strong load per poll) and fetches all partials of
-// all ranks from LOCAL memory with weak L2 loads that overlap, reducing them in one fixed (rank, block) order.
+//   * one NVLink hop (remote write -> visible to a poll of local memory) is ~2070 cycles whatever the instructions, +520 per
+//     extra polled word; REMOTE atomics on one address serialise badly (147 blocks x 7 peers bumping per-source counters:
+//     11.5 us per attempt at 8 GPUs against 4.2 us on one); an intra-GPU all-reduce followed by one message per peer puts
+//     the hop behind the whole local phase (+3.1 us per attempt at 2 GPUs).
+// Hence: every block stores its 16-byte tagged partial LOCALLY and, over NVLink, into EVERY peer's mailbox (plain stores: the
+// tag validates the data, no flag, no remote atomic).  Inside the GPU one RELAXED arrival atomic orders nothing (no fence: a
+// reader that finds a stale tag re-reads), lane 0 spins on the counter with one strong load per poll, then all partials
+// are fetched with weak loads that overlap.  The peers' partials, which travel during the local phase, are gathered by a
+// dedicated COMM warp (remote_gather) and handed to the control warp through shared memory; ranks combine in rank order.
 template <int MODE>
-__device__ __forceinline__ Pay control_allreduce(const FusedParams &p, const Pay *sh_part, int ncw, unsigned epoch, unsigned seq0,
-                                                 unsigned base_q /* lane q: arrivals from rank q before this launch */, int att = -1) {
+__device__ __forceinline__ Pay control_allreduce(const FusedParams &p, FusedShared &sh, int ncw, unsigned epoch, unsigned seq0,
+                                                 int att = -1) {
     const int lane = threadIdx.x & 31;
-    Pay x = (lane < ncw) ? sh_part[lane] : pay_identity<MODE>();
+    Pay x = (lane < ncw) ? sh.part[lane] : pay_identity<MODE>();
     x = pay_warp_reduce<MODE>(x);                                         // block total, all lanes
     FTRACE_DEP(att, 2, __double_as_longlong(x.a));
-    const int nranks = p.xnranks, rank = p.xrank;
-    if (nranks == 1 && gridDim.x == 1) return x;
+    const int nranks = p.comm.nranks > 1 ? p.comm.nranks : 1, rank = p.comm.rank;
+    const int G = (int)gridDim.x;
     // buffer parity follows the PERSISTENT sequence number, so the alternation continues across launches: a rank that has
     // already started the next solve cannot overwrite a partial a slower rank has not read yet
     const unsigned seq = seq0 + epoch, par = seq & 1u;
     unsigned long long w0, w1;
     pay_pack16(x, seq, w0, w1);
-    if (lane < nranks) {                                                  // lane q publishes to rank q
-        unsigned long long *dst = p.xpart[lane] + (((size_t)par * p.xpeers + rank) * p.xstride + blockIdx.x) * 2;
+    if (nranks > 1 && lane < nranks && lane != rank) {                    // lane q: this block's partial -> rank q, over NVLink
+        unsigned long long *dst = &p.comm.box[lane]->fused_part[par][rank][blockIdx.x][0];
         asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(dst), "l"(w0), "l"(w1) : "memory");
-        asm volatile("red.relaxed.sys.global.add.u32 [%0], 1;" ::"l"(p.xctr[lane] + 32 * rank) : "memory");
     }
-    // arrivals of source rank q at MY counters: lane q polls one word
-    if (lane < nranks) {
-        const unsigned target = base_q + epoch * (unsigned)p.xgrid[lane];
-        const unsigned *c = p.xctr[rank] + 32 * lane;
-        unsigned v;
-        do {
-            asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(c) : "memory");
-        } while ((int)(v - target) < 0);
-    }
-    __syncwarp();
-    FTRACE(att, 3);
-    // every partial of every rank now sits in local memory: weak .cg loads (they overlap), fixed (rank, block) order
-    const unsigned long long *mine = p.xpart[rank] + (size_t)par * p.xpeers * p.xstride * 2;
-    Pay acc = pay_identity<MODE>();
-    for (int s = 0; s < nranks; ++s) {
-        const unsigned long long *src = mine + (size_t)s * p.xstride * 2;
-        const int G = p.xgrid[s];
-        unsigned long long g0[kGatherPerLane], g1[kGatherPerLane];
-#pragma unroll
-        for (int q = 0; q < kGatherPerLane; ++q) {
-            const int b = lane + 32 * q;
-            const unsigned long long *a = src + (size_t)(b < G ? b : 0) * 2;
-            asm volatile("ld.global.cg.v2.u64 {%0, %1}, [%2];" : "=l"(g0[q]), "=l"(g1[q]) : "l"(a) : "memory");
-        }
-#pragma unroll
-        for (int q = 0; q < kGatherPerLane; ++q) {
-            const int b = lane + 32 * q;
-            if (b < G) {
-                while (!pay_valid16(g0[q], g1[q], seq))                   // rare: the arrival overtook the data
-                    asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(g0[q]), "=l"(g1[q]) : "l"(src + (size_t)b * 2) : "memory");
-                acc = pay_combine<MODE>(acc, pay_unpack16(g0[q], g1[q]));
-            }
-        }
-        for (int b = lane + 32 * kGatherPerLane; b < G; b += 32) {         // grids beyond 32 * kGatherPerLane blocks
-            unsigned long long a0, a1;
+    if (G > 1) {
+        unsigned long long *slots = p.part2 + (size_t)par * G * 2;
+        if (lane == 0) {
+            asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(slots + (size_t)blockIdx.x * 2), "l"(w0), "l"(w1) : "memory");
+            asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(p.ctr) : "memory");
+            const unsigned target = epoch * (unsigned)G;
+            unsigned v;
             do {
-                asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(a0), "=l"(a1) : "l"(src + (size_t)b * 2) : "memory");
-            } while (!pay_valid16(a0, a1, seq));
-            acc = pay_combine<MODE>(acc, pay_unpack16(a0, a1));
+                asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p.ctr) : "memory");
+            } while ((int)(v - target) < 0);
         }
+        __syncwarp();
+        FTRACE(att, 3);
+        x = gather_tagged<MODE, kGatherPerLane, false>(slots, G, seq);    // this LANE's share of this GPU's partials
+    } else {
+        x = (lane == 0) ? pay_unpack16(w0, w1) : pay_identity<MODE>();   // (the transported form, like everybody else's)
     }
-    return pay_warp_reduce<MODE>(acc);
+    if (nranks == 1) return pay_warp_reduce<MODE>(x);
+#ifdef B2ODE_COMM_RTOT
+    x = pay_warp_reduce<MODE>(x);
+#endif
+    asm volatile("bar.sync %0, %1;" ::"r"(kBarRemote), "r"(64) : "memory");                    // the comm warp has the peers' lane sums
+    Pay tot = pay_identity<MODE>();
+    for (int q = 0; q < nranks; ++q) {                                     // rank order, per lane: identical on every GPU
+        Pay v = x;
+        if (q != rank) {
+            const unsigned long long a = sh.rlane[q][lane][0];
+            v.flag = (unsigned)(a >> 63);
+            v.a = __longlong_as_double((long long)(a & 0x7fffffffffffffffull));
+            v.b = sh.rlane[q][lane][1];
+        }
+        tot = (q == 0) ? v : pay_combine<MODE>(tot, v);
+    }
+#ifdef B2ODE_COMM_RTOT
+    return tot;
+#else
+    return pay_warp_reduce<MODE>(tot);                                     // one butterfly for the whole group
+#endif
 }
 
 // The controller of the persistent kernel (one segment, the reference's controller: misc.py:250-287), written for the
@@ -323,20 +458,6 @@ __device__ __forceinline__ CtrlDecision ctrl_fast(const CtrlParams &c, double ss
     return d;
 }
 
-// what the control warp hands to the compute warps of its block
-struct CtlOut {
-    double dt_next;
-    int accept, done;
-    unsigned status;
-};
-
-// shared scratch of one block
-struct FusedShared {
-    Pay part[16];          // compute-warp partials
-    Pay tot;               // totals of the initial-step reductions (read by every thread)
-    CtlOut ctl;
-};
-
 // ------------------------------------------------------------------------------------------------
 // the persistent solve.  Block = NCW compute warps (one trajectory per thread) + 1 control warp (the last one).
 // ------------------------------------------------------------------------------------------------
@@ -346,16 +467,17 @@ __global__ void __launch_bounds__(MAXT) k_fused_adaptive(const __grid_constant__
     constexpr int D = RHS::D;
     __shared__ FusedShared sh;
     __shared__ T sw[RHS::kSmem];
-    constexpr int kDenseRows = 3;
+    constexpr int kDenseRows = (3 * (MAXT - 32) * D * (int)sizeof(T) + (int)sizeof(FusedShared) + RHS::kSmem * (int)sizeof(T) + 256 <= 48 * 1024) ? 3 : 2;
     __shared__ __align__(16) T s_rows[kDenseRows][(MAXT - 32) * D];     // dense-output rows of the step, waiting for the decision
     const int nthreads = blockDim.x;
-    const int ncw = (nthreads >> 5) - 1;                 // compute warps
+    const bool grouped = p.comm.nranks > 1;
+    const int nsvc = grouped ? 2 : 1;                    // service warps: control (+ comm with a shared-step group)
+    const int ncw = (nthreads >> 5) - nsvc;              // compute warps
+    const int nloc = 32 * (ncw + 1);                     // compute warps + control warp (barriers the comm warp is not part of)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool is_control = warp == ncw;
     // persistent sequence / arrival bases of the cross-GPU receive area (they survive across solves in the mailbox)
-    const bool grouped = p.comm.nranks > 1;
     const unsigned ll_base = grouped ? (unsigned)p.comm.box[p.comm.rank]->ll_seq : 0u;
-    const unsigned base_q = (grouped && lane < p.comm.nranks) ? p.comm.box[p.comm.rank]->fused_base[lane] : 0u;
     if (RHS::kSmem > 1) {
         const int nw = (int)p.rhs[0] * 5 + 2;
         for (int q = threadIdx.x; q < nw && q < RHS::kSmem; q += nthreads) sw[q] = ((const T *)p.rhs_data)[q];
@@ -373,8 +495,8 @@ __global__ void __launch_bounds__(MAXT) k_fused_adaptive(const __grid_constant__
             dt = p.first_step;
         } else {
             // misc.py:226-247 with the two reductions of _select_initial_step
-            named_sync(kBarPartials, nthreads);
-            Pay r = control_allreduce<1>(p, sh.part, ncw, ++epoch, ll_base, base_q);
+            named_sync(kBarPartials, nloc);
+            Pay r = control_allreduce<1>(p, sh, ncw, ++epoch, ll_base);
             if (lane == 0) sh.tot = r;
             named_arrive(kBarDecision, nthreads);
             Partial tot;
@@ -383,8 +505,8 @@ __global__ void __launch_bounds__(MAXT) k_fused_adaptive(const __grid_constant__
             tot.v[2] = tot.v[3] = 0.0;
             T d1max;
             const T h0 = init_h0<T>(p.c, &tot, 1, &d1max);
-            named_sync(kBarPartials, nthreads);
-            r = control_allreduce<1>(p, sh.part, ncw, ++epoch, ll_base, base_q);
+            named_sync(kBarPartials, nloc);
+            r = control_allreduce<1>(p, sh, ncw, ++epoch, ll_base);
             if (lane == 0) sh.tot = r;
             named_arrive(kBarDecision, nthreads);
             tot.v[0] = r.a;
@@ -408,8 +530,8 @@ __global__ void __launch_bounds__(MAXT) k_fused_adaptive(const __grid_constant__
             const double t1_acc = t_cur + dt;
             int c2 = cur;
             while (c2 < n_out && __ldg(t_out + c2) <= t1_acc) ++c2;             // advance(): `while next_t > t1`
-            if (c2 > cur) named_arrive(kBarRows, nthreads);                    // the previous step's rows have been copied out
-            named_sync(kBarPartials, nthreads);                                // the compute warps' partials are in
+            if (c2 > cur) named_arrive(kBarRows, nloc);                    // the previous step's rows have been copied out
+            named_sync(kBarPartials, nloc);                                // the compute warps' partials are in
             if (late_rows) {
                 // a long step's extra rows were stored by the compute warps themselves, before this barrier
                 __threadfence();
@@ -423,7 +545,7 @@ __global__ void __launch_bounds__(MAXT) k_fused_adaptive(const __grid_constant__
                 late_rows = 0;
             }
             FTRACE_DEP(att, 1, sh.part[0].flag);
-            const Pay r = control_allreduce<0>(p, sh.part, ncw, ++epoch, ll_base, base_q, att);
+            const Pay r = control_allreduce<0>(p, sh, ncw, ++epoch, ll_base, att);
             FTRACE_DEP(att, 4, __double_as_longlong(r.a));
             Partial tot;
             tot.v[0] = r.a;
@@ -450,7 +572,7 @@ __global__ void __launch_bounds__(MAXT) k_fused_adaptive(const __grid_constant__
             }
             named_arrive(kBarDecision, nthreads);
             FTRACE_DEP(att, 5, __double_as_longlong(dec.dt_next));
-            if (c2 > cur) named_sync(kBarRowsReady, nthreads);                  // the compute warps' rows are in shared memory
+            if (c2 > cur) named_sync(kBarRowsReady, nloc);                  // the compute warps' rows are in shared memory
             if (adv && c2 > cur) {
                 // The accepted step's dense-output rows wait in shared memory (written by the compute warps before the
                 // decision barrier): this otherwise idle warp streams them to the solution slab with 16-byte stores while
@@ -530,9 +652,38 @@ __global__ void __launch_bounds__(MAXT) k_fused_adaptive(const __grid_constant__
             *p.st = z;
         }
         if (blockIdx.x == 0 && grouped) {
-            Mailbox *mb = p.comm.box[p.comm.rank];
-            if (lane == 0) mb->ll_seq = (unsigned long long)(ll_base + epoch);
-            if (lane < p.comm.nranks) mb->fused_base[lane] = base_q + epoch * (unsigned)p.xgrid[lane];
+            if (lane == 0) p.comm.box[p.comm.rank]->ll_seq = (unsigned long long)(ll_base + epoch);
+        }
+        return;
+    }
+
+    if (warp == ncw + 1) {
+        // ================================ comm warp (shared-step groups only) ===========================
+        // mirrors the sequence of exchanges: per exchange, gather every peer's partials, then wait for the decision
+        unsigned epoch = 0;
+        double t_cur = p.t_start, dt;
+        if (p.have_first_step) {
+            dt = p.first_step;
+        } else {
+            remote_gather<1>(p, sh, ll_base + (++epoch));
+            named_sync(kBarDecision, nthreads);
+            Partial tot;
+            tot.v[0] = sh.tot.a;
+            tot.v[1] = __longlong_as_double((long long)sh.tot.b);
+            tot.v[2] = tot.v[3] = 0.0;
+            T d1max;
+            const T h0 = init_h0<T>(p.c, &tot, 1, &d1max);
+            remote_gather<1>(p, sh, ll_base + (++epoch));
+            named_sync(kBarDecision, nthreads);
+            tot.v[0] = sh.tot.a;
+            dt = (double)init_dt<T>(p.c, &tot, 1, h0, d1max);
+        }
+        int done = (n_out <= 1) ? 1 : 0;
+        if (!done && !(t_cur + dt > t_cur)) done = 1;
+        while (!done) {
+            remote_gather<0>(p, sh, ll_base + (++epoch));
+            named_sync(kBarDecision, nthreads);
+            done = sh.ctl.done;
         }
         return;
     }
@@ -562,11 +713,13 @@ __global__ void __launch_bounds__(MAXT) k_fused_adaptive(const __grid_constant__
         }
     };
     // hand this warp's share to the control warp; do not wait
+    unsigned xepoch = 0;              // exchanges so far (the control warp counts the same)
     auto contribute = [&](const Pay &mine, auto mode) {
         constexpr int MODE = decltype(mode)::value;
         const Pay w = pay_warp_reduce<MODE>(mine);
         if (lane == 0) sh.part[warp] = w;
-        named_arrive(kBarPartials, nthreads);
+        named_arrive(kBarPartials, nloc);
+        ++xepoch;
     };
     double t_cur = p.t_start;
     rhs((T)t_cur, y, f0);                                                    // dopri5.py:71
@@ -757,7 +910,7 @@ __global__ void __launch_bounds__(MAXT) k_fused_adaptive(const __grid_constant__
         // the rows wait in shared memory, laid out exactly like the block's contiguous chunk of an output row
         const bool blk_out = c2 > cur;                                        // uniform over the grid
         if (blk_out) {
-            named_sync(kBarRows, nthreads);                                   // the control warp has copied the previous step's rows out
+            named_sync(kBarRows, nloc);                                   // the control warp has copied the previous step's rows out
             if (live) {
                 T ca[D], cb[D], cc[D], cd[D];
                 fit(ca, cb, cc, cd);
@@ -772,7 +925,7 @@ __global__ void __launch_bounds__(MAXT) k_fused_adaptive(const __grid_constant__
                 }
             }
         }
-        if (blk_out) named_arrive(kBarRowsReady, nthreads);                   // rows handed to the control warp
+        if (blk_out) named_arrive(kBarRowsReady, nloc);                   // rows handed to the control warp
         FTRACE(att, 9);
         named_sync(kBarDecision, nthreads);                                 // the control warp's decision
         const bool accept = sh.ctl.accept != 0;
@@ -815,8 +968,8 @@ __global__ void __launch_bounds__(MAXT) k_fused_adaptive(const __grid_constant__
 // the register file, not the block size, is the limit).  A pure function of (n, device, instantiation): every rank of a
 // shared-step group computes the same geometry for every other rank's shard.
 template <typename T, typename RHS, int S, int MAXT>
-static int fused_geometry(long long n_traj, int nsm, int *ncw_out, int *grid_out) {
-    constexpr int kMaxNcw = MAXT / 32 - 1;
+static int fused_geometry(long long n_traj, int nsm, int nsvc, int *ncw_out, int *grid_out) {
+    const int kMaxNcw = MAXT / 32 - nsvc;
     long long per_block = (n_traj + nsm - 1) / nsm;
     int ncw = (int)((per_block + 31) / 32);
     if (ncw < 1) ncw = 1;
@@ -824,7 +977,7 @@ static int fused_geometry(long long n_traj, int nsm, int *ncw_out, int *grid_out
     for (; ncw >= 1; --ncw) {
         int per_sm = 0;
         const int grid = (int)((n_traj + (long long)ncw * 32 - 1) / ((long long)ncw * 32));
-        B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused_adaptive<T, RHS, S, MAXT>, 32 * (ncw + 1), 0));
+        B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused_adaptive<T, RHS, S, MAXT>, 32 * (ncw + nsvc), 0));
         if (grid <= per_sm * nsm) {
             *ncw_out = ncw;
             *grid_out = grid;
@@ -842,11 +995,11 @@ static int fused_launch(const FusedParams &p_in, long long n_traj, cudaStream_t 
     B2_CUDA(cudaGetDevice(&dev));
     B2_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
     B2_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
-    constexpr int kMaxNcw = MAXT / 32 - 1;
     if (capacity) {
+        // (reported for the geometry with both service warps, so that a batch that fits alone also fits in a group)
         long long best = 0;
-        for (int ncw = kMaxNcw; ncw >= 1 && coop; --ncw) {
-            B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused_adaptive<T, RHS, S, MAXT>, 32 * (ncw + 1), 0));
+        for (int ncw = MAXT / 32 - 2; ncw >= 1 && coop; --ncw) {
+            B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused_adaptive<T, RHS, S, MAXT>, 32 * (ncw + 2), 0));
             const long long cap = (long long)per_sm * nsm * ncw * 32;
             if (cap > best) best = cap;
         }
@@ -855,28 +1008,26 @@ static int fused_launch(const FusedParams &p_in, long long n_traj, cudaStream_t 
     }
     if (!coop) return b2_fail(B2ODE_ESTATE, "device does not support cooperative launch");
     FusedParams p = p_in;
+    const int nsvc = p.comm.nranks > 1 ? 2 : 1;        // control warp (+ comm warp with a shared-step group)
     int ncw = 0, grid = 0;
     {
-        const int rc = fused_geometry<T, RHS, S, MAXT>(n_traj, nsm, &ncw, &grid);
+        const int rc = fused_geometry<T, RHS, S, MAXT>(n_traj, nsm, nsvc, &ncw, &grid);
         if (rc) return rc;
     }
     if (p.comm.nranks > 1) {
         for (int r = 0; r < p.comm.nranks; ++r) {
             int ncw_r = 0, grid_r = 0;
-            const int rc = fused_geometry<T, RHS, S, MAXT>(n_traj_rank[r], nsm, &ncw_r, &grid_r);
+            const int rc = fused_geometry<T, RHS, S, MAXT>(n_traj_rank[r], nsm, nsvc, &ncw_r, &grid_r);
             if (rc) return rc;
             if (grid_r > kMaxFusedBlocks)
                 return b2_fail(B2ODE_ENOMEM, "rank %d needs %d blocks, the group mailbox holds %d", r, grid_r, kMaxFusedBlocks);
-            p.xgrid[r] = grid_r;
+            p.comm.grid_of[r] = grid_r;
         }
-        if (p.xgrid[p.comm.rank] != grid) return b2_fail(B2ODE_ESTATE, "inconsistent shard size for this rank");
-    } else {
-        p.xgrid[0] = grid;
-        p.xstride = grid;
+        if (p.comm.grid_of[p.comm.rank] != grid) return b2_fail(B2ODE_ESTATE, "inconsistent shard size for this rank");
     }
     void *args[] = {(void *)&p};
     const int slot = b2_timing_begin(6 /* B2_FAM_FUSED */, st);
-    B2_CUDA(cudaLaunchCooperativeKernel((const void *)k_fused_adaptive<T, RHS, S, MAXT>, dim3(grid), dim3(32 * (ncw + 1)), args, 0, st));
+    B2_CUDA(cudaLaunchCooperativeKernel((const void *)k_fused_adaptive<T, RHS, S, MAXT>, dim3(grid), dim3(32 * (ncw + nsvc)), args, 0, st));
     b2_timing_end(6, slot, st);
     b2_count_launch();
     return 0;
@@ -1005,33 +1156,22 @@ extern "C" int b2ode_fused_solve(const b2ode_adaptive_desc *desc, const b2ode_fu
     long long n_glob = n_traj;
     p.comm.rank = 0;
     p.comm.nranks = 0;
-    p.xnranks = 1;
-    p.xrank = 0;
     if (nranks > 1) {
         if (!f->mailboxes || nranks > B2ODE_MAXPEERS || f->rank < 0 || f->rank >= nranks) return b2_fail(B2ODE_EINVAL, "bad group arguments");
         n_glob = 0;
         for (int r = 0; r < nranks; ++r) {
             if (!f->mailboxes[r] || f->n_traj_rank[r] < 1) return b2_fail(B2ODE_EINVAL, "bad mailbox / shard size of rank %d", r);
             n_glob += f->n_traj_rank[r];
-            Mailbox *mb = (Mailbox *)f->mailboxes[r];
-            p.comm.box[r] = mb;
-            p.xctr[r] = &mb->fused_ctr[0].v;
-            p.xpart[r] = &mb->fused_part[0][0][0][0];
+            p.comm.box[r] = (Mailbox *)f->mailboxes[r];
         }
         if (f->n_traj_rank[f->rank] != n_traj) return b2_fail(B2ODE_EINVAL, "n_traj_rank[rank] does not match the state");
         p.comm.rank = f->rank;
         p.comm.nranks = nranks;
-        p.xnranks = nranks;
-        p.xrank = f->rank;
-        p.xpeers = B2ODE_MAXPEERS;
-        p.xstride = kMaxFusedBlocks;
-    } else {
-        // receive area = the caller's workspace: [arrival counter][progress][partials 2 x grid x 16 B], zeroed per launch
-        B2_CUDA(cudaMemsetAsync(w + 256, 0, b2ode_fused_workspace_bytes(n_traj) - 256, st));
-        p.xctr[0] = (unsigned *)w;
-        p.xpart[0] = (unsigned long long *)(w + 256);
-        p.xpeers = 1;          // xstride / xgrid[0] = the grid, filled in by the launcher
     }
+    // intra-GPU receive area = the caller's workspace: [arrival counter][row progress][partials 2 x grid x 16 B], zeroed per launch
+    B2_CUDA(cudaMemsetAsync(w + 256, 0, b2ode_fused_workspace_bytes(n_traj) - 256, st));
+    p.ctr = (unsigned *)w;
+    p.part2 = (unsigned long long *)(w + 256);
     p.c.n_global[0] = n_glob * D;
     if (desc->dtype == B2ODE_F64) return fused_dispatch_rhs<double>(p, rhs_kind, nk, n_traj, st, nullptr, f->n_traj_rank);
     if (desc->dtype == B2ODE_F32) return fused_dispatch_rhs<float>(p, rhs_kind, nk, n_traj, st, nullptr, f->n_traj_rank);
