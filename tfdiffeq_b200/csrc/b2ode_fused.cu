@@ -217,41 +217,6 @@ __device__ __forceinline__ Pay pay_unpack16(unsigned long long w0, unsigned long
     return r;
 }
 
-// Gather the G 16-byte tagged partials in `slots` (local memory; written by this GPU's blocks or, over NVLink, by a peer's)
-// with weak L2 loads, all of a lane's loads in flight together; partials whose tag is not `seq` yet are re-read, round by
-// round, until they are.  Called by a whole warp; returns the total in every lane (fixed order -> deterministic).
-// NPL = loads in flight per lane: 5 for the control warp (147 blocks in one round), 2 for the compute warps' gather of a
-// peer's partials (their registers are full of trajectory state and they are in no hurry).
-template <int MODE, int NPL, bool BUTTERFLY = true>
-__device__ __forceinline__ Pay gather_tagged(const unsigned long long *slots, int G, unsigned seq) {
-    const int lane = threadIdx.x & 31;
-    Pay acc = pay_identity<MODE>();
-    for (int base = 0; base < G; base += 32 * NPL) {
-        unsigned long long g0[NPL], g1[NPL];
-        unsigned pending = 0u;
-#pragma unroll
-        for (int q = 0; q < NPL; ++q) {
-            g0[q] = g1[q] = 0ull;
-            if (base + lane + 32 * q < G) pending |= 1u << q;
-        }
-        const unsigned mine = pending;
-        while (pending) {
-            const unsigned long long *sl = slots + (size_t)(base + lane) * 2 + opaque_zero();
-#pragma unroll
-            for (int q = 0; q < NPL; ++q)
-                if ((pending >> q) & 1u)
-                    asm volatile("ld.global.cg.v2.u64 {%0, %1}, [%2];" : "=l"(g0[q]), "=l"(g1[q]) : "l"(sl + 64 * q) : "memory");
-#pragma unroll
-            for (int q = 0; q < NPL; ++q)
-                if (((pending >> q) & 1u) && pay_valid16(g0[q], g1[q], seq)) pending &= ~(1u << q);
-        }
-#pragma unroll
-        for (int q = 0; q < NPL; ++q)
-            if ((mine >> q) & 1u) acc = pay_combine<MODE>(acc, pay_unpack16(g0[q], g1[q]));      // fixed order
-    }
-    return BUTTERFLY ? pay_warp_reduce<MODE>(acc) : acc;      // (without: this lane's share, blocks lane, lane + 32, ...)
-}
-
 // shared scratch of one block
 struct FusedShared {
     Pay part[16];                  // compute-warp partials
@@ -402,7 +367,33 @@ __device__ __forceinline__ Pay control_allreduce(const FusedParams &p, FusedShar
         }
         __syncwarp();
         FTRACE(att, 3);
-        x = gather_tagged<MODE, kGatherPerLane, false>(slots, G, seq);    // this LANE's share of this GPU's partials
+        // this LANE's share of this GPU's partials (blocks lane, lane + 32, ...: fixed order).  All arrivals have been seen, so
+        // the partials are almost always there: five unconditional weak loads in flight (a lane without a block at
+        // lane + 32 q reads slot 0 and ignores it), then the tag test; a stale tag -- the relaxed arrival overtook its
+        // data -- is re-read with strong loads, which the compiler may not hoist or elide.
+        unsigned long long g0[kGatherPerLane], g1[kGatherPerLane];
+#pragma unroll
+        for (int q = 0; q < kGatherPerLane; ++q) {
+            const int b = lane + 32 * q;
+            asm volatile("ld.global.cg.v2.u64 {%0, %1}, [%2];" : "=l"(g0[q]), "=l"(g1[q]) : "l"(slots + (size_t)(b < G ? b : 0) * 2) : "memory");
+        }
+        x = pay_identity<MODE>();
+#pragma unroll
+        for (int q = 0; q < kGatherPerLane; ++q) {
+            const int b = lane + 32 * q;
+            if (b < G) {
+                while (!pay_valid16(g0[q], g1[q], seq))
+                    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(g0[q]), "=l"(g1[q]) : "l"(slots + (size_t)b * 2) : "memory");
+                x = pay_combine<MODE>(x, pay_unpack16(g0[q], g1[q]));
+            }
+        }
+        for (int b = lane + 32 * kGatherPerLane; b < G; b += 32) {         // grids beyond 32 * kGatherPerLane blocks
+            unsigned long long a0, a1;
+            do {
+                asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a0), "=l"(a1) : "l"(slots + (size_t)b * 2) : "memory");
+            } while (!pay_valid16(a0, a1, seq));
+            x = pay_combine<MODE>(x, pay_unpack16(a0, a1));
+        }
     } else {
         x = (lane == 0) ? pay_unpack16(w0, w1) : pay_identity<MODE>();   // (the transported form, like everybody else's)
     }
