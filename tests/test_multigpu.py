@@ -51,6 +51,23 @@ def _worker(rank, world, port, q):
     assert s_full["fused_rhs"] and s_part["fused_rhs"]
     res["fused_dopri5"] = (float((part - full[:, lo:hi]).abs().max()), s_full["n_accepted"], s_full["n_rejected"],
                            s_part["n_accepted"], s_part["n_rejected"])
+    # one group, shard sizes that change from solve to solve (the persistent kernel's grid shrinks and grows): a partial left
+    # in the mailbox by an earlier, larger solve must never be taken for a fresh one (slots no longer written are poisoned)
+    tt = torch.arange(21, dtype=torch.float64) * 0.01
+    ref, worst = {}, 0.0
+    for cyc in range(6):
+        for n in (40000, 700):
+            yb = np.array([1., 1., 1.]) + 0.1 * np.random.default_rng(n).standard_normal((n, 3))
+            if n not in ref:
+                ref[n] = (tfd.odeint(fb, torch.tensor(yb, device=dev), tt, method="dopri5"), dict(tfd.last_stats))
+            l_, h_ = shard_bounds(n, world, rank)
+            part = tfd.odeint(fb, torch.tensor(yb[l_:h_], device=dev), tt, method="dopri5",
+                              options={"shared_step_group": group})
+            sp = dict(tfd.last_stats)
+            assert sp["fused_rhs"]
+            assert (sp["n_accepted"], sp["n_rejected"]) == (ref[n][1]["n_accepted"], ref[n][1]["n_rejected"]), (cyc, n)
+            worst = max(worst, float((part - ref[n][0][:, l_:h_]).abs().max()))
+    res["fused_regrid"] = (worst, 0, 0, 0, 0)
     # sharded odeint_adjoint: y / adj_y sharded like the batch, adj_t / adj_params replicated (all-reduced derivatives);
     # the returned parameter gradient is the gradient of the WHOLE batch's loss on every rank
     import torch.nn as nn

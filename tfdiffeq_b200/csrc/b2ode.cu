@@ -1,3 +1,5 @@
+#include <cstddef>
+#include <vector>
 // b2ode.cu -- sm_100a kernels + C ABI for the Runge-Kutta hot path of tfdiffeq's odeint().
 //
 // Reference citations are relative to the reference repository root (titu1994/tfdiffeq).
@@ -1153,6 +1155,15 @@ extern "C" int b2ode_mailbox_create(void **dev_ptr, unsigned char handle_out[64]
     void *p = nullptr;
     B2_CUDA(cudaMalloc(&p, sizeof(Mailbox)));
     B2_CUDA(cudaMemset(p, 0, sizeof(Mailbox)));
+    {   // the fused kernel's receive area starts out poisoned (see Mailbox::fused_part)
+        constexpr size_t n = sizeof(((Mailbox *)nullptr)->fused_part) / 16;
+        std::vector<unsigned long long> poison(2 * n);
+        for (size_t i = 0; i < n; ++i) {
+            poison[2 * i] = kPoisonW0;
+            poison[2 * i + 1] = kPoisonW1;
+        }
+        B2_CUDA(cudaMemcpy((char *)p + offsetof(Mailbox, fused_part), poison.data(), 16 * n, cudaMemcpyHostToDevice));
+    }
     B2_CUDA(cudaDeviceSynchronize());
     cudaIpcMemHandle_t h;
     B2_CUDA(cudaIpcGetMemHandle(&h, p));

@@ -216,11 +216,18 @@ struct Mailbox {
     MailSlot slot[2][B2ODE_MAXPEERS];
     unsigned long long local_seq;   // exchanges completed by the owning rank; persists across solves
     unsigned long long ll_seq;      // exchanges of the persistent fused kernel so far; persists across solves
-    unsigned long long pad[6];
+    unsigned fused_hw[2];           // per buffer parity: how many slots of THIS rank's region in its peers' mailboxes hold
+                                    // partials (= the grid of the last solve that wrote that buffer); slots beyond are poison
+    unsigned long long pad[5];
     // receive area of the persistent fused kernel (b2ode_fused.cu): every block of rank s stores its 16-byte tagged partial
     // of exchange `seq` into fused_part[seq & 1][s][block] of every other rank's mailbox (plain NVLink stores, no atomics)
+    // A slot that holds no partial holds the POISON pattern {tag 0, tag 1}, which no exchange number validates: mailboxes are
+    // created poisoned, and a solve with a smaller grid than its predecessor poisons the slots it no longer writes (before its
+    // first exchange on each buffer), so a later, larger solve can never mistake an old partial with a matching tag for a
+    // fresh one.
     unsigned long long fused_part[2][B2ODE_MAXPEERS][kMaxFusedBlocks][2];
 };
+constexpr unsigned long long kPoisonW0 = 0ull, kPoisonW1 = 1ull;
 
 struct CommParams {
     int rank;

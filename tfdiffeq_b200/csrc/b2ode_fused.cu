@@ -338,6 +338,7 @@ __device__ __forceinline__ void remote_gather(const FusedParams &p, FusedShared 
 // dedicated COMM warp (remote_gather) and handed to the control warp through shared memory; ranks combine in rank order.
 template <int MODE>
 __device__ __forceinline__ Pay control_allreduce(const FusedParams &p, FusedShared &sh, int ncw, unsigned epoch, unsigned seq0,
+                                                 unsigned long long hw2 = 0ull /* Mailbox::fused_hw[0..1] at kernel start */,
                                                  int att = -1) {
     const int lane = threadIdx.x & 31;
     Pay x = (lane < ncw) ? sh.part[lane] : pay_identity<MODE>();
@@ -350,6 +351,15 @@ __device__ __forceinline__ Pay control_allreduce(const FusedParams &p, FusedShar
     const unsigned seq = seq0 + epoch, par = seq & 1u;
     unsigned long long w0, w1;
     pay_pack16(x, seq, w0, w1);
+    if (nranks > 1 && epoch <= 2u && lane < nranks && lane != rank) {
+        // first use of this buffer in this solve: slots the previous writer of the buffer filled and this (smaller) grid does
+        // not are poisoned in every peer's mailbox, so that no later solve can take them for fresh partials
+        const int hw = (int)(par ? (unsigned)(hw2 >> 32) : (unsigned)hw2);
+        for (int b = G + (int)blockIdx.x; b < hw && b < kMaxFusedBlocks; b += G) {
+            unsigned long long *dst = &p.comm.box[lane]->fused_part[par][rank][b][0];
+            asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(dst), "l"(kPoisonW0), "l"(kPoisonW1) : "memory");
+        }
+    }
     if (nranks > 1 && lane < nranks && lane != rank) {                    // lane q: this block's partial -> rank q, over NVLink
         unsigned long long *dst = &p.comm.box[lane]->fused_part[par][rank][blockIdx.x][0];
         asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(dst), "l"(w0), "l"(w1) : "memory");
@@ -469,6 +479,7 @@ __global__ void __launch_bounds__(MAXT) k_fused_adaptive(const __grid_constant__
     const bool is_control = warp == ncw;
     // persistent sequence / arrival bases of the cross-GPU receive area (they survive across solves in the mailbox)
     const unsigned ll_base = grouped ? (unsigned)p.comm.box[p.comm.rank]->ll_seq : 0u;
+    const unsigned long long hw2 = (grouped && is_control) ? *(const volatile unsigned long long *)p.comm.box[p.comm.rank]->fused_hw : 0ull;
     if (RHS::kSmem > 1) {
         const int nw = (int)p.rhs[0] * 5 + 2;
         for (int q = threadIdx.x; q < nw && q < RHS::kSmem; q += nthreads) sw[q] = ((const T *)p.rhs_data)[q];
@@ -487,7 +498,7 @@ __global__ void __launch_bounds__(MAXT) k_fused_adaptive(const __grid_constant__
         } else {
             // misc.py:226-247 with the two reductions of _select_initial_step
             named_sync(kBarPartials, nloc);
-            Pay r = control_allreduce<1>(p, sh, ncw, ++epoch, ll_base);
+            Pay r = control_allreduce<1>(p, sh, ncw, ++epoch, ll_base, hw2);
             if (lane == 0) sh.tot = r;
             named_arrive(kBarDecision, nthreads);
             Partial tot;
@@ -497,7 +508,7 @@ __global__ void __launch_bounds__(MAXT) k_fused_adaptive(const __grid_constant__
             T d1max;
             const T h0 = init_h0<T>(p.c, &tot, 1, &d1max);
             named_sync(kBarPartials, nloc);
-            r = control_allreduce<1>(p, sh, ncw, ++epoch, ll_base);
+            r = control_allreduce<1>(p, sh, ncw, ++epoch, ll_base, hw2);
             if (lane == 0) sh.tot = r;
             named_arrive(kBarDecision, nthreads);
             tot.v[0] = r.a;
@@ -536,7 +547,7 @@ __global__ void __launch_bounds__(MAXT) k_fused_adaptive(const __grid_constant__
                 late_rows = 0;
             }
             FTRACE_DEP(att, 1, sh.part[0].flag);
-            const Pay r = control_allreduce<0>(p, sh, ncw, ++epoch, ll_base, att);
+            const Pay r = control_allreduce<0>(p, sh, ncw, ++epoch, ll_base, hw2, att);
             FTRACE_DEP(att, 4, __double_as_longlong(r.a));
             Partial tot;
             tot.v[0] = r.a;
@@ -643,7 +654,12 @@ __global__ void __launch_bounds__(MAXT) k_fused_adaptive(const __grid_constant__
             *p.st = z;
         }
         if (blockIdx.x == 0 && grouped) {
-            if (lane == 0) p.comm.box[p.comm.rank]->ll_seq = (unsigned long long)(ll_base + epoch);
+            if (lane == 0) {
+                Mailbox *mb = p.comm.box[p.comm.rank];
+                mb->ll_seq = (unsigned long long)(ll_base + epoch);
+                if (epoch >= 1u) mb->fused_hw[(ll_base + 1u) & 1u] = gridDim.x;     // what this solve left in each buffer
+                if (epoch >= 2u) mb->fused_hw[(ll_base + 2u) & 1u] = gridDim.x;
+            }
         }
         return;
     }
