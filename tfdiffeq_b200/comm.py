@@ -124,7 +124,9 @@ class SharedStepGroup(object):
     # Group-wide sums of per-rank integers are needed once per *shape*, not once per solve: the collective (and its
     # host synchronisation) runs the first time a rank presents a given local tuple and is cached afterwards.
     # Contract (SPMD): every rank of the group calls odeint with the same sequence of problems, so either all ranks hit
-    # their cache or all ranks miss it.
+    # their cache or all ranks miss it.  The key is the LOCAL shape: a sequence in which only some ranks' local shapes
+    # change (101 rows over two ranks = 51 + 50, then 102 = 51 + 51: rank 0 sees 51 twice) breaks the contract -- shard such
+    # batches so that every rank's size changes, or use a fresh group.
     def _sum_cached(self, tag, values):
         key = (tag,) + tuple(int(v) for v in values)
         hit = self._sums.get(key)
