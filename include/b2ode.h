@@ -174,7 +174,8 @@ int b2ode_poll_sync(b2ode_solver *s, b2ode_state *host_dst);
 
 /* Per-rank mailbox for the per-attempt exchange of {sum err^2, max|y0|, max|y1|, non-finite} per segment.
  * `mailboxes[r]` is the address, in THIS process, of rank r's mailbox (peer-mapped via CUDA IPC for r != rank;
- * each at least b2ode_mailbox_bytes() bytes, zero-initialised).  After this call b2ode_rk_finalize and the
+ * every mailbox comes from b2ode_mailbox_create, which initialises it: sequence numbers zero, the persistent kernel's
+ * receive area filled with a pattern no exchange validates).  After this call b2ode_rk_finalize and the
  * initial-step functions push their partials to every peer with st.global stores over NVLink and spin on the
  * arrival flags inside the same kernel (last block), so every rank takes the same accept / dt decision. */
 size_t b2ode_mailbox_bytes(void);
