@@ -235,8 +235,8 @@ constexpr int kBarPartials = 1, kBarDecision = 2, kBarRows = 3, kBarRowsReady = 
 // partials every peer wrote into this rank's mailbox over NVLink and leave, per source rank, each LANE's share (blocks
 // lane, lane + 32, ... summed in that order) in shared memory; the control warp folds the ranks in rank order and does the
 // one butterfly.  The comm warp starts polling the moment an exchange begins, so the peers' data is fetched while the
-// control warp is still in the intra-GPU phase: the NVLink hop (~2070 cycles) hides behind it.  Up to four source ranks
-// (20 weak loads per lane) are in flight together; partials whose tag is not `seq` yet are re-read, round by round.
+// control warp is still in the intra-GPU phase: the NVLink hop (~2070 cycles) hides behind it.  B2ODE_COMM_RG source ranks
+// (three: 15 weak loads per lane) are polled together, round by round, until every partial carries the tag of `seq`.
 template <int MODE>
 __device__ __forceinline__ void remote_gather(const FusedParams &p, FusedShared &sh, unsigned seq) {
     const int nranks = p.comm.nranks, lane = threadIdx.x & 31, rank = p.comm.rank;
@@ -477,7 +477,7 @@ __global__ void __launch_bounds__(MAXT) k_fused_adaptive(const __grid_constant__
     const int nloc = 32 * (ncw + 1);                     // compute warps + control warp (barriers the comm warp is not part of)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool is_control = warp == ncw;
-    // persistent sequence / arrival bases of the cross-GPU receive area (they survive across solves in the mailbox)
+    // persistent exchange number of the cross-GPU receive area (it survives across solves in the mailbox)
     const unsigned ll_base = grouped ? (unsigned)p.comm.box[p.comm.rank]->ll_seq : 0u;
     const unsigned long long hw2 = (grouped && is_control) ? *(const volatile unsigned long long *)p.comm.box[p.comm.rank]->fused_hw : 0ull;
     if (RHS::kSmem > 1) {
