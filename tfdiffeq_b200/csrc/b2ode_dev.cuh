@@ -1,6 +1,7 @@
 // b2ode_dev.cuh -- device helpers shared by b2ode.cu (generic func path) and b2ode_fused.cu (built-in RHS).
 #pragma once
 #include "b2ode.h"
+#include "b2ode_pay16.cuh"
 
 #include <cuda_runtime.h>
 #include <math.h>
@@ -227,7 +228,7 @@ struct Mailbox {
     // fresh one.
     unsigned long long fused_part[2][B2ODE_MAXPEERS][kMaxFusedBlocks][2];
 };
-constexpr unsigned long long kPoisonW0 = 0ull, kPoisonW1 = 1ull;
+constexpr unsigned long long kPoisonW0 = kPayPoisonW0, kPoisonW1 = kPayPoisonW1;   // b2ode_pay16.cuh
 
 struct CommParams {
     int rank;

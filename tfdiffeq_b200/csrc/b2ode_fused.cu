@@ -12,6 +12,7 @@
 
 #include "b2ode_dev.cuh"
 #include "b2ode_rhs.cuh"
+#include "b2ode_pay16.cuh"
 #include <stdlib.h>
 
 // ------------------------------------------------------------------------------------------------
@@ -89,12 +90,6 @@ __device__ __forceinline__ unsigned long long umax64(unsigned long long a, unsig
 
 // two 64-bit lanes of payload + one flag bit.  MODE 0: (a: sum >= 0, b: bit pattern of a non-negative double, combined
 // with an unsigned max -- NaN patterns sort above +inf, so it is a NaN-propagating max for free); MODE 1: (a, b: sums)
-struct Pay {
-    double a;
-    unsigned long long b;
-    unsigned flag;
-};
-
 template <int MODE>
 __device__ __forceinline__ Pay pay_identity() {
     Pay r;
@@ -195,28 +190,6 @@ __device__ __forceinline__ unsigned long long opaque_zero() {
 
 constexpr int kGatherPerLane = 5;        // 160 blocks gathered with every poll in flight (148 SMs x 1 block)
 
-// 16-byte message: {a | tag, b | tag}.  The 4-bit tag (exchange number mod 16) replaces the four lowest mantissa bits of
-// both words (2^-48 relative: below the rounding noise of the sums it carries) so that ONE 16-byte load both fetches and
-// validates a partial; the flag rides in the sign bit of `a` (a sum of squares; a NaN is made canonical first).  A buffer
-// is reused every second exchange, so a stale message always carries a different tag.
-__device__ __forceinline__ void pay_pack16(const Pay &x, unsigned seq, unsigned long long &w0, unsigned long long &w1) {
-    unsigned long long ab = (unsigned long long)__double_as_longlong(x.a);
-    if (x.a != x.a) ab = 0x7ff8000000000000ull;
-    ab = (ab & 0x7ffffffffffffff0ull) | ((unsigned long long)(x.flag & 1u) << 63) | (unsigned long long)(seq & 15u);
-    w0 = ab;
-    w1 = (x.b & ~0xfull) | (unsigned long long)(seq & 15u);
-}
-__device__ __forceinline__ bool pay_valid16(unsigned long long w0, unsigned long long w1, unsigned seq) {
-    return (unsigned)(w0 & 15ull) == (seq & 15u) && (unsigned)(w1 & 15ull) == (seq & 15u);
-}
-__device__ __forceinline__ Pay pay_unpack16(unsigned long long w0, unsigned long long w1) {
-    Pay r;
-    r.flag = (unsigned)(w0 >> 63);
-    r.a = __longlong_as_double((long long)(w0 & 0x7ffffffffffffff0ull));
-    r.b = w1 & ~0xfull;
-    return r;
-}
-
 // shared scratch of one block
 struct FusedShared {
     Pay part[16];                  // compute-warp partials
@@ -246,7 +219,7 @@ __device__ __forceinline__ void remote_gather(const FusedParams &p, FusedShared 
     constexpr int RG = B2ODE_COMM_RG;                       // source ranks per batch
     constexpr int NL = RG * kGatherPerLane;                 // loads in flight per lane
     const unsigned long long *base = &p.comm.box[rank]->fused_part[seq & 1u][0][0][0] + (size_t)lane * 2;
-    const unsigned tag = seq & 15u;
+    const unsigned tag = pay_tag(seq);
     for (int i0 = 0; i0 < nranks - 1; i0 += RG) {
         // The poll loop is INSTRUCTION bound (one warp, every load followed by its validation), so it is kept minimal: one
         // pointer per source rank, loads at immediate offsets and without predicates -- a slot past the source's grid, or
@@ -282,8 +255,7 @@ __device__ __forceinline__ void remote_gather(const FusedParams &p, FusedShared 
             got = 0u;
 #pragma unroll
             for (int k = 0; k < NL; ++k) {
-                const unsigned t = (((unsigned)g0[k] ^ tag) | ((unsigned)g1[k] ^ tag)) & 15u;
-                got |= (t == 0u) ? (1u << k) : 0u;
+                got |= (pay_mismatch(g0[k], g1[k], tag) == 0u) ? (1u << k) : 0u;
             }
         } while ((got & mine) != mine);
 #pragma unroll
