@@ -1148,7 +1148,8 @@ extern "C" int b2ode_timing_read(int family, double *total_ms, int *count) {
 }
 
 // ---- mailboxes of a shared-step group: the one place the library owns device memory ---------------------
-// (cudaMalloc'ed so that a CUDA IPC handle can be taken; 5 KB per rank)
+// (cudaMalloc'ed so that a CUDA IPC handle can be taken; 87 KB per rank: 7 KB of sequence-numbered slots for the generic kernels,
+// 80 KB of 16-byte partial slots for the persistent kernel)
 extern "C" int b2ode_mailbox_create(void **dev_ptr, unsigned char handle_out[64]) {
     if (!dev_ptr || !handle_out) return b2_fail(B2ODE_EINVAL, "null argument");
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle is 64 bytes");
